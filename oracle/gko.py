@@ -1,0 +1,376 @@
+"""ctypes binding of the CPU oracle (oracle/gko.c).  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product package (gokalman_b200/) must never import it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libgko.so")
+
+MAXN, MAXM = 64, 16
+VANILLA, PREDICTOR, INFORMATION, SQRT, HYBRID, SRIF = range(6)
+
+ERR_NAMES = {0: "ok", -1: "dims", -2: "singular_S", -3: "asymmetric", -4: "locked", -5: "singular_Phi",
+             -6: "singular_R", -7: "noise_range"}
+
+
+class Estimate(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("m", C.c_int),
+        ("state", C.c_double * MAXN),
+        ("meas", C.c_double * MAXM),
+        ("innov", C.c_double * MAXN),
+        ("innov_len", C.c_int),
+        ("covar", C.c_double * (MAXN * MAXN)),
+        ("pred_covar", C.c_double * (MAXN * MAXN)),
+        ("gain", C.c_double * (MAXN * MAXM)),
+        ("obs_dev", C.c_double * MAXM),
+        ("raw_vec", C.c_double * MAXN),
+        ("raw_mat", C.c_double * (MAXN * MAXN)),
+        ("raw_pred_mat", C.c_double * (MAXN * MAXN)),
+        ("covar_ok", C.c_int), ("pred_covar_ok", C.c_int),
+    ]
+
+    def _vec(self, field, k):
+        return np.frombuffer(getattr(self, field), dtype=np.float64, count=k).copy()
+
+    def State(self):
+        return self._vec("state", self.n)
+
+    def Measurement(self):
+        return self._vec("meas", self.m)
+
+    def Innovation(self):
+        return self._vec("innov", self.innov_len)
+
+    def ObservationDev(self):
+        return self._vec("obs_dev", self.m)
+
+    def Covariance(self):
+        return self._vec("covar", self.n * self.n).reshape(self.n, self.n)
+
+    def PredCovariance(self):
+        return self._vec("pred_covar", self.n * self.n).reshape(self.n, self.n)
+
+    def Gain(self):
+        return self._vec("gain", self.n * self.m).reshape(self.n, self.m)
+
+    def raw(self):
+        n = self.n
+        return (self._vec("raw_vec", n), self._vec("raw_mat", n * n).reshape(n, n),
+                self._vec("raw_pred_mat", n * n).reshape(n, n))
+
+
+class McConfig(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("m", C.c_int), ("c", C.c_int), ("kind", C.c_int),
+        ("F", C.c_void_p), ("G", C.c_void_p), ("H", C.c_void_p), ("Q", C.c_void_p), ("R", C.c_void_p),
+        ("x0_truth", C.c_void_p), ("x0_filter", C.c_void_p), ("P0", C.c_void_p),
+        ("trials", C.c_int), ("steps", C.c_int),
+        ("controls", C.c_void_p), ("w", C.c_void_p), ("v", C.c_void_p),
+        ("seed", C.c_uint64), ("trial_offset", C.c_int64),
+        ("with_nees", C.c_int), ("with_nis", C.c_int), ("threads", C.c_int),
+    ]
+
+
+def build(force=False):
+    """Compile oracle/_build/libgko.so with the committed Makefile (gcc only)."""
+    srcs = [os.path.join(_HERE, f) for f in ("gko.c", "gko_linalg.c", "gko.h", "gko_linalg.h", "Makefile")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
+        return _LIB_PATH
+    subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        build()
+    L = C.CDLL(_LIB_PATH)
+    dp, ip = C.c_void_p, C.c_int
+    L.gko_new_vanilla.restype = C.c_void_p
+    L.gko_new_vanilla.argtypes = [ip, ip, ip, dp, dp, dp, dp, dp, dp, dp, ip]
+    L.gko_new_information.restype = C.c_void_p
+    L.gko_new_information.argtypes = [ip, ip, ip, dp, dp, dp, dp, dp, dp, dp]
+    L.gko_new_information_from_state.restype = C.c_void_p
+    L.gko_new_information_from_state.argtypes = [ip, ip, ip, dp, dp, dp, dp, dp, dp, dp]
+    L.gko_new_sqrt.restype = C.c_void_p
+    L.gko_new_sqrt.argtypes = [ip, ip, ip, dp, dp, dp, dp, dp, dp, dp]
+    L.gko_new_hybrid.restype = C.c_void_p
+    L.gko_new_hybrid.argtypes = [ip, ip, ip, dp, dp, dp, dp]
+    L.gko_new_srif.restype = C.c_void_p
+    L.gko_new_srif.argtypes = [ip, ip, dp, dp, dp, ip]
+    L.gko_free.argtypes = [C.c_void_p]
+    L.gko_set_state_transition.argtypes = [C.c_void_p, dp]
+    L.gko_set_input_control.argtypes = [C.c_void_p, ip, dp]
+    L.gko_set_measurement_matrix.argtypes = [C.c_void_p, ip, dp]
+    L.gko_set_noise.argtypes = [C.c_void_p, dp, ip, dp]
+    L.gko_set_replay.argtypes = [C.c_void_p, ip, dp, dp, ip]
+    L.gko_reset.argtypes = [C.c_void_p]
+    L.gko_initial_estimate.argtypes = [C.c_void_p, C.POINTER(Estimate)]
+    L.gko_update.argtypes = [C.c_void_p, dp, dp, C.POINTER(Estimate)]
+    L.gko_prepare.argtypes = [C.c_void_p, dp, dp]
+    L.gko_prepare_pnt.argtypes = [C.c_void_p, dp]
+    L.gko_enable_ekf.argtypes = [C.c_void_p, ip]
+    L.gko_nl_predict.argtypes = [C.c_void_p, C.POINTER(Estimate)]
+    L.gko_nl_update.argtypes = [C.c_void_p, dp, dp, C.POINTER(Estimate)]
+    L.gko_srif_set_non_tri_r.argtypes = [C.c_void_p, ip]
+    L.gko_measurement_srif_update.argtypes = [ip, ip, dp, dp, dp, dp, dp, dp, dp]
+    L.gko_smooth_all.argtypes = [ip, ip, dp, dp, dp]
+    L.gko_mc_chisquare.argtypes = [C.POINTER(McConfig), dp, dp, dp, dp, dp, dp]
+    L.gko_philox4x32_10.argtypes = [dp, dp, dp]
+    L.gko_philox_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, ip, dp]
+    for name in ("gko_inverse",):
+        getattr(L, name).argtypes = [dp, dp, ip, dp]
+    L.gko_chol_lower.argtypes = [dp, dp, ip]
+    L.gko_qr_r.argtypes = [dp, dp, ip, ip]
+    L.gko_householder_transf.argtypes = [dp, ip, ip]
+    L.gko_as_sym.argtypes = [dp, ip]
+    _lib = L
+    return L
+
+
+def _a(x):
+    """contiguous float64 array (kept alive by the caller) or None"""
+    if x is None:
+        return None
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code):
+        super().__init__("oracle error %d (%s)" % (code, ERR_NAMES.get(code, "?")))
+        self.code = code
+
+
+class Filter:
+    """Stateful oracle filter mirroring the Go objects (LDKF and NLDKF)."""
+
+    def __init__(self, handle, kind, n, m):
+        if not handle:
+            raise OracleError(-1)
+        self.h, self.kind, self.n, self.m = handle, kind, n, m
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().gko_free(self.h)
+            self.h = None
+
+    # -- LDKF
+    def Update(self, y, u=None):
+        est = Estimate()
+        ya, ua = _a(y), _a(u)
+        rc = lib().gko_update(self.h, _p(ya), _p(ua), C.byref(est))
+        if rc != 0:
+            raise OracleError(rc)
+        return est
+
+    def SetStateTransition(self, F):
+        lib().gko_set_state_transition(self.h, _p(_a(F)))
+
+    def SetInputControl(self, G):
+        G = _a(G)
+        lib().gko_set_input_control(self.h, G.shape[1], _p(G))
+
+    def SetMeasurementMatrix(self, H):
+        H = np.atleast_2d(_a(H))
+        self.m = H.shape[0]
+        lib().gko_set_measurement_matrix(self.h, H.shape[0], _p(H))
+
+    def SetNoise(self, Q, R):
+        R = np.atleast_2d(_a(R))
+        lib().gko_set_noise(self.h, _p(_a(Q)), R.shape[0], _p(R))
+
+    def SetReplayNoise(self, w, v):
+        w, v = _a(w), _a(v)
+        steps = (w if w is not None else v).shape[0]
+        mv = v.shape[1] if v is not None else self.m
+        lib().gko_set_replay(self.h, steps, _p(w), _p(v), mv)
+
+    def Reset(self):
+        lib().gko_reset(self.h)
+
+    def InitialEstimate(self):
+        est = Estimate()
+        lib().gko_initial_estimate(self.h, C.byref(est))
+        return est
+
+    # -- NLDKF
+    def Prepare(self, Phi, Htilde):
+        lib().gko_prepare(self.h, _p(_a(Phi)), _p(_a(Htilde)))
+
+    def PreparePNT(self, Gamma):
+        lib().gko_prepare_pnt(self.h, _p(_a(Gamma)))
+
+    def EnableEKF(self):
+        lib().gko_enable_ekf(self.h, 1)
+
+    def DisableEKF(self):
+        lib().gko_enable_ekf(self.h, 0)
+
+    def Predict(self):
+        est = Estimate()
+        rc = lib().gko_nl_predict(self.h, C.byref(est))
+        if rc != 0:
+            raise OracleError(rc)
+        return est
+
+    def UpdateNL(self, real_obs, computed_obs):
+        est = Estimate()
+        rc = lib().gko_nl_update(self.h, _p(_a(real_obs)), _p(_a(computed_obs)), C.byref(est))
+        if rc != 0:
+            raise OracleError(rc)
+        return est
+
+
+def _dims(F, G, H):
+    F, H = _a(F), np.atleast_2d(_a(H))
+    n, m = F.shape[0], H.shape[0]
+    G = None if G is None else _a(G).reshape(n, -1)
+    c = 0 if G is None else G.shape[1]
+    return F, G, H, n, m, c
+
+
+def NewVanilla(x0, P0, F, G, H, Q, R, predictor=False):
+    F, G, H, n, m, c = _dims(F, G, H)
+    h = lib().gko_new_vanilla(n, m, c, _p(_a(x0)), _p(_a(P0)), _p(F), _p(G), _p(H), _p(_a(Q)),
+                              _p(np.atleast_2d(_a(R))), int(predictor))
+    return Filter(h, PREDICTOR if predictor else VANILLA, n, m)
+
+
+def NewInformation(i0, I0, F, G, H, Q, R):
+    F, G, H, n, m, c = _dims(F, G, H)
+    h = lib().gko_new_information(n, m, c, _p(_a(i0)), _p(_a(I0)), _p(F), _p(G), _p(H), _p(_a(Q)),
+                                  _p(np.atleast_2d(_a(R))))
+    return Filter(h, INFORMATION, n, m)
+
+
+def NewInformationFromState(x0, P0, F, G, H, Q, R):
+    F, G, H, n, m, c = _dims(F, G, H)
+    h = lib().gko_new_information_from_state(n, m, c, _p(_a(x0)), _p(_a(P0)), _p(F), _p(G), _p(H),
+                                             _p(_a(Q)), _p(np.atleast_2d(_a(R))))
+    return Filter(h, INFORMATION, n, m)
+
+
+def NewSquareRoot(x0, P0, F, G, H, Q, R):
+    F, G, H, n, m, c = _dims(F, G, H)
+    h = lib().gko_new_sqrt(n, m, c, _p(_a(x0)), _p(_a(P0)), _p(F), _p(G), _p(H), _p(_a(Q)),
+                           _p(np.atleast_2d(_a(R))))
+    return Filter(h, SQRT, n, m)
+
+
+def NewHybridKF(x0, P0, Q, R, meas_size):
+    x0 = _a(x0)
+    n = x0.shape[0]
+    Q = None if Q is None else np.atleast_2d(_a(Q))
+    q = 0 if Q is None else Q.shape[0]
+    h = lib().gko_new_hybrid(n, meas_size, q, _p(x0), _p(_a(P0)), _p(Q), _p(np.atleast_2d(_a(R))))
+    return Filter(h, HYBRID, n, meas_size)
+
+
+def NewSRIF(x0, P0, meas_size, non_tri_r, R):
+    x0 = _a(x0)
+    n = x0.shape[0]
+    h = lib().gko_new_srif(n, meas_size, _p(x0), _p(_a(P0)), _p(np.atleast_2d(_a(R))), int(non_tri_r))
+    return Filter(h, SRIF, n, meas_size)
+
+
+def measurement_srif_update(R, H, b, y):
+    R, H, b, y = _a(R), np.atleast_2d(_a(H)), _a(b), _a(y)
+    n, m = R.shape[0], H.shape[0]
+    Rk, bk, ek = np.zeros((n, n)), np.zeros(n), np.zeros(m)
+    lib().gko_measurement_srif_update(n, m, _p(R), _p(H), _p(b), _p(y), _p(Rk), _p(bk), _p(ek))
+    return Rk, bk, ek
+
+
+def householder_transf(A, n, m):
+    A = _a(A).copy()
+    lib().gko_householder_transf(_p(A), n, m)
+    return A
+
+
+def inverse(A):
+    A = _a(A)
+    n = A.shape[0]
+    out = np.zeros((n, n))
+    cond = C.c_double(0.0)
+    rc = lib().gko_inverse(_p(out), _p(A), n, C.cast(C.byref(cond), C.c_void_p))
+    return out, rc, cond.value
+
+
+def chol_lower(A):
+    A = _a(A)
+    n = A.shape[0]
+    L = np.zeros((n, n))
+    ok = lib().gko_chol_lower(_p(L), _p(A), n)
+    return L, bool(ok)
+
+
+def qr_r(A):
+    A = _a(A)
+    R = np.zeros_like(A)
+    lib().gko_qr_r(_p(R), _p(A), A.shape[0], A.shape[1])
+    return R
+
+
+def smooth_all(Phi, x, P):
+    Phi, x, P = _a(Phi), _a(x).copy(), _a(P).copy()
+    steps, n = x.shape
+    rc = lib().gko_smooth_all(n, steps, _p(Phi), _p(x), _p(P))
+    if rc != 0:
+        raise OracleError(rc)
+    return x, P
+
+
+def philox4x32_10(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    lib().gko_philox4x32_10(c.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p),
+                            o.ctypes.data_as(C.c_void_p))
+    return o
+
+
+def philox_normals(seed, trial, step, count):
+    z = np.zeros(count)
+    lib().gko_philox_normals(seed, trial, step, count, _p(z))
+    return z
+
+
+def mc_chisquare(kind, F, G, H, Q, R, x0_truth, x0_filter, P0, trials, steps, controls=None, w=None, v=None,
+                 seed=0, trial_offset=0, with_nees=True, with_nis=True, threads=1, want_stats=False,
+                 want_truth=False):
+    """montecarlo.go NewMonteCarloRuns + chisquare.go NewChiSquare. Returns dict with NIS/NEES means."""
+    F, G, H, n, m, c = _dims(F, G, H)
+    keep = [F, G, H, _a(Q), np.atleast_2d(_a(R)), _a(x0_truth), _a(x0_filter), _a(P0), _a(controls), _a(w), _a(v)]
+    cfg = McConfig()
+    cfg.n, cfg.m, cfg.c, cfg.kind = n, m, c, kind
+    (cfg.F, cfg.G, cfg.H, cfg.Q, cfg.R, cfg.x0_truth, cfg.x0_filter, cfg.P0, cfg.controls, cfg.w,
+     cfg.v) = [None if a is None else a.ctypes.data for a in keep]
+    cfg.trials, cfg.steps = trials, steps
+    cfg.seed, cfg.trial_offset = seed, trial_offset
+    cfg.with_nees, cfg.with_nis, cfg.threads = int(with_nees), int(with_nis), threads
+    nis, nees = np.zeros(steps), np.zeros(steps)
+    mean = np.zeros((steps, n)) if want_stats else None
+    std = np.zeros((steps, n)) if want_stats else None
+    tx = np.zeros((trials, steps, n)) if want_truth else None
+    ty = np.zeros((trials, steps, m)) if want_truth else None
+    rc = lib().gko_mc_chisquare(C.byref(cfg), _p(nis), _p(nees), _p(mean), _p(std), _p(tx), _p(ty))
+    if rc != 0:
+        raise OracleError(rc)
+    return {"NIS": nis, "NEES": nees, "mean": mean, "std": std, "truth_x": tx, "truth_y": ty}
