@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- filter-updates/sec of the batched Kalman hot path on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mc_jerk3|hybrid6] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  mc_jerk3 (default, BASELINE configs[1]): 10^6 Monte Carlo trials x 1000 filter steps per GPU of the
+      3-state jerk model -- Philox noise -> truth -> vanilla KF -> NEES/NIS reduction, fused in one
+      kernel; multi-GPU shards trials (weak scaling) and all-reduces the 2 x 1000 per-step sums (NCCL).
+  hybrid6 (BASELINE configs[3]): 10^5 six-state hybrid CKF->EKF filters x S epochs with per-filter,
+      per-epoch Phi / Htilde / observations streamed from HBM.
+Prints ONE JSON line (rank 0).  `value` is timed with everything resident in HBM; `e2e` goes through
+the public host-buffer API (host<->device copies inside the timed region).  --impl reference times
+the CPU oracle (the reference itself is Go + un-vendored gonum and cannot be built in this image).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+import fixtures as fx  # noqa: E402
+
+FLOPS_PER_UNIT = {"mc_jerk3": 537.0, "hybrid6": 2526.0}  # BASELINE.md section 3 (algorithmic, dense)
+BYTES_PER_UNIT = {"mc_jerk3": 0.0, "hybrid6": 416.0}
+SEED = 0x5EED
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples at or above half the max clock (idle samples precede the first launch)
+        load = [s for s in sm if s >= 0.5 * max(mx)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def fp64_peak():
+    """DFMA TFLOP/s: measured live with tools/peak_fp64 when built, else the committed measurement."""
+    exe = os.path.join(ROOT, "tools", "peak_fp64")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            return d["dfma_tflops_sustained"], "measured live: tools/peak_fp64 DFMA sustained (MEASURED_PEAKS.json has no FP64 entry)"
+        except Exception:
+            pass
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_peak_fp64.json")))
+        return d["dfma_tflops_sustained"], "profiles/r01_peak_fp64.json (DFMA sustained, measured on this pool's B200)"
+    except Exception:
+        return 34.2, "fallback constant (profiles/r01_peak_fp64.json)"
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def mc_model():
+    f = fx.jerk3()  # helper_test.go:17-22 + montecarlo_test.go:12-19
+    return f
+
+
+def mc_config_struct(L, f, trials, trial_offset, steps, device):
+    """gkb_mc_config for the device-resident leg (PHILOX noise, zero controls like montecarlo.go:98-104)."""
+    cfg = L.McConfig()
+    keep = {k: np.ascontiguousarray(np.asarray(f[k], dtype=np.float64)) for k in ("F", "G", "H", "Q", "R", "x0", "P0")}
+    keep["u"] = np.zeros((steps, 1))
+    cfg.kind, cfg.n, cfg.m, cfg.c = L.VANILLA, 3, 1, 1
+    cfg.F, cfg.G, cfg.H, cfg.Q, cfg.R = (keep[k].ctypes.data for k in ("F", "G", "H", "Q", "R"))
+    cfg.x0_truth = cfg.x0_filter = keep["x0"].ctypes.data
+    cfg.P0 = keep["P0"].ctypes.data
+    cfg.trials, cfg.trial_offset, cfg.steps = trials, trial_offset, steps
+    cfg.controls = keep["u"].ctypes.data
+    cfg.noise_mode, cfg.seed = L.NOISE_PHILOX, SEED
+    cfg.with_nees = cfg.with_nis = 1
+    cfg.device = device
+    return cfg, keep
+
+
+def run_ours_mc(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import gokalman_b200 as gk
+    from gokalman_b200 import _lib as L
+
+    lib = gk.load()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    trials, steps = args.trials, args.filter_steps
+    f = mc_model()
+    cfg, keep = mc_config_struct(L, f, trials, rank * trials, steps, local)
+    sums = torch.zeros(2, steps, dtype=torch.float64, device="cuda")
+    out = L.McOutputs()
+    out.mem, out.sums_only = L.DEVICE, 1
+    out.nis, out.nees = sums[0].data_ptr(), sums[1].data_ptr()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step_device():
+        L.check(lib.gkb_mc_chisquare(C.byref(cfg), C.byref(out)))
+        if world > 1:
+            dist.all_reduce(sums)  # the one collective of the path: 2 x steps doubles (NCCL)
+        return sums / float(trials * world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_tf, peak_src = fp64_peak() if rank == 0 else (None, None)
+    for _ in range(args.warmup):
+        flush.zero_()
+        means = step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the per-step event bracket)
+        ev[i][0].record()
+        means = step_device()
+        ev[i][1].record()
+        kern_ms.append(lib.gkb_last_main_kernel_ms())  # CUDA events on the launch stream, inside the lib
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)  # max over ranks
+    total_ms = float(total_ms.item())
+    units = float(trials) * steps * world * args.steps
+    value = units / (total_ms * 1e-3)
+    nis_mean, nees_mean = float(means[0].mean().item()), float(means[1].mean().item())
+
+    # ---- e2e: the public API with HOST buffers (model + controls in, NIS/NEES means out), every step
+    controls = [np.zeros(1)]
+    def step_e2e():
+        runs = gk.NewMonteCarloRuns(trials, steps, 1, controls, mckf, trial_offset=rank * trials)
+        nis, nees = gk.NewChiSquare(chikf, runs, controls, True, True)
+        if world > 1:
+            t = torch.from_numpy(np.stack([nis, nees]) * trials).cuda()
+            dist.all_reduce(t)
+            nis, nees = (t / float(trials * world)).cpu().numpy()
+        return nis, nees
+    mckf, _ = gk.NewPurePredictorVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewAWGN(f["Q"], f["R"], seed=SEED),
+                                         device=local)
+    chikf, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewNoiseless(f["Q"], f["R"]), device=local)
+    step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_e2e = max(1, min(args.steps, 5))
+    for _ in range(n_e2e):
+        nis_h, nees_h = step_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = float(trials) * steps * world * n_e2e / (float(e2e_ms.item()) * 1e-3)
+    h2d = 8 * (9 + 3 + 3 + 9 + 1 + 3 + 3 + 9 + steps * 1)  # F,G,H,Q,R,x0,x0,P0 + controls
+    d2h = 8 * 2 * steps + 4 * trials                          # NIS, NEES means + per-trial status words
+    assert np.allclose(nis_h.mean(), nis_mean, rtol=1e-9), (nis_h.mean(), nis_mean)
+
+    if rank != 0:
+        return None
+    main_ms = statistics.mean(kern_ms)
+    achieved_tf = FLOPS_PER_UNIT["mc_jerk3"] * float(trials) * steps / (main_ms * 1e-3) / 1e12
+    line = {
+        "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "mc_jerk3: jerkcar 3-state vanilla KF Monte Carlo + chi-square (BASELINE configs[1])",
+                   "trials_per_gpu": trials, "filter_steps": steps, "n": 3, "m": 1, "c": 1, "noise": "philox4x32-10 in-kernel",
+                   "sharding": "trials split by rank, one NCCL all-reduce of 2 x %d doubles per step" % steps,
+                   "l2": "flushed between timed iterations (256 MiB memset)", "nis_mean": nis_mean, "nees_mean": nees_mean},
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "traffic": None,
+                     "kernel": "mc_chisquare_kernel<3,1,VanillaTested>", "kernel_ms": main_ms,
+                     "flops_per_unit": FLOPS_PER_UNIT["mc_jerk3"], "peak_source": peak_src,
+                     "note": "537 algorithmic flop per (trial, step) per BASELINE.md s3; RNG/Box-Muller work not counted"},
+        "e2e": {"value": e2e_value, "unit": "filter-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "NewMonteCarloRuns + NewChiSquare (host buffers)"},
+        "gpu_launches": 3 * args.steps,  # setup + fused MC kernel + finish per step (ours; torch memset/NCCL not counted)
+        "clocks": clocks,
+        "wall_s": wall,
+    }
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ------------------------------------------------------------------------------------------------
+def oracle_mc_rate(trials, steps, threads):
+    from oracle import gko
+    gko.build()
+    f = mc_model()
+    t0 = time.perf_counter()
+    r = gko.mc_chisquare(gko.VANILLA, f["F"], f["G"], f["H"], f["Q"], f["R"], f["x0"], f["x0"], f["P0"], trials, steps,
+                         controls=None, seed=SEED, threads=threads)
+    dt = time.perf_counter() - t0
+    return trials * steps / dt, dt, float(r["NIS"].mean())
+
+
+def cpu_baseline(target_s=12.0):
+    cores = os.cpu_count() or 1
+    steps = 1000
+    rate, _, _ = oracle_mc_rate(cores * 4, steps, cores)  # calibration
+    trials = max(cores, int(rate * target_s / steps / cores) * cores)
+    rate, dt, _ = oracle_mc_rate(trials, steps, cores)
+    return {"value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port",
+            "sample": "%d trials x %d steps of mc_jerk3 (%.1f s), C oracle restatement with OpenMP over trials; "
+                      "the Go/gonum reference cannot be built here (no Go toolchain)" % (trials, steps, dt)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    steps = args.filter_steps
+    rate, _, _ = oracle_mc_rate(cores * 4, steps, cores)
+    trials = max(cores, int(rate * 6.0 / steps / cores) * cores)  # ~6 s of CPU per step
+    times = []
+    for i in range(args.warmup + args.steps):
+        r, dt, _ = oracle_mc_rate(trials, steps, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = trials * steps * args.steps / total
+    sample = "%d trials x %d steps per step (bounded sample of the 10^6-trial workload), OpenMP x %d" % (trials, steps, cores)
+    return {
+        "impl": "reference", "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "mc_jerk3: jerkcar 3-state vanilla KF Monte Carlo + chi-square (BASELINE configs[1])",
+                   "filter_steps": steps, "n": 3, "m": 1, "c": 1},
+        "cpu_baseline": {"value": value, "unit": "filter-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "filter-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle port (C, OpenMP); the reference is Go + un-vendored gonum and cannot be built in this image",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mc_jerk3", choices=["mc_jerk3", "hybrid6"])
+    ap.add_argument("--trials", type=int, default=1000000, help="Monte Carlo trials (filters) per GPU")
+    ap.add_argument("--filter-steps", type=int, default=1000, help="filter steps per trial")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    if args.workload == "hybrid6":
+        from bench_hybrid import run_ours_hybrid
+        line = run_ours_hybrid(args, rank, world, local)
+    else:
+        line = run_ours_mc(args, rank, world, local)
+    if line is not None:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        elif "cpu_baseline" not in line:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

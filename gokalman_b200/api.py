@@ -1,0 +1,795 @@
+"""Host-side mirror of the gokalman Go API over the CUDA engine's C-ABI.
+
+Same names and argument meaning as the reference (the Go toolchain is absent here, so this Python
+layer is the tested caller; go/gokalman_b200.go carries the cgo shim as source):
+
+    NewVanilla / NewPurePredictorVanilla    vanilla.go:21-62
+    NewInformation / NewInformationFromState information.go:20-81
+    NewSquareRoot                            squareroot.go:21-50
+    NewHybridKF                              hybrid.go:23-34
+    NewSRIF                                  srif.go:14-49
+    NewNoiseless / BatchNoise / NewAWGN      noise.go:23-159
+    NewMonteCarloRuns, NewChiSquare          montecarlo.go:92-119, chisquare.go:16-95
+
+Each constructor takes two extra keyword arguments, `n_filters` and `device`: a filter object is a
+batch of `n_filters` independent filters advanced in lockstep on the GPU (1 = the drop-in case).
+`Update` keeps the reference's one-step signature; `UpdateBatch` / `RunBatch` are the new batched
+entry points that run many steps inside one kernel launch.  Go's `(value, error)` returns become
+exceptions (`GkbError`); the reference's panics become exceptions too.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import GkbError  # noqa: F401  (re-exported)
+
+
+def _arr(x, shape=None):
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _mat(x):
+    a = _arr(x)
+    if a.ndim == 0:
+        a = a.reshape(1, 1)
+    elif a.ndim == 1:
+        a = a.reshape(1, -1)
+    return a
+
+
+# --------------------------------------------------------------------------------------------------
+# Noise (noise.go)
+# --------------------------------------------------------------------------------------------------
+class Noiseless:
+    """noise.go:23-64: zero samples, carries Q and R."""
+
+    def __init__(self, Q, R):
+        if Q is None or R is None:
+            raise ValueError("Q and R must be specified")  # noise.go:30-32 panics
+        self.Q, self.R = _mat(Q), _mat(R)
+
+    def Process(self, k):
+        return np.zeros(self.Q.shape[0])
+
+    def Measurement(self, k):
+        return np.zeros(self.R.shape[0])
+
+    def ProcessMatrix(self):
+        return self.Q
+
+    def MeasurementMatrix(self):
+        return self.R
+
+    def Reset(self):
+        pass
+
+    def __str__(self):
+        return "Noiseless{\nQ=%s\nR=%s}\n" % (self.Q, self.R)
+
+
+def NewNoiseless(Q, R):
+    return Noiseless(Q, R)
+
+
+class ReplayNoise(Noiseless):
+    """Pre-baked samples indexed by step like noise.go BatchNoise (73-86), but carrying Q and R so
+    that it can drive a real filter.  process: [steps, n] or [steps, n, n_filters]."""
+
+    def __init__(self, Q, R, process, measurement):
+        super().__init__(Q, R)
+        self.process = None if process is None else _arr(process)
+        self.measurement = None if measurement is None else _arr(measurement)
+
+    def _get(self, arr, k, what):
+        if arr is None:
+            return None
+        if k >= arr.shape[0]:
+            raise IndexError("no %s noise defined at step k=%d" % (what, k))  # noise.go:74-76 panics
+        return arr[k]
+
+    def Process(self, k):
+        v = self._get(self.process, k, "process")
+        return np.zeros(self.Q.shape[0]) if v is None else v
+
+    def Measurement(self, k):
+        v = self._get(self.measurement, k, "measurement")
+        return np.zeros(self.R.shape[0]) if v is None else v
+
+
+class BatchNoise(ReplayNoise):
+    """noise.go:67-106: stored vectors, Q = R = zero matrices."""
+
+    def __init__(self, process, measurement):
+        process, measurement = _arr(process), _arr(measurement)
+        super().__init__(np.zeros((process.shape[1],) * 2), np.zeros((measurement.shape[1],) * 2), process, measurement)
+
+    def __str__(self):
+        return "BatchNoise"
+
+
+class AWGN:
+    """noise.go:109-159.  The reference seeds math/rand from the clock (irreproducible by design);
+    here the samples come from the engine's counter-based Philox4x32-10 stream keyed by
+    (seed, trial, step), generated inside the Monte Carlo kernel.  It is the noise of the pure
+    predictor that NewMonteCarloRuns drives."""
+
+    def __init__(self, Q, R, seed=None):
+        self.Q, self.R = _mat(Q), _mat(R)
+        for name, M in (("process", self.Q), ("measurement", self.R)):
+            try:
+                np.linalg.cholesky(M)
+            except np.linalg.LinAlgError:
+                raise ValueError("%s noise invalid" % name)  # noise.go:149-156 panics
+        self._seed0 = seed
+        self.Reset()
+
+    def Reset(self):
+        # a new stream per Reset(), as the reference re-seeds (noise.go:145-159)
+        if self._seed0 is None:
+            self.seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
+        else:
+            self.seed = int(self._seed0)
+
+    def ProcessMatrix(self):
+        return self.Q
+
+    def MeasurementMatrix(self):
+        return self.R
+
+    def Process(self, k):
+        raise NotImplementedError("AWGN samples are generated on the device by the Monte Carlo kernel")
+
+    Measurement = Process
+
+    def __str__(self):
+        return "AWGN{\nQ=%s\nR=%s}\n" % (self.Q, self.R)
+
+
+def NewAWGN(Q, R, seed=None):
+    return AWGN(Q, R, seed)
+
+
+# --------------------------------------------------------------------------------------------------
+# Estimate (kalman.go:64-72)
+# --------------------------------------------------------------------------------------------------
+class Estimate:
+    """One Estimate, or a batch: arrays are [component] for a single filter / single step and gain
+    leading `steps` and trailing `n_filters` axes in the batched calls."""
+
+    def __init__(self, n, m, fields, status=None, squeeze=True):
+        self._n, self._m, self._f, self._squeeze = n, m, fields, squeeze
+        self.status = status
+
+    def _get(self, name, shape):
+        a = self._f.get(name)
+        if a is None:
+            return None
+        steps, nf = a.shape[0], a.shape[-1]
+        a = a.reshape((steps,) + shape + (nf,))
+        if self._squeeze:
+            if nf == 1:
+                a = a[..., 0]
+            if steps == 1:
+                a = a[0]
+        return a
+
+    def State(self):
+        return self._get("state", (self._n,))
+
+    def Measurement(self):
+        return self._get("meas", (self._m,))
+
+    def Innovation(self):
+        a = self._f.get("innov")
+        if a is None:
+            return None
+        return self._get("innov", (a.shape[1],))
+
+    def ObservationDev(self):
+        return self._get("obs_dev", (self._m,))
+
+    def Covariance(self):
+        return self._get("covar", (self._n, self._n))
+
+    def PredCovariance(self):
+        return self._get("pred_covar", (self._n, self._n))
+
+    def Gain(self):
+        return self._get("gain", (self._n, self._m))
+
+    def IsWithinNσ(self, N):
+        """vanilla.go:231-239: |x_i| <= N sqrt(P_ii) for every component (single estimate only)."""
+        x, P = np.asarray(self.State()), np.asarray(self.Covariance())
+        if x.ndim != 1:
+            raise ValueError("IsWithinNσ is defined for a single estimate")
+        for i in range(x.shape[0]):
+            b = N * np.sqrt(P[i, i])
+            if x[i] > b or x[i] < -b:
+                return False
+        return True
+
+    IsWithinNsigma = IsWithinNσ
+
+    def IsWithin2σ(self):
+        return self.IsWithinNσ(2)
+
+    IsWithin2sigma = IsWithin2σ
+
+    def __str__(self):
+        return "{\ns=%s\ny=%s\nP=%s\nK=%s\nP-=%s\ni=%s\n}" % (self.State(), self.Measurement(), self.Covariance(),
+                                                           self.Gain(), self.PredCovariance(), self.Innovation())
+
+
+_OUT_FIELDS = ("state", "meas", "innov", "covar", "pred_covar", "gain", "obs_dev")
+
+
+class _Filter:
+    """Common handle plumbing."""
+
+    def __init__(self):
+        self._h = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().gkb_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def n_filters(self):
+        return self._nf
+
+    def _alloc_out(self, steps, every_step, want, innov_len):
+        n, m, nf = self._n, self._m, self._nf
+        rows = steps if every_step else 1
+        sizes = {"state": n, "meas": m, "innov": innov_len, "covar": n * n, "pred_covar": n * n, "gain": n * m,
+                 "obs_dev": m}
+        fields = {k: np.zeros((rows, sizes[k], nf)) for k in _OUT_FIELDS if k in want and sizes[k] > 0}
+        status = np.zeros(nf, dtype=np.int32)
+        out = _lib.Outputs()
+        out.mem, out.every_step = _lib.HOST, int(every_step)
+        for k, a in fields.items():
+            setattr(out, k, a.ctypes.data)
+        out.status = status.ctypes.data
+        return out, fields, status
+
+    def _raise_status(self, status):
+        bad = status[status != 0]
+        if bad.size and self._nf == 1:
+            raise GkbError(int(bad[0]), "filter 0 failed during Update")
+
+    def GetState(self):
+        """raw (vector [n, N], matrix [n, n, N]) of the filters: x,P / i,I / x,S / b,R by kind"""
+        vec, mat = np.zeros((self._n, self._nf)), np.zeros((self._n * self._n, self._nf))
+        _lib.check(_lib.load().gkb_get_state(self._h, _ptr(vec), _ptr(mat)))
+        return vec, mat.reshape(self._n, self._n, self._nf)
+
+
+# --------------------------------------------------------------------------------------------------
+# LDKF: Vanilla / Information / SquareRoot (kalman.go:35-48)
+# --------------------------------------------------------------------------------------------------
+class _LDKF(_Filter):
+    _kind = None
+    _want = ("state", "meas", "innov", "covar", "pred_covar", "gain")
+
+    def _create(self, kind, x0, P0, F, G, H, noise, n_filters, device, from_state=False):
+        lib = _lib.load()
+        F, H = _arr(F), _mat(H)
+        n, m = F.shape[0], H.shape[0]
+        x0 = _arr(x0)
+        P0 = _arr(P0)
+        # checkMatDims (vanilla.go:23-31): x0 rows vs Covar0 cols, F rows vs Covar0 cols, H cols vs x0 rows
+        if x0.shape[0] != P0.shape[1]:
+            raise GkbError(-1, "x0(%dx...) Covar0(...x%d)" % (x0.shape[0], P0.shape[1]))
+        if F.shape[0] != P0.shape[1]:
+            raise GkbError(-1, "F(%dx...) Covar0(...x%d)" % (F.shape[0], P0.shape[1]))
+        if H.shape[1] != x0.shape[0]:
+            raise GkbError(-1, "H(...x%d) x0(%dx...)" % (H.shape[1], x0.shape[0]))
+        G = None if G is None else _arr(G).reshape(n, -1)
+        c = 0 if G is None else G.shape[1]
+        Q, R = _mat(noise.ProcessMatrix()), _mat(noise.MeasurementMatrix())
+        per_filter = 1 if x0.ndim == 2 else 0
+        h = C.c_void_p()
+        if from_state:
+            _lib.check(lib.gkb_create_information_from_state(n, m, c, n_filters, device, _ptr(x0), _ptr(P0), _ptr(F),
+                                                             _ptr(G), _ptr(H), _ptr(Q), _ptr(R), C.byref(h)))
+        else:
+            _lib.check(lib.gkb_create_lti(kind, n, m, c, n_filters, device, _ptr(x0), per_filter, _ptr(P0), _ptr(F),
+                                          _ptr(G), _ptr(H), _ptr(Q), _ptr(R), C.byref(h)))
+        self._h, self._n, self._m, self._c, self._nf, self._device = h, n, m, c, n_filters, device
+        self.F, self.G, self.H = F, G, H
+        self.needCtrl = not (G is None or not np.any(G))
+        self.Noise = None
+        self._apply_noise(noise, set_matrices=False)
+        self._x0, self._P0, self._from_state = x0, P0, from_state
+
+    # -- getters / setters (vanilla.go:80-118)
+    def GetStateTransition(self):
+        return self.F
+
+    def GetInputControl(self):
+        return self.G
+
+    def GetMeasurementMatrix(self):
+        return self.H
+
+    def GetNoise(self):
+        return self.Noise
+
+    def SetStateTransition(self, F):
+        self.F = _arr(F)
+        _lib.check(_lib.load().gkb_set_state_transition(self._h, _ptr(self.F)))
+
+    def SetInputControl(self, G):
+        self.G = _arr(G).reshape(self._n, -1)
+        self._c = self.G.shape[1]
+        _lib.check(_lib.load().gkb_set_input_control(self._h, self._c, _ptr(self.G)))
+
+    def SetMeasurementMatrix(self, H):
+        self.H = _mat(H)
+        self._m = self.H.shape[0]
+        _lib.check(_lib.load().gkb_set_measurement_matrix(self._h, self._m, _ptr(self.H)))
+
+    def _apply_noise(self, noise, set_matrices=True):
+        lib = _lib.load()
+        if isinstance(noise, AWGN):
+            if self._kind != _lib.PREDICTOR:
+                raise NotImplementedError("AWGN drives the Monte Carlo pure predictor; give a tested filter "
+                                          "Noiseless(Q, R) or ReplayNoise (examples/robot/main.go:32-33)")
+        if set_matrices:
+            Q, R = _mat(noise.ProcessMatrix()), _mat(noise.MeasurementMatrix())
+            _lib.check(lib.gkb_set_noise(self._h, _ptr(Q), R.shape[0], _ptr(R)))
+        if isinstance(noise, ReplayNoise):
+            w, v = noise.process, noise.measurement
+            steps = (w if w is not None else v).shape[0]
+
+            def soa(a, comps):
+                if a is None:
+                    return None
+                if a.ndim == 2:  # [steps, comps] shared by all filters -> broadcast
+                    a = np.repeat(a[:, :, None], self._nf, axis=2)
+                return np.ascontiguousarray(a.reshape(steps, comps, self._nf))
+            w, v = soa(w, self._n), soa(v, self._m)
+            _lib.check(lib.gkb_set_replay_noise(self._h, steps, _ptr(w), _ptr(v), _lib.HOST))
+        self.Noise = noise
+
+    def SetNoise(self, n):
+        self._apply_noise(n)
+
+    def Reset(self):
+        _lib.check(_lib.load().gkb_reset(self._h))
+        self.Noise.Reset()
+
+    def __str__(self):
+        return "F=%s\nG=%s\nH=%s\n%s" % (self.F, self.G, self.H, self.Noise)
+
+    # -- Update
+    def _innov_len(self):
+        return self._m
+
+    def Update(self, measurement, control=None):
+        """LDKF.Update(measurement, control) (kalman.go:36): one step of every filter in the batch.
+        measurement: [m] (shared) or [m, n_filters]; control: [c]."""
+        y = _arr(measurement)
+        if y.shape[0] != self._m:  # checkMatDims(measurement, H, rows2rows) vanilla.go:133-135
+            raise GkbError(-1, "measurement (y)(%dx...) H(%dx...)" % (y.shape[0], self._m))
+        u = None if control is None else _arr(control)
+        if self.needCtrl and (u is None or u.shape[0] != self._c):  # vanilla.go:129-131
+            raise GkbError(-1, "control (u)(%sx...) G(...x%d)" % ("nil" if u is None else u.shape[0], self._c))
+        if u is not None and u.shape[0] != self._c:
+            u = None
+        est = self.UpdateBatch(y[None], None if u is None else u[None], every_step=False)
+        return est
+
+    def UpdateBatch(self, measurements, controls=None, every_step=True, want=None):
+        """Batched entry point: `steps` Updates inside one kernel launch.
+        measurements: [steps, m] (shared by all filters) or [steps, m, n_filters]; controls [steps, c]."""
+        lib = _lib.load()
+        y = _arr(measurements)
+        steps = y.shape[0]
+        shared = 1 if y.ndim == 2 else 0
+        if y.shape[1] != self._m:
+            raise GkbError(-1, "measurement (y)(%dx...) H(%dx...)" % (y.shape[1], self._m))
+        if not shared and y.shape[2] != self._nf:
+            raise GkbError(-1, "measurements for %d filters given to a batch of %d" % (y.shape[2], self._nf))
+        u = None if controls is None else _arr(controls).reshape(steps, -1)
+        if self.needCtrl and (u is None or u.shape[1] != self._c):
+            raise GkbError(-1, "control (u) G(...x%d)" % self._c)
+        out, fields, status = self._alloc_out(steps, every_step, want or self._want, self._innov_len())
+        _lib.check(lib.gkb_update(self._h, steps, _ptr(y), shared, _ptr(u), _lib.HOST, C.byref(out)))
+        self._raise_status(status)
+        return Estimate(self._n, self._m, fields, status)
+
+
+class Vanilla(_LDKF):
+    _kind = _lib.VANILLA
+
+
+class Information(_LDKF):
+    _kind = _lib.INFORMATION
+    _want = ("state", "meas", "innov", "covar", "pred_covar")
+
+    def _innov_len(self):
+        return self._n  # Innovation() returns the information state (information.go:272-274)
+
+    def GetStateTransition(self):
+        """*WARNING:* returns the INVERSE of F, like the reference (information.go:103-105)."""
+        return np.linalg.inv(self.F)
+
+
+class SquareRoot(_LDKF):
+    _kind = _lib.SQRT
+
+
+def NewVanilla(x0, Covar0, F, G, H, noise, n_filters=1, device=0):
+    kf = Vanilla()
+    kf._create(_lib.VANILLA, x0, Covar0, F, G, H, noise, n_filters, device)
+    return kf, _est0(kf, x0, Covar0)
+
+
+def NewPurePredictorVanilla(x0, Covar0, F, G, H, noise, n_filters=1, device=0):
+    kf = Vanilla()
+    kf._kind = _lib.PREDICTOR
+    kf.predictionOnly = True
+    kf._create(_lib.PREDICTOR, x0, Covar0, F, G, H, noise, n_filters, device)
+    return kf, _est0(kf, x0, Covar0)
+
+
+def NewInformation(i0, I0, F, G, H, noise, n_filters=1, device=0):
+    kf = Information()
+    kf._create(_lib.INFORMATION, i0, I0, F, G, H, noise, n_filters, device)
+    return kf, None
+
+
+def NewInformationFromState(x0, P0, F, G, H, noise, n_filters=1, device=0):
+    kf = Information()
+    kf._create(_lib.INFORMATION, x0, P0, F, G, H, noise, n_filters, device, from_state=True)
+    return kf, None
+
+
+def NewSquareRoot(x0, P0, F, G, H, noise, n_filters=1, device=0):
+    kf = SquareRoot()
+    kf._create(_lib.SQRT, x0, P0, F, G, H, noise, n_filters, device)
+    return kf, _est0(kf, x0, P0)
+
+
+def _est0(kf, x0, P0):
+    """est0 = {x0, 0, 0, P0, 0, nil} (vanilla.go:34-37)"""
+    n, m = kf._n, kf._m
+    x0 = _arr(x0)
+    if x0.ndim == 2:
+        x0 = x0[:, 0]
+    f = {"state": x0.reshape(1, n, 1), "meas": np.zeros((1, m, 1)), "innov": np.zeros((1, m, 1)),
+         "covar": _arr(P0).reshape(1, n * n, 1), "pred_covar": np.zeros((1, n * n, 1))}
+    return Estimate(n, m, f)
+
+
+# --------------------------------------------------------------------------------------------------
+# NLDKF: HybridKF / SRIF (kalman.go:51-60)
+# --------------------------------------------------------------------------------------------------
+class _NLDKF(_Filter):
+    _want = ("state", "meas", "innov", "covar", "pred_covar", "gain", "obs_dev")
+
+    def __init__(self):
+        super().__init__()
+        self._Phi = self._Ht = self._Gamma = None
+        self.locked = True
+        self.ekfMode = False
+        self.sncEnabled = False
+
+    def Prepare(self, Phi, Htilde):
+        """hybrid.go:78-82 / srif.go:82-86"""
+        self._Phi = _arr(Phi)
+        self._Ht = None if Htilde is None else _mat(Htilde)
+        self.locked = False
+
+    def EKFEnabled(self):
+        return self.ekfMode
+
+    def _innov_len(self):
+        return self._m
+
+    def _one(self, has_meas, real, computed):
+        if self.locked:
+            raise GkbError(-4, "kf is locked (call Prepare() first)")  # hybrid.go:105-107
+        flags = np.array([(_lib.F_MEAS if has_meas else 0) | (_lib.F_EKF if self.ekfMode else 0) |
+                          (_lib.F_SNC if self.sncEnabled else 0)], dtype=np.uint8)
+        if has_meas:
+            real, computed = _arr(real), _arr(computed)
+            if real.shape != computed.shape:  # checkMatDims(real, computed, rowsAndcols) hybrid.go:108-112
+                raise GkbError(-1, "real observation %s computed observation %s" % (real.shape, computed.shape))
+        est = self.RunBatch(flags, self._Phi[None], None if self._Ht is None else self._Ht[None],
+                            None if real is None else real[None], None if computed is None else computed[None],
+                            None if self._Gamma is None else self._Gamma[None], every_step=False)
+        self.sncEnabled = False  # hybrid.go:140,201
+        self.locked = True
+        return est
+
+    def Update(self, realObservation, computedObservation):
+        return self._one(True, realObservation, computedObservation)
+
+    def Predict(self):
+        return self._one(False, None, None)
+
+    def RunBatch(self, flags, Phi, Htilde, real_obs, computed_obs, Gamma=None, every_step=True, want=None):
+        """Batched entry point: `steps` epochs of Prepare + Update/Predict in one kernel launch.
+        Phi: [steps, n, n] (shared) or [steps, n*n, n_filters]; Htilde likewise; observations
+        [steps, m] or [steps, m, n_filters]; flags uint8[steps]; Gamma [steps, n, q] (shared)."""
+        lib = _lib.load()
+        n, m, nf = self._n, self._m, self._nf
+        flags = None if flags is None else np.ascontiguousarray(np.asarray(flags, dtype=np.uint8))
+        Phi = _arr(Phi)
+        steps = Phi.shape[0]
+        # shared by all filters: [steps, n, n]; per filter: [steps, n, n, N] or [steps, n*n, N]
+        phi_shared = 1 if (Phi.ndim == 3 and Phi.shape[1:] == (n, n)) else 0
+        Phi = np.ascontiguousarray(Phi.reshape(steps, n * n) if phi_shared else Phi.reshape(steps, n * n, nf))
+        h_shared = 1
+        if Htilde is not None:
+            Htilde = _arr(Htilde)
+            h_shared = 1 if (Htilde.ndim == 3 and Htilde.shape[1:] == (m, n)) else 0
+            Htilde = np.ascontiguousarray(Htilde.reshape(steps, m * n) if h_shared else Htilde.reshape(steps, m * n, nf))
+
+        def obs(a):
+            if a is None:
+                return None
+            a = _arr(a)
+            if a.ndim == 2:
+                a = np.repeat(a[:, :, None], nf, axis=2)
+            return np.ascontiguousarray(a.reshape(steps, m, nf))
+        real_obs, computed_obs = obs(real_obs), obs(computed_obs)
+        if Gamma is not None:
+            Gamma = np.ascontiguousarray(_arr(Gamma).reshape(steps, -1))
+        out, fields, status = self._alloc_out(steps, every_step, want or self._want, self._innov_len())
+        _lib.check(lib.gkb_nl_run(self._h, steps, _ptr(flags), _ptr(Phi), phi_shared, _ptr(Htilde), h_shared,
+                                  _ptr(real_obs), _ptr(computed_obs), _ptr(Gamma), _lib.HOST, C.byref(out)))
+        self._raise_status(status)
+        return Estimate(n, m, fields, status)
+
+
+class HybridKF(_NLDKF):
+    def EnableEKF(self):
+        self.ekfMode = True
+
+    def DisableEKF(self):
+        self.ekfMode = False
+
+    def PreparePNT(self, Gamma):
+        """hybrid.go:86-89: enables the SNC for the next update only."""
+        self._Gamma = _arr(Gamma)
+        self.sncEnabled = True
+
+    def SetNoise(self, n):
+        Q, R = _mat(n.ProcessMatrix()), _mat(n.MeasurementMatrix())
+        _lib.check(_lib.load().gkb_set_noise(self._h, _ptr(Q), R.shape[0], _ptr(R)))
+        self.Noise = n
+
+    def GetNoise(self):
+        return self.Noise
+
+    def __str__(self):
+        return "HybridKF [k=%d]\n%s" % (_lib.load().gkb_step(self._h), self.Noise)
+
+
+class SRIF(_NLDKF):
+    _want = ("state", "meas", "innov", "covar", "pred_covar", "obs_dev")
+
+    def _innov_len(self):
+        return self._n  # Innovation() returns b (srif.go:238-240)
+
+    def EnableEKF(self):
+        pass  # srif.go:66-72: no-ops
+
+    def DisableEKF(self):
+        pass
+
+    def EKFEnabled(self):
+        return False
+
+    def PreparePNT(self, Gamma):
+        pass  # srif.go:75
+
+    def SetNoise(self, n):
+        raise NotImplementedError("noise not yet supported for SRIF")  # srif.go:77-79 panics
+
+
+def NewHybridKF(x0, P0, noise, measSize, n_filters=1, device=0):
+    lib = _lib.load()
+    x0, P0 = _arr(x0), _arr(P0)
+    n = x0.shape[0]
+    if n != P0.shape[1]:  # hybrid.go:25-27
+        raise GkbError(-1, "x0(%dx...) Covar0(...x%d)" % (n, P0.shape[1]))
+    Q, R = noise.ProcessMatrix(), _mat(noise.MeasurementMatrix())
+    Q = None if Q is None else _mat(Q)
+    q = 0 if Q is None else Q.shape[0]
+    if q > 3:  # only a q x q SNC matrix (q <= 3) is used as Gamma Q Gamma^T
+        raise GkbError(-8, "process noise of size %d: the SNC path takes q <= 3" % q)
+    kf = HybridKF()
+    h = C.c_void_p()
+    per_filter = 1 if x0.ndim == 2 else 0
+    _lib.check(lib.gkb_create_hybrid(n, measSize, q, n_filters, device, _ptr(x0), per_filter, _ptr(P0), _ptr(Q), _ptr(R),
+                                     C.byref(h)))
+    kf._h, kf._n, kf._m, kf._nf, kf._device, kf.Noise = h, n, measSize, n_filters, device, noise
+    f = {"state": (x0[:, 0] if x0.ndim == 2 else x0).reshape(1, n, 1), "meas": np.zeros((1, measSize, 1)),
+         "innov": np.zeros((1, measSize, 1)), "obs_dev": np.zeros((1, measSize, 1)),
+         "covar": P0.reshape(1, n * n, 1), "pred_covar": np.zeros((1, n * n, 1))}
+    return kf, Estimate(n, measSize, f)
+
+
+def NewSRIF(x0, P0, measSize, nonTriR, noise, n_filters=1, device=0):
+    lib = _lib.load()
+    x0, P0 = _arr(x0), _arr(P0)
+    n = x0.shape[0]
+    if n != P0.shape[1]:  # srif.go:16-18
+        raise GkbError(-1, "x0(%dx...) P0(...x%d)" % (n, P0.shape[1]))
+    R = _mat(noise.MeasurementMatrix())
+    kf = SRIF()
+    h = C.c_void_p()
+    _lib.check(lib.gkb_create_srif(n, measSize, n_filters, device, _ptr(x0), 0, _ptr(P0), _ptr(R), int(bool(nonTriR)),
+                                   C.byref(h)))
+    kf._h, kf._n, kf._m, kf._nf, kf._device, kf.Noise = h, n, measSize, n_filters, device, noise
+    # est0: R0 = chol(diag(1/P0_ii)), b0 = R0 x0; Covariance() = inv(R0) inv(R0)^T (srif.go:20-47)
+    d = np.diag(P0).copy()
+    f = {"state": x0.reshape(1, n, 1), "covar": np.diag(d).reshape(1, n * n, 1),
+         "pred_covar": np.diag(d).reshape(1, n * n, 1), "innov": (x0 / np.sqrt(d)).reshape(1, n, 1)}
+    return kf, Estimate(n, measSize, f)
+
+
+# --------------------------------------------------------------------------------------------------
+# Monte Carlo + chi-square (montecarlo.go, chisquare.go)
+# --------------------------------------------------------------------------------------------------
+class MonteCarloRuns:
+    """montecarlo.go:12-16.  The reference stores every Estimate of every run; here the runs are a
+    recipe (model, noise seed, controls) that the fused kernel regenerates on demand -- Philox is
+    counter-based, so NewChiSquare sees exactly the trajectories Mean/StdDev/Truth describe."""
+
+    def __init__(self, samples, steps, rowsH, controls, kf, trial_offset=0):
+        self.runs, self.steps, self.rowsH = samples, steps, rowsH
+        self.kf, self.controls, self.trial_offset = kf, controls, trial_offset
+        self.noise = kf.Noise
+        self._stats = None
+
+    def _config(self, kind, tested, with_nees, with_nis, trials=None):
+        kf = self.kf
+        cfg = _lib.McConfig()
+        self._keep = keep = {}
+        keep["F"], keep["H"] = _arr(kf.F), _mat(kf.H)
+        keep["G"] = None if kf.G is None else _arr(kf.G)
+        keep["Q"], keep["R"] = _mat(self.noise.ProcessMatrix()), _mat(self.noise.MeasurementMatrix())
+        if tested is not None:
+            tn = tested.Noise
+            keep["Q"], keep["R"] = _mat(tn.ProcessMatrix()), _mat(tn.MeasurementMatrix())
+        keep["x0t"] = _arr(kf._x0)
+        keep["x0f"] = _arr(tested._x0) if tested is not None else _arr(kf._x0)
+        keep["P0"] = _arr(tested._P0) if tested is not None else _arr(kf._P0)
+        keep["u"] = None if self.controls is None else _arr(self.controls).reshape(self.steps, -1)
+        cfg.kind, cfg.n, cfg.m, cfg.c = kind, kf._n, kf._m, kf._c
+        for name, key in (("F", "F"), ("G", "G"), ("H", "H"), ("Q", "Q"), ("R", "R"), ("x0_truth", "x0t"),
+                          ("x0_filter", "x0f"), ("P0", "P0"), ("controls", "u")):
+            setattr(cfg, name, None if keep[key] is None else keep[key].ctypes.data)
+        cfg.trials = self.runs if trials is None else trials
+        cfg.trial_offset, cfg.steps = self.trial_offset, self.steps
+        cfg.with_nees, cfg.with_nis = int(with_nees), int(with_nis)
+        cfg.info_raw_init = int(kind == _lib.INFORMATION and tested is not None and not tested._from_state)
+        cfg.device = kf._device
+        if isinstance(self.noise, ReplayNoise):
+            cfg.noise_mode = _lib.NOISE_REPLAY
+            w = _arr(self.noise.process).reshape(self.steps, kf._n, self.runs)
+            v = _arr(self.noise.measurement).reshape(self.steps, kf._m, self.runs)
+            keep["w"], keep["v"] = w, v
+            cfg.w, cfg.v, cfg.noise_mem = w.ctypes.data, v.ctypes.data, _lib.HOST
+        else:
+            cfg.noise_mode, cfg.seed = _lib.NOISE_PHILOX, self.noise.seed
+        return cfg
+
+    def _run(self, cfg, want_stats=False, want_truth=False, want_noise=False):
+        n, m, steps, runs = cfg.n, cfg.m, cfg.steps, cfg.trials
+        out = _lib.McOutputs()
+        out.mem, out.sums_only = _lib.HOST, 0
+        res = {"NIS": np.zeros(steps), "NEES": np.zeros(steps)}
+        out.nis, out.nees = res["NIS"].ctypes.data, res["NEES"].ctypes.data
+        if want_stats:
+            for key in ("sum_d", "sum_dd", "x_ref"):
+                res[key] = np.zeros((steps, n))
+                setattr(out, key, res[key].ctypes.data)
+        if want_truth:
+            res["truth_x"], res["truth_y"] = np.zeros((steps, n, runs)), np.zeros((steps, m, runs))
+            out.truth_x, out.truth_y = res["truth_x"].ctypes.data, res["truth_y"].ctypes.data
+        if want_noise:
+            res["noise_w"], res["noise_v"] = np.zeros((steps, n, runs)), np.zeros((steps, m, runs))
+            out.noise_w, out.noise_v = res["noise_w"].ctypes.data, res["noise_v"].ctypes.data
+        res["status"] = np.zeros(runs, dtype=np.int32)
+        out.status = res["status"].ctypes.data
+        _lib.check(_lib.load().gkb_mc_chisquare(C.byref(cfg), C.byref(out)))
+        return res
+
+    def _get_stats(self):
+        if self._stats is None:
+            cfg = self._config(_lib.VANILLA, None, True, True)
+            self._stats = self._run(cfg, want_stats=True)
+        return self._stats
+
+    def Mean(self, step):
+        """montecarlo.go:18-37: mean of every state component over the runs at `step`."""
+        s = self._get_stats()
+        return s["x_ref"][step] + s["sum_d"][step] / self.runs
+
+    def StdDev(self, step):
+        """montecarlo.go:40-59: unbiased standard deviation over the runs at `step`."""
+        s = self._get_stats()
+        var = (s["sum_dd"][step] - s["sum_d"][step] ** 2 / self.runs) / (self.runs - 1)
+        return np.sqrt(np.maximum(var, 0.0))
+
+    def Truth(self, with_noise=False):
+        """The (state, measurement) trajectories of every run: [steps, n, runs], [steps, m, runs]."""
+        cfg = self._config(_lib.VANILLA, None, True, True)
+        r = self._run(cfg, want_truth=True, want_noise=with_noise)
+        if with_noise:
+            return r["truth_x"], r["truth_y"], r["noise_w"], r["noise_v"]
+        return r["truth_x"], r["truth_y"]
+
+    def AsCSV(self, headers):
+        """montecarlo.go:62-89"""
+        tx, _ = self.Truth()
+        n = tx.shape[1]
+        out = []
+        for i in range(n):
+            header = headers[i]
+            lines = ["".join("%s-%d," % (header, r) for r in range(self.runs)) + header + "-mean," + header + "-stddev"]
+            for k in range(self.steps):
+                mean, std = self.Mean(k), self.StdDev(k)
+                lines.append("".join("%f," % tx[k, i, r] for r in range(self.runs)) + "%f,%f" % (mean[i], std[i]))
+            out.append("\n".join(lines))
+        return out
+
+
+def _controls(controls, steps):
+    """montecarlo.go:97-107 / chisquare.go:26-35: exactly `steps` vectors, or one vector => zeros."""
+    if controls is None:
+        return None
+    controls = [np.asarray(c, dtype=np.float64).reshape(-1) for c in controls]
+    if len(controls) == 1:
+        return np.zeros((steps, controls[0].shape[0]))
+    if len(controls) != steps:
+        raise ValueError("must provide as much control vectors as steps, or just one control vector")
+    return np.stack(controls)
+
+
+def NewMonteCarloRuns(samples, steps, rowsH, controls, kf, trial_offset=0):
+    """montecarlo.go:92-119.  `kf` must be a pure predictor whose noise is AWGN (or ReplayNoise)."""
+    if not getattr(kf, "predictionOnly", False):
+        raise ValueError("the Kalman filter needed for the Monte Carlo runs must be a pure predictor")
+    return MonteCarloRuns(samples, steps, rowsH, _controls(controls, steps), kf, trial_offset)
+
+
+_KIND_OF = {Vanilla: _lib.VANILLA, Information: _lib.INFORMATION, SquareRoot: _lib.SQRT}
+
+
+def NewChiSquare(kf, runs, controls, withNEES, withNIS):
+    """chisquare.go:16-95.  Returns (NISmeans, NEESmeans) -- in that order, like the reference."""
+    if not withNEES and not withNIS:
+        raise GkbError(-10, "Chi Square requires either NEES or NIS or both")
+    ctrl = _controls(controls, runs.steps)  # raises like chisquare.go:33-35 returns an error
+    if ctrl is not None and kf.needCtrl and ctrl.shape[1] != kf._c:
+        raise GkbError(-1, "control (u)(%dx...) G(...x%d)" % (ctrl.shape[1], kf._c))  # Update error -> panic, chisquare.go:40-42
+    kind = _lib.VANILLA if isinstance(kf, Vanilla) else _KIND_OF[type(kf)]
+    saved = runs.controls
+    runs.controls = ctrl if ctrl is not None else saved
+    try:
+        cfg = runs._config(kind, kf, withNEES, withNIS)
+        res = runs._run(cfg)
+    finally:
+        runs.controls = saved
+    bad = res["status"][res["status"] != 0]
+    if bad.size:
+        raise GkbError(int(bad[0]), "%d trial(s) failed during Update" % bad.size)
+    return res["NIS"], res["NEES"]

@@ -1,0 +1,818 @@
+// engine.cu -- host runtime and C-ABI of libgokalman_b200.so (see include/gokalman_b200.h).
+//
+// A handle owns the device-resident state of a batch of filters (SoA [component][filter]), a host
+// copy of the shared model and growable device staging buffers for host-side callers.  Calls with
+// host pointers copy in, launch, copy out and synchronise; calls with device pointers only enqueue
+// work on the handle's stream (the legacy default stream unless gkb_set_stream is used), so a
+// caller can bracket them with its own CUDA events.  There is no CPU path anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine_internal.h"
+
+using namespace gkb;
+
+namespace {
+
+thread_local std::string g_last_error;
+thread_local float g_last_ms = 0.f;
+thread_local int g_last_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define GKB_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(GKB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+      if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaMalloc(%zu) failed", bytes);
+      want = bytes;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// CUDA-event bracket around the kernels of the last call on this thread.  The events are kept so
+// that gkb_last_kernel_ms() can be asked later, also after an asynchronous (device-pointer) call.
+struct LastTiming {
+  cudaEvent_t e0 = nullptr, e1 = nullptr, m0 = nullptr, m1 = nullptr;  // whole call / dominant kernel
+  bool valid = false, main_valid = false;
+};
+thread_local LastTiming g_timing;
+
+struct Timer {
+  cudaStream_t s;
+  explicit Timer(cudaStream_t st) : s(st) {
+    if (!g_timing.e0) {
+      cudaEventCreate(&g_timing.e0);
+      cudaEventCreate(&g_timing.e1);
+      cudaEventCreate(&g_timing.m0);
+      cudaEventCreate(&g_timing.m1);
+    }
+    g_timing.valid = g_timing.main_valid = false;
+    cudaEventRecord(g_timing.e0, s);
+  }
+  void main_begin() { cudaEventRecord(g_timing.m0, s); }
+  void main_end() {
+    cudaEventRecord(g_timing.m1, s);
+    g_timing.main_valid = true;
+  }
+  void stop(int launches, bool /*sync*/) {
+    cudaEventRecord(g_timing.e1, s);
+    g_timing.valid = true;
+    g_last_launches = launches;
+  }
+};
+
+void sym_from_upper(double* dst, const double* src, int n) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) dst[i * n + j] = (j >= i) ? src[i * n + j] : src[j * n + i];
+}
+
+bool is_nil(const double* M, int len) {  // helper.go:50-63
+  if (!M) return true;
+  for (int i = 0; i < len; ++i)
+    if (M[i] != 0.0) return false;
+  return true;
+}
+
+// vec[i][f] = x0[i] (or per-filter copy), mat[i][f] = A0[i]
+__global__ void fill_state_kernel(double* vec, double* mat, const double* x0, int x0_per_filter, const double* A0,
+                                  int n, int64_t nf) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  for (int i = 0; i < n; ++i) vec[(int64_t)i * nf + f] = x0_per_filter ? x0[(int64_t)i * nf + f] : x0[i];
+  for (int i = 0; i < n * n; ++i) mat[(int64_t)i * nf + f] = A0[i];
+}
+
+int check_device(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(GKB_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
+  if (device < 0 || device >= count) return fail(GKB_ERR_ARG, "device %d out of range (0..%d)", device, count - 1);
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (p.major != 10)
+    return fail(GKB_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, p.major, p.minor);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  return 0;
+}
+
+}  // namespace
+
+struct gkb_filter {
+  HostModel hm;
+  int64_t nf = 0;
+  int device = 0;
+  cudaStream_t stream = cudaStreamLegacy;
+  int step = 0;
+  bool ekf = false;
+  DevBuf vec, mat, vec0, mat0, status;
+  DevBuf replay_w, replay_v;
+  int replay_steps = 0;
+  bool has_w = false, has_v = false;
+  DevBuf in_y, in_u, in_a, in_b, in_c, in_d, in_e, in_f;  // staging for host inputs
+  DevBuf o_state, o_meas, o_innov, o_covar, o_pred, o_gain, o_obsdev;
+};
+
+extern "C" {
+
+const char* gkb_version(void) { return "gokalman_b200 0.1 (sm_100a)"; }
+const char* gkb_last_error(void) { return g_last_error.c_str(); }
+float gkb_last_kernel_ms(void) {
+  if (!g_timing.valid) return -1.f;
+  if (cudaEventSynchronize(g_timing.e1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&g_last_ms, g_timing.e0, g_timing.e1) != cudaSuccess) return -1.f;
+  return g_last_ms;
+}
+float gkb_last_main_kernel_ms(void) {
+  if (!g_timing.main_valid) return gkb_last_kernel_ms();
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_timing.m1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_timing.m0, g_timing.m1) != cudaSuccess) return -1.f;
+  return ms;
+}
+int gkb_last_kernel_launches(void) { return g_last_launches; }
+
+int gkb_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+  return c;
+}
+
+int gkb_shape_supported(int kind, int n, int m) {
+  if (kind < GKB_VANILLA || kind > GKB_SRIF) return 0;
+#define GKB_CASE(NN, MM) \
+  if (n == NN && m == MM) return 1;
+  GKB_FOR_EACH_SHAPE(GKB_CASE)
+#undef GKB_CASE
+  return 0;
+}
+
+static int finish_create(gkb_filter* f, const double* x0, int x0_per_filter, const double* A0) {
+  const int n = f->hm.n;
+  const int64_t nf = f->nf;
+  int rc;
+  if ((rc = f->vec.ensure(sizeof(double) * n * nf))) return rc;
+  if ((rc = f->mat.ensure(sizeof(double) * n * n * nf))) return rc;
+  if ((rc = f->vec0.ensure(sizeof(double) * n * nf))) return rc;
+  if ((rc = f->mat0.ensure(sizeof(double) * n * n * nf))) return rc;
+  if ((rc = f->status.ensure(sizeof(int32_t) * nf))) return rc;
+  DevBuf dx, dA;
+  const size_t xbytes = sizeof(double) * (x0_per_filter ? (size_t)n * nf : (size_t)n);
+  if ((rc = dx.ensure(xbytes))) return rc;
+  if ((rc = dA.ensure(sizeof(double) * n * n))) { dx.release(); return rc; }
+  cudaMemcpyAsync(dx.p, x0, xbytes, cudaMemcpyHostToDevice, f->stream);
+  cudaMemcpyAsync(dA.p, A0, sizeof(double) * n * n, cudaMemcpyHostToDevice, f->stream);
+  fill_state_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, f->stream>>>(f->vec0.as<double>(), f->mat0.as<double>(),
+                                                                        dx.as<double>(), x0_per_filter, dA.as<double>(), n, nf);
+  cudaMemcpyAsync(f->vec.p, f->vec0.p, sizeof(double) * n * nf, cudaMemcpyDeviceToDevice, f->stream);
+  cudaMemcpyAsync(f->mat.p, f->mat0.p, sizeof(double) * n * n * nf, cudaMemcpyDeviceToDevice, f->stream);
+  cudaMemsetAsync(f->status.p, 0, sizeof(int32_t) * nf, f->stream);
+  cudaError_t e = cudaStreamSynchronize(f->stream);
+  dx.release();
+  dA.release();
+  if (e != cudaSuccess) return fail(GKB_ERR_CUDA, "state initialisation failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static void destroy_filter(gkb_filter* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  DevBuf* bufs[] = {&f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u,
+                    &f->in_a, &f->in_b, &f->in_c, &f->in_d, &f->in_e, &f->in_f, &f->o_state, &f->o_meas, &f->o_innov,
+                    &f->o_covar, &f->o_pred, &f->o_gain, &f->o_obsdev};
+  for (DevBuf* b : bufs) b->release();
+  delete f;
+}
+
+int gkb_create_lti(int kind, int n, int m, int c, int64_t n_filters, int device, const double* x0, int x0_per_filter,
+                   const double* P0, const double* F, const double* G, const double* H, const double* Q,
+                   const double* R, gkb_filter** out) {
+  if (!out) return fail(GKB_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (kind != GKB_VANILLA && kind != GKB_PREDICTOR && kind != GKB_INFORMATION && kind != GKB_SQRT)
+    return fail(GKB_ERR_ARG, "gkb_create_lti: kind %d is not an LDKF kind", kind);
+  if (!x0 || !P0 || !F || !H || !Q || !R) return fail(GKB_ERR_ARG, "gkb_create_lti: NULL model array");
+  if (n_filters < 1) return fail(GKB_ERR_ARG, "n_filters must be >= 1");
+  if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
+  if (!gkb_shape_supported(kind, n, m))
+    return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d (kind %d)", n, m, kind);
+  int rc = check_device(device);
+  if (rc) return rc;
+  gkb_filter* f = new gkb_filter();
+  f->nf = n_filters;
+  f->device = device;
+  HostModel& hm = f->hm;
+  memset(&hm, 0, sizeof hm);
+  hm.kind = kind; hm.n = n; hm.m = m; hm.c = c; hm.m_r = m;
+  memcpy(hm.F, F, sizeof(double) * n * n);
+  if (G && c > 0) memcpy(hm.G, G, sizeof(double) * n * c);
+  hm.need_ctrl = !(G == nullptr || c == 0 || is_nil(G, n * c));  // vanilla.go:39
+  memcpy(hm.H, H, sizeof(double) * m * n);
+  sym_from_upper(hm.Q, Q, n);
+  sym_from_upper(hm.R, R, m);
+  double A0[GKB_MAX_N * GKB_MAX_N];
+  sym_from_upper(A0, P0, n);
+  std::vector<double> x0v(x0, x0 + (x0_per_filter ? (size_t)n * n_filters : (size_t)n));
+  int ops = 0;
+  if (kind == GKB_INFORMATION) { ops = kOpFinv | kOpQinv | kOpRinv; hm.rinv_dim = m; }
+  if (kind == GKB_SQRT) ops = kOpSqrtQ | kOpSqrtR | kOpCholA0;
+  if (ops) {
+    rc = launch_model_setup(hm, ops, nullptr, A0, f->stream);
+    if (rc) { destroy_filter(f); return fail(rc, "model setup failed (%d)", rc); }
+  }
+  rc = finish_create(f, x0v.data(), x0_per_filter, A0);
+  if (rc) { destroy_filter(f); return rc; }
+  *out = f;
+  return 0;
+}
+
+int gkb_create_information_from_state(int n, int m, int c, int64_t n_filters, int device, const double* x0,
+                                      const double* P0, const double* F, const double* G, const double* H,
+                                      const double* Q, const double* R, gkb_filter** out) {
+  if (!out) return fail(GKB_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (!x0 || !P0 || !F || !H || !Q || !R) return fail(GKB_ERR_ARG, "NULL model array");
+  if (!gkb_shape_supported(GKB_INFORMATION, n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", n, m);
+  int rc = check_device(device);
+  if (rc) return rc;
+  // I0 = inv(P0) (zeros if singular), i0 = I0 x0 (information.go:65-81), on the device
+  HostModel tmp;
+  memset(&tmp, 0, sizeof tmp);
+  tmp.kind = GKB_INFORMATION; tmp.n = n; tmp.m = m; tmp.m_r = m;
+  double A0[GKB_MAX_N * GKB_MAX_N], xv[GKB_MAX_N];
+  sym_from_upper(A0, P0, n);
+  memcpy(xv, x0, sizeof(double) * n);
+  rc = launch_model_setup(tmp, kOpFromState, xv, A0, cudaStreamLegacy);
+  if (rc) return fail(rc, "information-from-state setup failed (%d)", rc);
+  return gkb_create_lti(GKB_INFORMATION, n, m, c, n_filters, device, xv, 0, A0, F, G, H, Q, R, out);
+}
+
+int gkb_create_hybrid(int n, int m, int q, int64_t n_filters, int device, const double* x0, int x0_per_filter,
+                      const double* P0, const double* Q, const double* R, gkb_filter** out) {
+  if (!out) return fail(GKB_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (!x0 || !P0 || !R) return fail(GKB_ERR_ARG, "NULL model array");
+  if (q < 0 || q > GKB_MAX_Q) return fail(GKB_ERR_UNSUPPORTED, "process-noise size %d outside 0..%d", q, GKB_MAX_Q);
+  if (n_filters < 1) return fail(GKB_ERR_ARG, "n_filters must be >= 1");
+  if (!gkb_shape_supported(GKB_HYBRID, n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", n, m);
+  int rc = check_device(device);
+  if (rc) return rc;
+  gkb_filter* f = new gkb_filter();
+  f->nf = n_filters;
+  f->device = device;
+  HostModel& hm = f->hm;
+  memset(&hm, 0, sizeof hm);
+  hm.kind = GKB_HYBRID; hm.n = n; hm.m = m; hm.q = q; hm.m_r = m;
+  if (Q && q > 0) sym_from_upper(hm.Q, Q, q);
+  sym_from_upper(hm.R, R, m);
+  double A0[GKB_MAX_N * GKB_MAX_N];
+  sym_from_upper(A0, P0, n);
+  rc = finish_create(f, x0, x0_per_filter, A0);
+  if (rc) { destroy_filter(f); return rc; }
+  *out = f;
+  return 0;
+}
+
+int gkb_create_srif(int n, int m, int64_t n_filters, int device, const double* x0, int x0_per_filter,
+                    const double* P0, const double* R, int non_tri_r, gkb_filter** out) {
+  if (!out) return fail(GKB_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (!x0 || !P0 || !R) return fail(GKB_ERR_ARG, "NULL model array");
+  if (x0_per_filter) return fail(GKB_ERR_UNSUPPORTED, "per-filter x0 is not supported for SRIF (b0 = R0 x0 is formed once)");
+  if (n_filters < 1) return fail(GKB_ERR_ARG, "n_filters must be >= 1");
+  if (!gkb_shape_supported(GKB_SRIF, n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", n, m);
+  int rc = check_device(device);
+  if (rc) return rc;
+  gkb_filter* f = new gkb_filter();
+  f->nf = n_filters;
+  f->device = device;
+  HostModel& hm = f->hm;
+  memset(&hm, 0, sizeof hm);
+  hm.kind = GKB_SRIF; hm.n = n; hm.m = m; hm.m_r = m; hm.non_tri_r = non_tri_r;
+  sym_from_upper(hm.R, R, m);
+  double A0[GKB_MAX_N * GKB_MAX_N], xv[GKB_MAX_N];
+  memset(A0, 0, sizeof A0);
+  for (int i = 0; i < n * n; ++i) A0[i] = P0[i];
+  memcpy(xv, x0, sizeof(double) * n);
+  rc = launch_model_setup(hm, kOpSqrtR | kOpSrifInit, xv, A0, f->stream);
+  if (rc) { destroy_filter(f); return fail(rc, "NewSRIF: sqrt of the measurement noise is not invertible (%d)", rc); }
+  memcpy(hm.L, hm.sqrtR, sizeof(double) * m * m);  // srif.go:48 keeps L, not its inverse
+  rc = finish_create(f, xv, 0, A0);
+  if (rc) { destroy_filter(f); return rc; }
+  *out = f;
+  return 0;
+}
+
+void gkb_destroy(gkb_filter* f) { destroy_filter(f); }
+
+int64_t gkb_n_filters(const gkb_filter* f) { return f ? f->nf : 0; }
+int gkb_step(const gkb_filter* f) { return f ? f->step : 0; }
+
+int gkb_set_stream(gkb_filter* f, void* stream) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  f->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamLegacy;
+  return 0;
+}
+
+int gkb_set_state_transition(gkb_filter* f, const double* F) {
+  if (!f || !F) return fail(GKB_ERR_ARG, "NULL argument");
+  cudaSetDevice(f->device);
+  memcpy(f->hm.F, F, sizeof(double) * f->hm.n * f->hm.n);
+  if (f->hm.kind == GKB_INFORMATION) {  // information.go:117-123
+    int rc = launch_model_setup(f->hm, kOpFinv, nullptr, nullptr, f->stream);
+    if (rc) return fail(rc, "inv(F) setup failed");
+  }
+  return 0;
+}
+
+int gkb_set_input_control(gkb_filter* f, int c, const double* G) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
+  f->hm.c = c;  // needCtrl is not re-evaluated (vanilla.go:99-101)
+  if (G && c > 0) memcpy(f->hm.G, G, sizeof(double) * f->hm.n * c);
+  return 0;
+}
+
+int gkb_set_measurement_matrix(gkb_filter* f, int m, const double* H) {
+  if (!f || !H) return fail(GKB_ERR_ARG, "NULL argument");
+  if (!gkb_shape_supported(f->hm.kind, f->hm.n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", f->hm.n, m);
+  f->hm.m = m;
+  memcpy(f->hm.H, H, sizeof(double) * m * f->hm.n);
+  return 0;
+}
+
+int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R) {
+  if (!f || !R) return fail(GKB_ERR_ARG, "NULL argument");
+  if (m_r < 1 || m_r > GKB_MAX_M) return fail(GKB_ERR_UNSUPPORTED, "R dimension %d outside 1..%d", m_r, GKB_MAX_M);
+  if (f->hm.kind == GKB_SRIF) return fail(GKB_ERR_UNSUPPORTED, "noise not yet supported for SRIF (srif.go:77-79 panics)");
+  cudaSetDevice(f->device);
+  const int qd = (f->hm.kind == GKB_HYBRID) ? f->hm.q : f->hm.n;
+  if (Q && qd > 0) sym_from_upper(f->hm.Q, Q, qd);
+  sym_from_upper(f->hm.R, R, m_r);
+  f->hm.m_r = m_r;
+  if (f->hm.kind == GKB_SQRT) {  // squareroot.go:100-114
+    if (!gkb_shape_supported(GKB_SQRT, f->hm.n, m_r)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", f->hm.n, m_r);
+    int rc = launch_model_setup(f->hm, kOpSqrtQ | kOpSqrtR, nullptr, nullptr, f->stream);
+    if (rc) return fail(rc, "chol(Q), chol(R) setup failed");
+  }
+  // GKB_INFORMATION: inv(Q), inv(R) deliberately left stale (information.go:136-138)
+  f->has_w = f->has_v = false;
+  f->replay_steps = 0;
+  return 0;
+}
+
+int gkb_set_replay_noise(gkb_filter* f, int steps, const double* w, const double* v, int mem) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  if (steps < 1) return fail(GKB_ERR_ARG, "steps must be >= 1");
+  cudaSetDevice(f->device);
+  const cudaMemcpyKind kind = mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  int rc;
+  f->has_w = f->has_v = false;
+  if (w) {
+    const size_t bytes = sizeof(double) * (size_t)steps * f->hm.n * f->nf;
+    if ((rc = f->replay_w.ensure(bytes))) return rc;
+    GKB_CUDA(cudaMemcpyAsync(f->replay_w.p, w, bytes, kind, f->stream));
+    f->has_w = true;
+  }
+  if (v) {
+    const size_t bytes = sizeof(double) * (size_t)steps * f->hm.m * f->nf;
+    if ((rc = f->replay_v.ensure(bytes))) return rc;
+    GKB_CUDA(cudaMemcpyAsync(f->replay_v.p, v, bytes, kind, f->stream));
+    f->has_v = true;
+  }
+  GKB_CUDA(cudaStreamSynchronize(f->stream));
+  f->replay_steps = steps;
+  return 0;
+}
+
+int gkb_reset(gkb_filter* f) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  cudaSetDevice(f->device);
+  const int n = f->hm.n;
+  GKB_CUDA(cudaMemcpyAsync(f->vec.p, f->vec0.p, sizeof(double) * n * f->nf, cudaMemcpyDeviceToDevice, f->stream));
+  GKB_CUDA(cudaMemcpyAsync(f->mat.p, f->mat0.p, sizeof(double) * n * n * f->nf, cudaMemcpyDeviceToDevice, f->stream));
+  GKB_CUDA(cudaMemsetAsync(f->status.p, 0, sizeof(int32_t) * f->nf, f->stream));
+  f->step = 0;
+  f->ekf = false;
+  return 0;
+}
+
+int gkb_get_state(const gkb_filter* f, double* vec, double* mat) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  cudaSetDevice(f->device);
+  const int n = f->hm.n;
+  GKB_CUDA(cudaStreamSynchronize(f->stream));
+  if (vec) GKB_CUDA(cudaMemcpy(vec, f->vec.p, sizeof(double) * n * f->nf, cudaMemcpyDeviceToHost));
+  if (mat) GKB_CUDA(cudaMemcpy(mat, f->mat.p, sizeof(double) * n * n * f->nf, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gkb_set_state(gkb_filter* f, const double* vec, const double* mat) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  cudaSetDevice(f->device);
+  const int n = f->hm.n;
+  if (vec) GKB_CUDA(cudaMemcpy(f->vec.p, vec, sizeof(double) * n * f->nf, cudaMemcpyHostToDevice));
+  if (mat) GKB_CUDA(cudaMemcpy(f->mat.p, mat, sizeof(double) * n * n * f->nf, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Device-side views of a gkb_outputs request (staged in the handle when the caller passed host
+// pointers) and the copy-back afterwards.
+struct OutPlan {
+  double *state = nullptr, *meas = nullptr, *innov = nullptr, *covar = nullptr, *pred = nullptr, *gain = nullptr,
+         *obsdev = nullptr;
+  size_t b_state = 0, b_meas = 0, b_innov = 0, b_covar = 0, b_pred = 0, b_gain = 0, b_obsdev = 0;
+};
+
+int plan_outputs(gkb_filter* f, const gkb_outputs* out, int steps, int innov_len, OutPlan& pl) {
+  if (!out) return 0;
+  const int n = f->hm.n, m = f->hm.m;
+  const size_t rows = out->every_step ? (size_t)steps : 1;
+  const size_t per = sizeof(double) * rows * f->nf;
+  pl.b_state = per * n; pl.b_meas = per * m; pl.b_innov = per * innov_len; pl.b_covar = per * n * n;
+  pl.b_pred = per * n * n; pl.b_gain = per * n * m; pl.b_obsdev = per * m;
+  if (out->mem == GKB_DEVICE) {
+    pl.state = out->state; pl.meas = out->meas; pl.innov = out->innov; pl.covar = out->covar;
+    pl.pred = out->pred_covar; pl.gain = out->gain; pl.obsdev = out->obs_dev;
+    return 0;
+  }
+  int rc;
+#define GKB_STAGE(field, buf, bytes, dst)        \
+  if (out->field) {                              \
+    if ((rc = f->buf.ensure(bytes))) return rc;  \
+    dst = f->buf.as<double>();                   \
+  }
+  GKB_STAGE(state, o_state, pl.b_state, pl.state)
+  GKB_STAGE(meas, o_meas, pl.b_meas, pl.meas)
+  GKB_STAGE(innov, o_innov, pl.b_innov, pl.innov)
+  GKB_STAGE(covar, o_covar, pl.b_covar, pl.covar)
+  GKB_STAGE(pred_covar, o_pred, pl.b_pred, pl.pred)
+  GKB_STAGE(gain, o_gain, pl.b_gain, pl.gain)
+  GKB_STAGE(obs_dev, o_obsdev, pl.b_obsdev, pl.obsdev)
+#undef GKB_STAGE
+  return 0;
+}
+
+int copy_back(gkb_filter* f, const gkb_outputs* out, const OutPlan& pl) {
+  if (!out) return 0;
+  if (out->mem == GKB_HOST) {
+#define GKB_BACK(field, src, bytes) \
+  if (out->field && src) GKB_CUDA(cudaMemcpyAsync(out->field, src, bytes, cudaMemcpyDeviceToHost, f->stream));
+    GKB_BACK(state, pl.state, pl.b_state)
+    GKB_BACK(meas, pl.meas, pl.b_meas)
+    GKB_BACK(innov, pl.innov, pl.b_innov)
+    GKB_BACK(covar, pl.covar, pl.b_covar)
+    GKB_BACK(pred_covar, pl.pred, pl.b_pred)
+    GKB_BACK(gain, pl.gain, pl.b_gain)
+    GKB_BACK(obs_dev, pl.obsdev, pl.b_obsdev)
+#undef GKB_BACK
+    if (out->status)
+      GKB_CUDA(cudaMemcpyAsync(out->status, f->status.p, sizeof(int32_t) * f->nf, cudaMemcpyDeviceToHost, f->stream));
+  } else if (out->status) {
+    GKB_CUDA(cudaMemcpyAsync(out->status, f->status.p, sizeof(int32_t) * f->nf, cudaMemcpyDeviceToDevice, f->stream));
+  }
+  return 0;
+}
+
+// Stage a host input array on the device (or pass a device pointer through).
+int stage_in(gkb_filter* f, DevBuf& buf, const void* src, size_t bytes, int in_mem, const void** dev) {
+  *dev = nullptr;
+  if (!src) return 0;
+  if (in_mem == GKB_DEVICE) {
+    *dev = src;
+    return 0;
+  }
+  int rc = buf.ensure(bytes);
+  if (rc) return rc;
+  GKB_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, f->stream));
+  *dev = buf.p;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gkb_update(gkb_filter* f, int steps, const double* y, int y_shared, const double* u, int in_mem,
+               const gkb_outputs* out) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  const HostModel& hm = f->hm;
+  if (hm.kind == GKB_HYBRID || hm.kind == GKB_SRIF) return fail(GKB_ERR_ARG, "gkb_update: handle is an NLDKF, use gkb_nl_run");
+  if (steps < 1) return fail(GKB_ERR_ARG, "steps must be >= 1");
+  if (!y) return fail(GKB_ERR_DIMS, "measurement (y) is NULL");  // checkMatDims(measurement, H) vanilla.go:133-135
+  if (hm.need_ctrl && !u) return fail(GKB_ERR_DIMS, "dimensions must agree: control (u) is required because G is not nil");
+  if ((hm.kind == GKB_VANILLA || hm.kind == GKB_PREDICTOR || hm.kind == GKB_SQRT) && hm.m_r != hm.m)
+    return fail(GKB_ERR_DIMS, "dimensions must agree: H has %d rows but R is %dx%d", hm.m, hm.m_r, hm.m_r);
+  if (hm.kind == GKB_INFORMATION && hm.rinv_dim != 1 && hm.rinv_dim != hm.m)
+    return fail(GKB_ERR_DIMS, "dimensions must agree: H has %d rows but inv(R) is %dx%d", hm.m, hm.rinv_dim, hm.rinv_dim);
+  int rc = 0;
+  if (cudaSetDevice(f->device) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaSetDevice failed");
+  const int n = hm.n, m = hm.m;
+  LtiIo io;
+  memset(&io, 0, sizeof io);
+  io.nf = f->nf;
+  io.steps = steps;
+  io.step0 = f->step;
+  io.vec = f->vec.as<double>();
+  io.mat = f->mat.as<double>();
+  const void* dy = nullptr;
+  const void* du = nullptr;
+  const size_t ybytes = sizeof(double) * (size_t)steps * m * (y_shared ? 1 : f->nf);
+  if ((rc = stage_in(f, f->in_y, y, ybytes, in_mem, &dy))) return rc;
+  if (u && hm.c > 0)
+    if ((rc = stage_in(f, f->in_u, u, sizeof(double) * (size_t)steps * hm.c, in_mem, &du))) return rc;
+  io.y = static_cast<const double*>(dy);
+  io.y_shared = y_shared;
+  io.u = static_cast<const double*>(du);
+  io.w = f->has_w ? f->replay_w.as<double>() : nullptr;
+  io.v = f->has_v ? f->replay_v.as<double>() : nullptr;
+  io.replay_steps = f->replay_steps;
+  const int innov_len = (hm.kind == GKB_INFORMATION) ? n : m;
+  OutPlan pl;
+  if ((rc = plan_outputs(f, out, steps, innov_len, pl))) return rc;
+  io.every_step = out ? out->every_step : 0;
+  io.o_state = pl.state; io.o_meas = pl.meas; io.o_innov = pl.innov; io.o_covar = pl.covar;
+  io.o_pred = pl.pred; io.o_gain = pl.gain; io.o_obsdev = nullptr;
+  io.status = f->status.as<int32_t>();
+  const bool sync = !(in_mem == GKB_DEVICE && (!out || out->mem == GKB_DEVICE));
+  Timer tm(f->stream);
+  rc = launch_lti_update(hm, io, f->stream);
+  if (rc) return fail(rc, "no kernel for kind=%d n=%d m=%d", hm.kind, n, m);
+  tm.stop(1, sync);
+  GKB_CUDA(cudaGetLastError());
+  f->step += steps;
+  if ((rc = copy_back(f, out, pl))) return rc;
+  if (sync) GKB_CUDA(cudaStreamSynchronize(f->stream));
+  return 0;
+}
+
+int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi, int phi_shared,
+               const double* Htilde, int h_shared, const double* real_obs, const double* computed_obs,
+               const double* Gamma, int in_mem, const gkb_outputs* out) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  const HostModel& hm = f->hm;
+  if (hm.kind != GKB_HYBRID && hm.kind != GKB_SRIF) return fail(GKB_ERR_ARG, "gkb_nl_run: handle is an LDKF, use gkb_update");
+  if (steps < 1) return fail(GKB_ERR_ARG, "steps must be >= 1");
+  if (!Phi) return fail(GKB_ERR_LOCKED, "kf is locked (call Prepare() first): Phi is NULL");  // hybrid.go:105-107
+  bool any_meas = (flags == nullptr);
+  bool any_snc = false;
+  std::vector<uint8_t> hflags;
+  if (flags) {
+    if (in_mem == GKB_DEVICE) {
+      hflags.resize(steps);
+      GKB_CUDA(cudaMemcpy(hflags.data(), flags, steps, cudaMemcpyDeviceToHost));
+    } else {
+      hflags.assign(flags, flags + steps);
+    }
+    for (int k = 0; k < steps; ++k) {
+      any_meas = any_meas || (hflags[k] & GKB_F_MEAS);
+      any_snc = any_snc || (hflags[k] & GKB_F_SNC);
+    }
+  }
+  if (any_meas && (!Htilde || !real_obs || !computed_obs))
+    return fail(GKB_ERR_DIMS, "dimensions must agree: Update epochs need Htilde, real and computed observations");
+  if (any_snc && hm.kind == GKB_HYBRID && (!Gamma || hm.q == 0))
+    return fail(GKB_ERR_DIMS, "SNC epochs need Gamma and a q x q process noise matrix");
+  if (cudaSetDevice(f->device) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaSetDevice failed");
+  const int n = hm.n, m = hm.m;
+  int rc;
+  NlIo io;
+  memset(&io, 0, sizeof io);
+  io.nf = f->nf;
+  io.steps = steps;
+  io.vec = f->vec.as<double>();
+  io.mat = f->mat.as<double>();
+  const void *dfl = nullptr, *dphi = nullptr, *dh = nullptr, *dr = nullptr, *dc = nullptr, *dg = nullptr;
+  if ((rc = stage_in(f, f->in_a, flags, (size_t)steps, in_mem, &dfl))) return rc;
+  if ((rc = stage_in(f, f->in_b, Phi, sizeof(double) * (size_t)steps * n * n * (phi_shared ? 1 : f->nf), in_mem, &dphi))) return rc;
+  if ((rc = stage_in(f, f->in_c, Htilde, sizeof(double) * (size_t)steps * m * n * (h_shared ? 1 : f->nf), in_mem, &dh))) return rc;
+  if ((rc = stage_in(f, f->in_d, real_obs, sizeof(double) * (size_t)steps * m * f->nf, in_mem, &dr))) return rc;
+  if ((rc = stage_in(f, f->in_e, computed_obs, sizeof(double) * (size_t)steps * m * f->nf, in_mem, &dc))) return rc;
+  if (hm.kind == GKB_HYBRID && Gamma && hm.q > 0)
+    if ((rc = stage_in(f, f->in_f, Gamma, sizeof(double) * (size_t)steps * n * hm.q, in_mem, &dg))) return rc;
+  io.flags = static_cast<const uint8_t*>(dfl);
+  io.Phi = static_cast<const double*>(dphi);
+  io.phi_shared = phi_shared;
+  io.Htilde = static_cast<const double*>(dh);
+  io.h_shared = h_shared;
+  io.real_obs = static_cast<const double*>(dr);
+  io.computed_obs = static_cast<const double*>(dc);
+  io.Gamma = static_cast<const double*>(dg);
+  const int innov_len = (hm.kind == GKB_SRIF) ? n : m;
+  OutPlan pl;
+  if ((rc = plan_outputs(f, out, steps, innov_len, pl))) return rc;
+  io.every_step = out ? out->every_step : 0;
+  io.o_state = pl.state; io.o_meas = pl.meas; io.o_innov = pl.innov; io.o_covar = pl.covar;
+  io.o_pred = pl.pred; io.o_gain = pl.gain; io.o_obsdev = pl.obsdev;
+  io.status = f->status.as<int32_t>();
+  const bool sync = !(in_mem == GKB_DEVICE && (!out || out->mem == GKB_DEVICE));
+  Timer tm(f->stream);
+  rc = launch_nl_run(hm, io, f->stream);
+  if (rc) return fail(rc, "no kernel for kind=%d n=%d m=%d", hm.kind, n, m);
+  tm.stop(1, sync);
+  GKB_CUDA(cudaGetLastError());
+  f->step += steps;
+  if ((rc = copy_back(f, out, pl))) return rc;
+  if (sync) GKB_CUDA(cudaStreamSynchronize(f->stream));
+  return 0;
+}
+
+// ---- Monte Carlo + chi-square ------------------------------------------------------------------------
+
+namespace {
+struct McScratch {
+  DevBuf partial, out, u, w, v;
+  int device = -1;
+};
+thread_local McScratch g_mc;
+}  // namespace
+
+int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
+  if (!cfg || !out) return fail(GKB_ERR_ARG, "NULL argument");
+  if (!cfg->with_nees && !cfg->with_nis)
+    return fail(GKB_ERR_ARG, "Chi Square requires either NEES or NIS or both");  // chisquare.go:17-19
+  if (cfg->kind != GKB_VANILLA && cfg->kind != GKB_INFORMATION && cfg->kind != GKB_SQRT)
+    return fail(GKB_ERR_ARG, "tested filter kind %d is not an LDKF kind", cfg->kind);
+  const int n = cfg->n, m = cfg->m, c = cfg->c, steps = cfg->steps;
+  if (!gkb_shape_supported(cfg->kind, n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", n, m);
+  if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
+  if (cfg->trials < 1 || steps < 1) return fail(GKB_ERR_ARG, "trials and steps must be >= 1");
+  if (!cfg->F || !cfg->H || !cfg->Q || !cfg->R || !cfg->x0_truth || !cfg->x0_filter || !cfg->P0)
+    return fail(GKB_ERR_ARG, "NULL model array");
+  if (cfg->kind == GKB_INFORMATION && cfg->with_nis && n != m)
+    return fail(GKB_ERR_DIMS, "NIS of an information filter multiplies an m x m matrix by the n-vector Innovation() (information.go:272-274)");
+  if (cfg->noise_mode == GKB_NOISE_REPLAY && (!cfg->w || !cfg->v)) return fail(GKB_ERR_ARG, "replay noise needs w and v");
+  int rc = check_device(cfg->device);
+  if (rc) return rc;
+  cudaStream_t s = cudaStreamLegacy;
+  if (g_mc.device != cfg->device) {
+    g_mc = McScratch();
+    g_mc.device = cfg->device;
+  }
+  HostModel hm;
+  memset(&hm, 0, sizeof hm);
+  hm.kind = cfg->kind; hm.n = n; hm.m = m; hm.c = c; hm.m_r = m; hm.rinv_dim = m;
+  memcpy(hm.F, cfg->F, sizeof(double) * n * n);
+  if (cfg->G && c > 0) memcpy(hm.G, cfg->G, sizeof(double) * n * c);
+  hm.need_ctrl = !(cfg->G == nullptr || c == 0 || is_nil(cfg->G, n * c));
+  memcpy(hm.H, cfg->H, sizeof(double) * m * n);
+  sym_from_upper(hm.Q, cfg->Q, n);
+  sym_from_upper(hm.R, cfg->R, m);
+  McIo io;
+  memset(&io, 0, sizeof io);
+  sym_from_upper(io.P0, cfg->P0, n);
+  memcpy(io.x0_truth, cfg->x0_truth, sizeof(double) * n);
+  memcpy(io.x0_filter, cfg->x0_filter, sizeof(double) * n);
+  int ops = kOpSqrtQ | kOpSqrtR;  // AWGN colouring (noise.go:146-153) and the sqrt filter's model
+  if (cfg->kind == GKB_INFORMATION) ops |= kOpFinv | kOpQinv | kOpRinv | (cfg->info_raw_init ? 0 : kOpFromState);
+  if (cfg->kind == GKB_SQRT) ops |= kOpCholA0;
+  rc = launch_model_setup(hm, ops, io.x0_filter, io.P0, s);
+  if (rc) return fail(rc, "model setup failed (%d)", rc);
+  memcpy(io.LQ, hm.sqrtQ, sizeof(double) * n * n);
+  memcpy(io.LR, hm.sqrtR, sizeof(double) * m * m);
+  if (cfg->noise_mode == GKB_NOISE_PHILOX) {
+    for (int i = 0; i < n * n; ++i)
+      if (!std::isfinite(io.LQ[i])) return fail(GKB_ERR_ARG, "process noise invalid: Q is not positive definite (noise.go:149-151)");
+    for (int i = 0; i < m * m; ++i)
+      if (!std::isfinite(io.LR[i])) return fail(GKB_ERR_ARG, "measurement noise invalid: R is not positive definite (noise.go:154-156)");
+  }
+  io.trials = cfg->trials;
+  io.trial_offset = cfg->trial_offset;
+  io.steps = steps;
+  io.noise_mode = cfg->noise_mode;
+  io.seed = cfg->seed;
+  io.with_nees = cfg->with_nees;
+  io.with_nis = cfg->with_nis;
+  io.want_xstats = (out->sum_d || out->sum_dd || out->x_ref) ? 1 : 0;
+  const int cols = mc_cols(n, io.want_xstats);
+  if (cfg->controls && c > 0 && hm.need_ctrl) {
+    if ((rc = g_mc.u.ensure(sizeof(double) * (size_t)steps * c))) return rc;
+    GKB_CUDA(cudaMemcpyAsync(g_mc.u.p, cfg->controls, sizeof(double) * (size_t)steps * c, cudaMemcpyHostToDevice, s));
+    io.u = g_mc.u.as<double>();
+  }
+  if (cfg->noise_mode == GKB_NOISE_REPLAY) {
+    if (cfg->noise_mem == GKB_DEVICE) {
+      io.w = cfg->w;
+      io.v = cfg->v;
+    } else {
+      const size_t wb = sizeof(double) * (size_t)steps * n * cfg->trials, vb = sizeof(double) * (size_t)steps * m * cfg->trials;
+      if ((rc = g_mc.w.ensure(wb))) return rc;
+      if ((rc = g_mc.v.ensure(vb))) return rc;
+      GKB_CUDA(cudaMemcpyAsync(g_mc.w.p, cfg->w, wb, cudaMemcpyHostToDevice, s));
+      GKB_CUDA(cudaMemcpyAsync(g_mc.v.p, cfg->v, vb, cudaMemcpyHostToDevice, s));
+      io.w = g_mc.w.as<double>();
+      io.v = g_mc.v.as<double>();
+    }
+  }
+  // optional dumps: device pointers pass through, host pointers are staged
+  DevBuf d_tx, d_ty, d_nw, d_nv, d_st;
+  const size_t txb = sizeof(double) * (size_t)steps * n * cfg->trials, tyb = sizeof(double) * (size_t)steps * m * cfg->trials;
+  auto stage_out = [&](double* user, DevBuf& buf, size_t bytes, double** dev) -> int {
+    *dev = nullptr;
+    if (!user) return 0;
+    if (out->mem == GKB_DEVICE) { *dev = user; return 0; }
+    int r = buf.ensure(bytes);
+    if (r) return r;
+    *dev = buf.as<double>();
+    return 0;
+  };
+  if ((rc = stage_out(out->truth_x, d_tx, txb, &io.truth_x))) return rc;
+  if ((rc = stage_out(out->truth_y, d_ty, tyb, &io.truth_y))) return rc;
+  if ((rc = stage_out(out->noise_w, d_nw, txb, &io.noise_w))) return rc;
+  if ((rc = stage_out(out->noise_v, d_nv, tyb, &io.noise_v))) return rc;
+  if (out->status) {
+    if (out->mem == GKB_DEVICE) io.status = out->status;
+    else {
+      if ((rc = d_st.ensure(sizeof(int32_t) * cfg->trials))) return rc;
+      io.status = d_st.as<int32_t>();
+    }
+    GKB_CUDA(cudaMemsetAsync(io.status, 0, sizeof(int32_t) * cfg->trials, s));
+  }
+  const int max_grid = mc_max_grid(cfg->device);
+  const size_t pbytes = sizeof(double) * (size_t)max_grid * steps * cols;
+  if ((rc = g_mc.partial.ensure(pbytes))) return rc;
+  if ((rc = g_mc.out.ensure(sizeof(double) * (size_t)steps * cols))) return rc;
+  io.partial = g_mc.partial.as<double>();
+  const bool sync = out->mem != GKB_DEVICE;
+  Timer tm(s);
+  if (steps > kMcChunk) GKB_CUDA(cudaMemsetAsync(io.partial, 0, pbytes, s));  // chunked flush accumulates into the rows
+  int grid = 0;
+  tm.main_begin();
+  rc = launch_mc(hm, io, cfg->device, &grid, s);
+  tm.main_end();
+  if (rc) return fail(rc, "no Monte Carlo kernel for kind=%d n=%d m=%d", hm.kind, n, m);
+  const double scale = out->sums_only ? 1.0 : 1.0 / (double)cfg->trials;  // stat.Mean, chisquare.go:85-92
+  launch_mc_finish(io.partial, grid, steps, cols, scale, g_mc.out.as<double>(), s);
+  tm.stop(2, sync);
+  GKB_CUDA(cudaGetLastError());
+  const cudaMemcpyKind back = out->mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const double* o = g_mc.out.as<double>();
+  const size_t sb = sizeof(double) * (size_t)steps;
+  if (out->nis) GKB_CUDA(cudaMemcpyAsync(out->nis, o, sb, back, s));
+  if (out->nees) GKB_CUDA(cudaMemcpyAsync(out->nees, o + steps, sb, back, s));
+  if (io.want_xstats) {
+    // device layout [col][steps] -> user layout [steps][n] (small: transposed on the host)
+    if (out->mem == GKB_DEVICE) return fail(GKB_ERR_UNSUPPORTED, "sum_d / sum_dd / x_ref are host-only outputs");
+    std::vector<double> tmp((size_t)steps * 3 * n);
+    GKB_CUDA(cudaMemcpyAsync(tmp.data(), o + (size_t)kMcBaseCols * steps, sizeof(double) * steps * 3 * n, cudaMemcpyDeviceToHost, s));
+    GKB_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < steps; ++k)
+      for (int i = 0; i < n; ++i) {
+        if (out->sum_d) out->sum_d[(size_t)k * n + i] = tmp[(size_t)i * steps + k];
+        if (out->sum_dd) out->sum_dd[(size_t)k * n + i] = tmp[(size_t)(n + i) * steps + k];
+        if (out->x_ref) out->x_ref[(size_t)k * n + i] = tmp[(size_t)(2 * n + i) * steps + k];
+      }
+  }
+  if (out->mem == GKB_HOST) {
+    if (out->truth_x) GKB_CUDA(cudaMemcpyAsync(out->truth_x, io.truth_x, txb, cudaMemcpyDeviceToHost, s));
+    if (out->truth_y) GKB_CUDA(cudaMemcpyAsync(out->truth_y, io.truth_y, tyb, cudaMemcpyDeviceToHost, s));
+    if (out->noise_w) GKB_CUDA(cudaMemcpyAsync(out->noise_w, io.noise_w, txb, cudaMemcpyDeviceToHost, s));
+    if (out->noise_v) GKB_CUDA(cudaMemcpyAsync(out->noise_v, io.noise_v, tyb, cudaMemcpyDeviceToHost, s));
+    if (out->status) GKB_CUDA(cudaMemcpyAsync(out->status, io.status, sizeof(int32_t) * cfg->trials, cudaMemcpyDeviceToHost, s));
+    GKB_CUDA(cudaStreamSynchronize(s));
+  }
+  d_tx.release(); d_ty.release(); d_nw.release(); d_nv.release(); d_st.release();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// engine_internal.h -- host runtime <-> kernel launchers (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gokalman_b200.h"
+
+namespace gkb {
+
+// (n, m) shapes with compiled one-filter-per-thread kernels.
+#define GKB_FOR_EACH_SHAPE(X) \
+  X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 3) X(5, 1) X(5, 2) X(6, 1) X(6, 2) X(6, 3)
+
+constexpr int kThreads = 128;  // threads per CTA for the register kernels
+
+// Host copy of everything a filter handle knows about its model (row-major, full matrices).
+struct HostModel {
+  int kind, n, m, c, q;
+  int m_r;        // dimension of R as last set (SetNoise may change it independently of H)
+  int need_ctrl;  // !IsNil(G) at construction
+  int rinv_dim;   // information: dimension of Rinv fixed at construction
+  int non_tri_r;
+  double F[GKB_MAX_N * GKB_MAX_N];
+  double G[GKB_MAX_N * GKB_MAX_C];
+  double H[GKB_MAX_M * GKB_MAX_N];
+  double Q[GKB_MAX_N * GKB_MAX_N];
+  double R[GKB_MAX_M * GKB_MAX_M];
+  double Finv[GKB_MAX_N * GKB_MAX_N];
+  double Qinv[GKB_MAX_N * GKB_MAX_N];
+  double Rinv[GKB_MAX_M * GKB_MAX_M];
+  double sqrtQ[GKB_MAX_N * GKB_MAX_N];
+  double sqrtR[GKB_MAX_M * GKB_MAX_M];
+  double L[GKB_MAX_M * GKB_MAX_M];
+};
+
+// Device-side I/O of a batched LDKF update launch (all pointers are device pointers).
+struct LtiIo {
+  int64_t nf;
+  int steps;
+  int step0;  // filter step counter at entry: index into the replay noise
+  double* vec;  // [n][nf]
+  double* mat;  // [n*n][nf]
+  const double* y;
+  int y_shared;
+  const double* u;  // [steps][c] or nullptr
+  const double* w;  // replay noise [replay_steps][n][nf] or nullptr
+  const double* v;  // [replay_steps][m_v][nf] or nullptr
+  int replay_steps;
+  int every_step;
+  double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain, *o_obsdev;
+  int32_t* status;
+};
+
+struct NlIo {
+  int64_t nf;
+  int steps;
+  double* vec;
+  double* mat;
+  const uint8_t* flags;  // [steps]
+  const double* Phi;
+  int phi_shared;
+  const double* Htilde;
+  int h_shared;
+  const double* real_obs;
+  const double* computed_obs;
+  const double* Gamma;  // [steps][n*q] shared or nullptr
+  int every_step;
+  double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain, *o_obsdev;
+  int32_t* status;
+};
+
+struct McIo {
+  int64_t trials;
+  int64_t trial_offset;
+  int steps;
+  const double* u;  // device [steps][c] or nullptr
+  int noise_mode;
+  unsigned long long seed;
+  const double* w;  // replay [steps][n][trials]
+  const double* v;  // replay [steps][m][trials]
+  int with_nees, with_nis;
+  double* partial;  // [grid][steps][kMcCols] per-CTA partial sums
+  int want_xstats;
+  double *truth_x, *truth_y, *noise_w, *noise_v;
+  int32_t* status;
+  double x0_truth[GKB_MAX_N];
+  double x0_filter[GKB_MAX_N];
+  double P0[GKB_MAX_N * GKB_MAX_N];
+  double LQ[GKB_MAX_N * GKB_MAX_N];  // chol_lower(Q): colours the process noise
+  double LR[GKB_MAX_M * GKB_MAX_M];
+};
+// columns of McIo::partial per step: NIS, NEES, then sum d_i (n), sum d_i^2 (n), xref_i (n), d = x - xref
+constexpr int kMcBaseCols = 2;
+constexpr int kMcChunk = 256;  // steps accumulated in shared memory between flushes to McIo::partial
+inline int mc_cols(int n, int want_xstats) { return kMcBaseCols + (want_xstats ? 3 * n : 0); }
+
+// ---- launchers (each returns a gkb_status; GKB_ERR_UNSUPPORTED when the shape is not compiled) ----
+// One-thread device kernel for the constructor-time algebra (the same templates the filters use).
+enum SetupOps {
+  kOpFinv = 1,        // Finv = inv(F)                       information.go:38-41,117-123
+  kOpQinv = 2,        // Qinv = inv(Q)                       information.go:43-46
+  kOpRinv = 4,        // Rinv = inv(R)                       information.go:47-50
+  kOpSqrtQ = 8,       // sqrtQ = chol_lower(Q)               squareroot.go:102-105, distmv.NewNormal
+  kOpSqrtR = 16,      // sqrtR = chol_lower(R)               squareroot.go:107-110, srif.go:39-41
+  kOpFromState = 32,  // A0 = inv(P0) or 0, x0 = A0 x0       information.go:65-81
+  kOpCholA0 = 64,     // A0 = chol_lower(P0)                 squareroot.go:35-40
+  kOpSrifInit = 128   // A0 = chol(diag(1/P0_ii)), x0 = A0 x0, check inv(L)   srif.go:20-45
+};
+// x0 [n] and A0 [n*n] are host arrays, updated in place where an op says so.  Dispatches on
+// (hm.n, hm.m_r).  Returns a gkb_status (GKB_ERR_SINGULAR_R when NewSRIF's inverse of L fails).
+int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStream_t s);
+int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s);
+int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s);
+// Upper bound on the CTAs launch_mc will use (rows of McIo::partial to allocate, zero-filled).
+int mc_max_grid(int device);
+// Picks a persistent grid (SM count x resident CTAs per SM, capped by the work) and launches.
+int launch_mc(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_finish(const double* partial, int grid, int steps, int cols, double scale, double* out_cols,
+                     cudaStream_t s);
+
+}  // namespace gkb

@@ -1,0 +1,61 @@
+// philox.cuh -- counter-based Philox4x32-10 (Salmon et al., SC'11) + Box-Muller, device side.
+//
+// Replaces noise.go AWGN (noise.go:109-159), which draws from a time-seeded math/rand stream and
+// is irreproducible by design.  Here the standard normals of (trial, step) are a pure function of
+// (seed, global trial index, step): normals 4b..4b+3 come from Philox block
+//     counter = (trial_lo, trial_hi, step, b),  key = (seed_lo, seed_hi)
+// with u = (word + 0.5) * 2^-32 and (z0, z1) = sqrt(-2 ln u0) * (cos, sin)(2 pi u1).
+// oracle/gko.c gko_philox_normals restates the same stream on the CPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gkb {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double& z0, double& z1) {
+  double u0 = ((double)a + 0.5) * 2.3283064365386963e-10;
+  double u1 = ((double)b + 0.5) * 2.3283064365386963e-10;
+  double r = sqrt(-2.0 * log(u0));
+  double s, c;
+  sincospi(2.0 * u1, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// COUNT standard normals for (seed, trial, step).
+template <int COUNT>
+__device__ __forceinline__ void philox_normals(uint64_t seed, uint64_t trial, uint32_t step, double (&z)[COUNT]) {
+  constexpr int BLOCKS = (COUNT + 3) / 4;
+#pragma unroll
+  for (int b = 0; b < BLOCKS; ++b) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), step, (uint32_t)b, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), o);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (4 * b + 2 * p < COUNT) {
+        double z0, z1;
+        box_muller(o[2 * p], o[2 * p + 1], z0, z1);
+        z[4 * b + 2 * p] = z0;
+        if (4 * b + 2 * p + 1 < COUNT) z[4 * b + 2 * p + 1] = z1;
+      }
+    }
+  }
+}
+
+}  // namespace gkb

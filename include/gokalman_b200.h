@@ -1,0 +1,219 @@
+/* gokalman_b200.h -- C-ABI of the B200-native batched Kalman-filter engine.
+ *
+ * The reference (ChristopherRabotin/gokalman) is a pure-Go library with no FFI; its extension
+ * points are the Go interfaces LDKF / NLDKF (kalman.go:35-60), Estimate (kalman.go:64-72) and
+ * Noise (noise.go:13-20).  This header is the boundary a cgo shim binds to put hand-written
+ * sm_100a kernels behind those interfaces (INTEGRATION.md shows the shim).  Each entry point cites
+ * the reference method it replaces.
+ *
+ * One handle = a batch of `n_filters` independent filters that share one model, advanced in
+ * lockstep; n_filters = 1 is the drop-in for a single Go filter object.  Plain pointers and sizes
+ * only.  Every call returns 0 on success or a negative gkb_status; gkb_last_error() gives the
+ * message of the calling thread's last failure.  A handle must be used by one host thread at a
+ * time (the Go filters are not goroutine-safe either: vanilla.go:217-218).  There is no CPU
+ * fallback: every call fails with GKB_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Array layout ("SoA"): a per-filter quantity with C components over S steps is
+ * double[S][C][n_filters] (filter index fastest), so that a warp's loads are coalesced; with
+ * n_filters = 1 this is the ordinary row-major [S][C].  Matrices are row-major (n x n -> n*n
+ * components).  All arithmetic is FP64.
+ */
+#ifndef GOKALMAN_B200_H
+#define GOKALMAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKB_MAX_N 8  /* one-filter-per-thread register kernels */
+#define GKB_MAX_M 3
+#define GKB_MAX_C 4
+#define GKB_MAX_Q 3
+
+typedef enum gkb_kind {
+  GKB_VANILLA = 0,     /* NewVanilla                vanilla.go:21-40    */
+  GKB_PREDICTOR = 1,   /* NewPurePredictorVanilla   vanilla.go:43-62    */
+  GKB_INFORMATION = 2, /* NewInformation[FromState] information.go:20-81 */
+  GKB_SQRT = 3,        /* NewSquareRoot             squareroot.go:21-50 */
+  GKB_HYBRID = 4,      /* NewHybridKF               hybrid.go:23-34     */
+  GKB_SRIF = 5         /* NewSRIF                   srif.go:14-49       */
+} gkb_kind;
+
+typedef enum gkb_status {
+  GKB_OK = 0,
+  GKB_ERR_DIMS = -1,         /* checkMatDims failures (helper.go:100-130)                  */
+  GKB_ERR_SINGULAR_S = -2,   /* vanilla.go:164-167, hybrid.go:150-152                      */
+  GKB_ERR_ASYMMETRIC = -3,   /* vanilla.go:207-215 (never raised: P is kept symmetric)     */
+  GKB_ERR_LOCKED = -4,       /* hybrid.go:105-107, srif.go:102-104                         */
+  GKB_ERR_SINGULAR_PHI = -5, /* srif.go:112-114                                            */
+  GKB_ERR_SINGULAR_R = -6,   /* srif.go:228-230 (panic in the reference)                   */
+  GKB_ERR_NOISE_RANGE = -7,  /* noise.go:74-76,82-84 (panic in the reference)              */
+  GKB_ERR_UNSUPPORTED = -8,  /* shape outside the compiled kernel table                    */
+  GKB_ERR_CUDA = -9,         /* CUDA runtime failure / no device                           */
+  GKB_ERR_ARG = -10,
+  GKB_ERR_NONFINITE = -11    /* a filter produced a non-finite state or covariance         */
+} gkb_status;
+
+typedef struct gkb_filter gkb_filter;
+
+/* Where the arrays passed to a call live. */
+typedef enum gkb_mem { GKB_HOST = 0, GKB_DEVICE = 1 } gkb_mem;
+
+const char* gkb_version(void);
+const char* gkb_last_error(void);
+int gkb_device_count(void);
+/* 1 if (kind, n, m) has a compiled kernel. */
+int gkb_shape_supported(int kind, int n, int m);
+
+/* ---- construction: replaces NewVanilla / NewPurePredictorVanilla / NewInformation /
+ *      NewSquareRoot (LDKF, kalman.go:35-48).  x0 is [n] (shared by all filters) or, when
+ *      x0_per_filter != 0, [n][n_filters].  P0 is n x n (for GKB_INFORMATION x0/P0 are the
+ *      information state i0 and matrix I0).  G may be NULL (c = 0).  Arrays are host pointers and
+ *      are copied.  Only the upper triangle of P0, Q, R is read (mat64.SymDense semantics). */
+int gkb_create_lti(int kind, int n, int m, int c, int64_t n_filters, int device,
+                   const double* x0, int x0_per_filter, const double* P0,
+                   const double* F, const double* G, const double* H, const double* Q, const double* R,
+                   gkb_filter** out);
+/* NewInformationFromState (information.go:65-81): I0 = inv(P0) (zeros if singular), i0 = I0 x0. */
+int gkb_create_information_from_state(int n, int m, int c, int64_t n_filters, int device,
+                                      const double* x0, const double* P0, const double* F, const double* G,
+                                      const double* H, const double* Q, const double* R, gkb_filter** out);
+/* NewHybridKF (hybrid.go:23-34).  Q is q x q (used as Gamma Q Gamma^T), may be NULL when q = 0. */
+int gkb_create_hybrid(int n, int m, int q, int64_t n_filters, int device, const double* x0,
+                      int x0_per_filter, const double* P0, const double* Q, const double* R, gkb_filter** out);
+/* NewSRIF (srif.go:14-49).  P0 is assumed diagonal, as in the reference. */
+int gkb_create_srif(int n, int m, int64_t n_filters, int device, const double* x0, int x0_per_filter,
+                    const double* P0, const double* R, int non_tri_r, gkb_filter** out);
+void gkb_destroy(gkb_filter* f);
+
+/* ---- LDKF setters (kalman.go:41-46).  Same quirks as the reference: SetInputControl does not
+ *      re-evaluate needCtrl; on GKB_INFORMATION SetNoise does NOT refresh inv(Q)/inv(R)
+ *      (information.go:136-138); on GKB_SQRT it re-factors chol(Q), chol(R) (squareroot.go:100-114). */
+int gkb_set_state_transition(gkb_filter* f, const double* F);
+int gkb_set_input_control(gkb_filter* f, int c, const double* G);
+int gkb_set_measurement_matrix(gkb_filter* f, int m, const double* H);
+int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R);
+/* Replay noise: Noise.Process(k)/Measurement(k) return the uploaded vectors, indexed by the
+ * filter's step counter like noise.go BatchNoise (73-86) but keeping Q and R.  w is
+ * [steps][n][n_filters], v is [steps][m][n_filters] (either may be NULL = zeros), `mem` says
+ * where they live; they are copied.  Cleared by gkb_set_noise. */
+int gkb_set_replay_noise(gkb_filter* f, int steps, const double* w, const double* v, int mem);
+/* Reset() (vanilla.go:121-125): state <- initial estimate, step <- 0. */
+int gkb_reset(gkb_filter* f);
+/* Stream the handle's kernels and copies are enqueued on (a cudaStream_t; NULL = the legacy
+ * default stream, which is the default). */
+int gkb_set_stream(gkb_filter* f, void* stream);
+int64_t gkb_n_filters(const gkb_filter* f);
+int gkb_step(const gkb_filter* f);
+
+/* ---- outputs of an update call: the fields of Estimate (kalman.go:64-72), any pointer may be
+ *      NULL.  With every_step = 0 only the estimate after the last step is written ([C][N]);
+ *      with every_step = 1 all steps are ([steps][C][N]).  `mem` = GKB_HOST or GKB_DEVICE for all
+ *      pointers in the struct. */
+typedef struct gkb_outputs {
+  int mem;
+  int every_step;
+  double* state;      /* Estimate.State()           [n]                                        */
+  double* meas;       /* Estimate.Measurement()     [m]                                        */
+  double* innov;      /* Estimate.Innovation()      [m]  (information / SRIF: [n], see below)   */
+  double* covar;      /* Estimate.Covariance()      [n*n]                                      */
+  double* pred_covar; /* Estimate.PredCovariance()  [n*n]                                      */
+  double* gain;       /* Gain()                     [n*m]                                      */
+  double* obs_dev;    /* ObservationDev() (hybrid, SRIF) [m]                                   */
+  int32_t* status;    /* [n_filters]: 0 or the first gkb_status the filter hit                  */
+} gkb_outputs;
+/* innov has n components for GKB_INFORMATION (returns i+, information.go:272-274) and GKB_SRIF
+ * (returns b, srif.go:238-240). */
+
+/* ---- LDKF.Update(measurement, control), `steps` times (vanilla.go:128-220,
+ *      information.go:153-227, squareroot.go:129-274).  y is [steps][m][n_filters], or
+ *      [steps][m] when y_shared != 0; u is [steps][c] (shared) or NULL.  `in_mem` says where y/u
+ *      live.  The time loop runs inside one kernel launch with the state in registers. */
+int gkb_update(gkb_filter* f, int steps, const double* y, int y_shared, const double* u, int in_mem,
+               const gkb_outputs* out);
+
+/* ---- NLDKF (kalman.go:51-60): one call runs `steps` epochs of
+ *        Prepare(Phi, Htilde) [+ PreparePNT(Gamma)] + Update(real, computed)  or  Predict()
+ *      (hybrid.go:78-204, srif.go:82-160).  flags[k] (shared by all filters) selects per epoch:
+ *        GKB_F_MEAS  Update (else Predict);  GKB_F_EKF  EKF mode on (EnableEKF/DisableEKF);
+ *        GKB_F_SNC   PreparePNT(Gamma[k]) was called.
+ *      Phi [steps][n*n][N] (or [steps][n*n] if phi_shared), Htilde [steps][m*n][N] (or shared),
+ *      real_obs/computed_obs [steps][m][N], Gamma [steps][n*q] shared or NULL. */
+#define GKB_F_MEAS 1
+#define GKB_F_EKF 2
+#define GKB_F_SNC 4
+int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi, int phi_shared,
+               const double* Htilde, int h_shared, const double* real_obs, const double* computed_obs,
+               const double* Gamma, int in_mem, const gkb_outputs* out);
+
+/* Raw filter state: x-like vector [n][N] and matrix [n*n][N] (vanilla/hybrid: x, P; information:
+ * i, I; sqrt: x, S; SRIF: b, R).  Host pointers. */
+int gkb_get_state(const gkb_filter* f, double* vec, double* mat);
+int gkb_set_state(gkb_filter* f, const double* vec, const double* mat);
+
+/* ---- Monte Carlo + chi-square: NewMonteCarloRuns (montecarlo.go:92-119) fused with
+ *      NewChiSquare (chisquare.go:16-95).  Per trial: a pure-predictor Vanilla with AWGN noise
+ *      generates the truth (state, measurement) and a tested filter of `kind` consumes the
+ *      measurements; NEES and NIS are reduced over trials per step.  Nothing is stored unless an
+ *      optional dump pointer is given. */
+typedef enum gkb_noise_mode {
+  GKB_NOISE_PHILOX = 0, /* Philox4x32-10, key = seed, counter = (trial, step, block); Box-Muller */
+  GKB_NOISE_REPLAY = 1  /* uploaded, already coloured w [steps][n][trials], v [steps][m][trials]  */
+} gkb_noise_mode;
+
+typedef struct gkb_mc_config {
+  int kind;               /* tested filter: GKB_VANILLA, GKB_INFORMATION (from state) or GKB_SQRT */
+  int n, m, c;
+  const double *F, *G, *H, *Q, *R; /* host; model shared by the truth generator and the filter   */
+  const double* x0_truth; /* [n]                                                                */
+  const double* x0_filter;/* [n]                                                                */
+  const double* P0;       /* [n*n]                                                              */
+  int64_t trials;         /* trials run by THIS call (this GPU's shard)                         */
+  int64_t trial_offset;   /* global index of the first trial: Philox is keyed by global trial   */
+  int steps;
+  const double* controls; /* [steps][c] host, or NULL = zero controls (montecarlo.go:98-104)    */
+  int noise_mode;
+  uint64_t seed;
+  const double *w, *v;    /* GKB_NOISE_REPLAY only; location given by noise_mem                 */
+  int noise_mem;
+  int with_nees, with_nis;
+  int info_raw_init;      /* GKB_INFORMATION only: x0_filter / P0 already are (i0, I0) as given to
+                             NewInformation, instead of (x0, P0) as given to NewInformationFromState */
+  int device;
+} gkb_mc_config;
+
+typedef struct gkb_mc_outputs {
+  int mem;              /* location of every pointer below                                        */
+  int sums_only;        /* 1: write per-step SUMS over this call's trials (for a multi-GPU
+                           all-reduce); 0: write means = sum / trials (chisquare.go:85-92)        */
+  double* nis;          /* [steps]                                                               */
+  double* nees;         /* [steps]                                                               */
+  /* optional, host only: per-step statistics of the truth states over this call's trials for
+   * MonteCarloRuns.Mean / StdDev (montecarlo.go:18-59), always raw sums.  d = x - x_ref where
+   * x_ref is the noise-free trajectory:  mean = x_ref + sum_d / N,
+   * var = (sum_dd - sum_d^2 / N) / (N - 1).  Each is [steps][n]. */
+  double* sum_d;
+  double* sum_dd;
+  double* x_ref;
+  double* truth_x;      /* optional dump [steps][n][trials]                                      */
+  double* truth_y;      /* optional dump [steps][m][trials]                                      */
+  double* noise_w;      /* optional dump of the coloured noise actually used [steps][n][trials]  */
+  double* noise_v;      /* optional dump [steps][m][trials]                                      */
+  int32_t* status;      /* optional [trials]                                                     */
+} gkb_mc_outputs;
+
+int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out);
+
+/* Device time (ms, CUDA events on the launch stream) of the kernels launched by the last
+ * gkb_update / gkb_nl_run / gkb_mc_chisquare call on this thread, and how many kernels that was. */
+float gkb_last_kernel_ms(void);
+/* Same, for the dominant kernel alone (the fused Monte Carlo kernel without its memset/finish). */
+float gkb_last_main_kernel_ms(void);
+int gkb_last_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

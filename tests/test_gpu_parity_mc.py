@@ -1,0 +1,171 @@
+"""GPU parity, Monte Carlo + chi-square (montecarlo.go + chisquare.go fused kernel) against the oracle.
+
+Parity protocol: the reference's AWGN stream (Go ziggurat on a clock seed) cannot
+be reproduced, so the kernel DUMPS the coloured noise it generated from Philox and the oracle
+replays exactly those samples through its restatement of NewMonteCarloRuns + NewChiSquare.
+Tolerance 1e-10 relative to the array's max-abs."""
+import numpy as np
+import pytest
+
+import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _gpu():
+    import gokalman_b200 as gk
+    gk.load()
+    return gk
+
+
+def _mc_pair(gk, oracle, fxm, kind, trials, steps, controls, seed=0x5EED, trial_offset=0):
+    noise = gk.NewAWGN(fxm["Q"], fxm["R"], seed=seed)
+    mckf, _ = gk.NewPurePredictorVanilla(fxm["x0_truth"], fxm["P0"], fxm["F"], fxm["G"], fxm["H"], noise)
+    tested_noise = gk.NewNoiseless(fxm["Q"], fxm["R"])
+    ctor = {"vanilla": gk.NewVanilla, "information": gk.NewInformationFromState, "sqrt": gk.NewSquareRoot}[kind]
+    chikf, _ = ctor(fxm["x0"], fxm["P0"], fxm["F"], fxm["G"], fxm["H"], tested_noise)
+    runs = gk.NewMonteCarloRuns(trials, steps, fxm["H"].shape[0], controls, mckf, trial_offset=trial_offset)
+    with_nis = kind != "information"
+    nis, nees = gk.NewChiSquare(chikf, runs, controls, True, with_nis)
+    tx, ty, w, v = runs.Truth(with_noise=True)
+    okind = {"vanilla": oracle.VANILLA, "information": oracle.INFORMATION, "sqrt": oracle.SQRT}[kind]
+    ctrl = None
+    if controls is not None and len(controls) == steps:
+        ctrl = np.stack(controls)
+    ref = oracle.mc_chisquare(okind, fxm["F"], fxm["G"], fxm["H"], fxm["Q"], fxm["R"], fxm["x0_truth"], fxm["x0"],
+                              fxm["P0"], trials, steps, controls=ctrl,
+                              w=np.ascontiguousarray(w.transpose(2, 0, 1)), v=np.ascontiguousarray(v.transpose(2, 0, 1)),
+                              with_nees=True, with_nis=with_nis, want_truth=True, want_stats=True)
+    return dict(nis=nis, nees=nees, tx=tx, ty=ty, w=w, v=v, ref=ref, runs=runs)
+
+
+def _jerk3():
+    f = fx.jerk3()
+    f["x0_truth"] = f["x0"]
+    return f
+
+
+def _robot():
+    f = fx.robot_1d()
+    f["x0_truth"] = np.array([0.7, -0.4])  # "a random initial state" drawn once (examples/robot/main.go:28-30)
+    return f
+
+
+@pytest.mark.parametrize("kind", ["vanilla", "information", "sqrt"])
+def test_mc_chisquare_robot_matches_oracle(oracle, kind):
+    """examples/robot/main.go (n=2, m=1, cos controls), all three tested filter kinds (config 3)."""
+    gk = _gpu()
+    steps, trials = 120, 300
+    controls = list(fx.robot_controls(steps))
+    r = _mc_pair(gk, oracle, _robot(), kind, trials, steps, controls)
+    ref = r["ref"]
+    assert fx.scaled_err(r["tx"], ref["truth_x"].transpose(1, 2, 0)) <= TOL
+    assert fx.scaled_err(r["ty"], ref["truth_y"].transpose(1, 2, 0)) <= TOL
+    assert fx.scaled_err(r["nees"], ref["NEES"]) <= TOL, fx.scaled_err(r["nees"], ref["NEES"])
+    if kind != "information":
+        assert fx.scaled_err(r["nis"], ref["NIS"]) <= TOL
+
+
+def test_mc_chisquare_jerk3_matches_oracle(oracle):
+    """BASELINE config 2 shape (3-state jerk fixture of montecarlo_test.go:12-20, m=1, zero controls
+    from a single control vector), reduced trial count."""
+    gk = _gpu()
+    steps, trials = 300, 257  # > one 256-step chunk, ragged trial count
+    r = _mc_pair(gk, oracle, _jerk3(), "vanilla", trials, steps, [np.zeros(1)])
+    ref = r["ref"]
+    assert fx.scaled_err(r["nees"], ref["NEES"]) <= TOL
+    assert fx.scaled_err(r["nis"], ref["NIS"]) <= TOL
+    # MonteCarloRuns.Mean / StdDev (montecarlo.go:18-59)
+    for k in (0, 17, steps - 1):
+        assert fx.scaled_err(r["runs"].Mean(k), ref["mean"][k]) <= 1e-9
+        assert fx.scaled_err(r["runs"].StdDev(k), ref["std"][k]) <= 1e-7  # one-pass vs two-pass variance
+
+
+def test_philox_stream_matches_oracle(oracle):
+    """The device Philox4x32-10 + Box-Muller stream is the one the oracle restates: same integers,
+    normals equal to libm-vs-CUDA rounding (1e-13), keyed by the GLOBAL trial index."""
+    gk = _gpu()
+    f = _jerk3()
+    steps, trials, seed, off = 5, 64, 0xC0FFEE, 12345
+    noise = gk.NewAWGN(f["Q"], f["R"], seed=seed)
+    mckf, _ = gk.NewPurePredictorVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], noise)
+    runs = gk.NewMonteCarloRuns(trials, steps, 1, [np.zeros(1)], mckf, trial_offset=off)
+    _, _, w, v = runs.Truth(with_noise=True)
+    LQ, _ = oracle.chol_lower(f["Q"])
+    LR, _ = oracle.chol_lower(f["R"])
+    for t in (0, 31, 63):
+        for k in range(steps):
+            z = oracle.philox_normals(seed, off + t, k, 4)
+            assert np.max(np.abs(w[k, :, t] - LQ @ z[:3])) <= 1e-12 * np.max(np.abs(LQ))
+            assert abs(v[k, 0, t] - (LR @ z[3:])[0]) <= 1e-12
+
+
+def test_mc_sharding_invariance():
+    """8(e): trials shard across GPUs by contiguous ranges with Philox keyed by global trial id, so
+    the per-step SUMS of two half-shards add up to the full run's (to summation rounding)."""
+    gk = _gpu()
+    f = _jerk3()
+    steps, trials, seed = 64, 1000, 99
+
+    def sums(n_trials, offset):
+        noise = gk.NewAWGN(f["Q"], f["R"], seed=seed)
+        mckf, _ = gk.NewPurePredictorVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], noise)
+        chikf, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewNoiseless(f["Q"], f["R"]))
+        runs = gk.NewMonteCarloRuns(n_trials, steps, 1, [np.zeros(1)], mckf, trial_offset=offset)
+        nis, nees = gk.NewChiSquare(chikf, runs, [np.zeros(1)], True, True)
+        return nis * n_trials, nees * n_trials
+    full = sums(trials, 0)
+    a, b = sums(400, 0), sums(600, 400)
+    assert fx.scaled_err(a[0] + b[0], full[0]) <= 1e-12
+    assert fx.scaled_err(a[1] + b[1], full[1]) <= 1e-12
+
+
+def test_chisquare_philox_end_to_end_and_statistics(oracle):
+    """examples/robot/main.go:32-58 at a larger size.  (a) The whole PHILOX pipeline (device RNG,
+    colouring, truth, filter, NEES/NIS means) equals the oracle running its OWN restatement of the
+    same Philox stream (no noise hand-over): the only difference is libm vs CUDA log/sincos
+    rounding in Box-Muller, so 1e-9.  (b) Statistical sanity at 2e5 trials: NIS -> m.  (NEES does
+    not tend to n here: the reference pairs the state x_{k+1} with the measurement of x_k,
+    montecarlo.go:110-113 / vanilla.go:155-157 -- both sides reproduce that.)"""
+    gk = _gpu()
+    f = _robot()
+    f["x0_truth"] = np.zeros(2)
+    steps = 120
+    controls = list(fx.robot_controls(steps))
+
+    def gpu_run(trials, seed):
+        noise = gk.NewAWGN(f["Q"], f["R"], seed=seed)
+        mckf, _ = gk.NewPurePredictorVanilla(f["x0_truth"], f["P0"], f["F"], f["G"], f["H"], noise)
+        chikf, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewNoiseless(f["Q"], f["R"]))
+        runs = gk.NewMonteCarloRuns(trials, steps, 1, controls, mckf)
+        return gk.NewChiSquare(chikf, runs, controls, True, True)
+    nis, nees = gpu_run(4000, 2024)
+    ref = oracle.mc_chisquare(oracle.VANILLA, f["F"], f["G"], f["H"], f["Q"], f["R"], f["x0_truth"], f["x0"], f["P0"],
+                              4000, steps, controls=np.stack(controls), seed=2024, threads=4)
+    assert fx.scaled_err(nis, ref["NIS"]) <= 1e-9
+    assert fx.scaled_err(nees, ref["NEES"]) <= 1e-9
+    nis, nees = gpu_run(200000, 7)
+    assert nis.shape == nees.shape == (steps,)
+    assert np.all(np.isfinite(nees)) and np.all(nees > 0)
+    assert abs(np.mean(nis[40:]) - 1.0) < 0.02
+
+
+def test_chisquare_errors_mirror_reference():
+    """montecarlo_test.go:54-88"""
+    gk = _gpu()
+    f = _jerk3()
+    noise = gk.NewAWGN(f["Q"], f["R"], seed=1)
+    mckf, _ = gk.NewPurePredictorVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], noise)
+    with pytest.raises(ValueError):  # two control vectors for ten steps
+        gk.NewMonteCarloRuns(5, 10, 1, [np.zeros(1), np.zeros(1)], mckf)
+    notpred, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewNoiseless(f["Q"], f["R"]))
+    with pytest.raises(ValueError):  # not a pure predictor
+        gk.NewMonteCarloRuns(5, 10, 1, [np.zeros(1)], notpred)
+    runs = gk.NewMonteCarloRuns(5, 10, 1, [np.zeros(1)], mckf)
+    with pytest.raises(gk.GkbError):  # neither NEES nor NIS
+        gk.NewChiSquare(notpred, runs, [np.zeros(1)], False, False)
+    with pytest.raises(ValueError):  # too few controls
+        gk.NewChiSquare(notpred, runs, [np.zeros(1), np.zeros(1)], True, False)
+    nis, nees = gk.NewChiSquare(notpred, runs, [np.zeros(1)], True, True)
+    assert len(nis) == len(nees) == 10

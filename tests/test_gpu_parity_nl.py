@@ -1,0 +1,173 @@
+"""GPU parity, NLDKF kinds (HybridKF CKF/EKF/SNC and SRIF) against the CPU oracle, 1e-10."""
+import numpy as np
+import pytest
+
+import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _gpu():
+    import gokalman_b200 as gk
+    gk.load()
+    return gk
+
+
+def _od_streams(rng, n, m, nf, steps):
+    """Synthetic per-filter STM-like Phi (near identity, well conditioned) and measurement partials."""
+    Phi = np.eye(n)[None, :, :, None] + 0.02 * rng.standard_normal((steps, n, n, nf))
+    Ht = rng.standard_normal((steps, m, n, nf))
+    real = rng.standard_normal((steps, m, nf))
+    comp = real + 0.05 * rng.standard_normal((steps, m, nf))
+    return Phi, Ht, real, comp
+
+
+def _oracle_run(o, flags, Phi, Ht, real, comp, Gamma, f, F_MEAS, F_EKF, F_SNC):
+    ests = []
+    for k in range(len(flags)):
+        o.Prepare(Phi[k, :, :, f], Ht[k, :, :, f])
+        if flags[k] & F_EKF:
+            o.EnableEKF()
+        else:
+            o.DisableEKF()
+        if flags[k] & F_SNC:
+            o.PreparePNT(Gamma[k])
+        ests.append(o.UpdateNL(real[k, :, f], comp[k, :, f]) if flags[k] & F_MEAS else o.Predict())
+    return ests
+
+
+def _check(est, refs, fields, tag):
+    getters = {"state": "State", "meas": "Measurement", "innov": "Innovation", "covar": "Covariance",
+               "pred_covar": "PredCovariance", "gain": "Gain", "obs_dev": "ObservationDev"}
+    nf, steps = len(refs), len(refs[0])
+    for fld in fields:
+        g = getattr(est, getters[fld])()
+        for f in range(nf):
+            rows = []
+            for k in range(steps):
+                a = np.asarray(getattr(refs[f][k], getters[fld])())
+                rows.append(a)
+            width = max(r.size for r in rows)
+            ref = np.stack([np.pad(r.reshape(-1), (0, width - r.size)) for r in rows])
+            got = (g[..., f] if nf > 1 else g).reshape(steps, -1)[:, :width]
+            err = fx.scaled_err(got, ref)
+            assert err <= TOL, (tag, fld, f, err)
+
+
+@pytest.mark.parametrize("n,m,q", [(6, 2, 3), (4, 2, 2), (3, 1, 0), (6, 3, 3)])
+def test_hybrid_ckf_ekf_snc_matches_oracle(oracle, n, m, q):
+    """hybrid.go:104-204: Predict / CKF update / EKF update / SNC epochs mixed in one batched run
+    with per-filter Phi, Htilde and observations (BASELINE config 4 shape is n=6, m=2, q=3)."""
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS, F_EKF, F_SNC
+    rng = np.random.default_rng(42 + n + m)
+    nf, steps = 33, 48
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    P0 = np.diag(np.concatenate([np.full(n - n // 2, 10.0), np.full(n // 2, 1.0)]))
+    Q = np.diag(np.full(q, 1e-3)) if q else None
+    R = np.diag(np.full(m, 1e-2))
+    flags = np.zeros(steps, dtype=np.uint8)
+    for k in range(steps):
+        fl = F_MEAS if (k % 5 != 3) else 0        # every 5th epoch has no measurement -> Predict()
+        if k >= 15:
+            fl |= F_EKF                            # EKF after 15 epochs (hybrid_test.go:65,270-273)
+        if q and (fl & F_MEAS) and k % 2 == 0:
+            fl |= F_SNC
+        flags[k] = fl
+    Gamma = None
+    if q:
+        dt = 10.0
+        Gamma = np.zeros((steps, n, q))
+        for i in range(q):
+            Gamma[:, i, i] = dt * dt / 2
+            if n - n // 2 + i < n:
+                Gamma[:, n - n // 2 + i, i] = dt
+    class NoQ:  # a Noise without a process matrix (q = 0): SNC is never enabled
+        def ProcessMatrix(self):
+            return None
+
+        def MeasurementMatrix(self):
+            return R
+    kf, est0 = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R) if q else NoQ(), m, n_filters=nf)
+    est = kf.RunBatch(flags, Phi, Ht, real, comp, Gamma, every_step=True)
+    assert np.all(est.status == 0)
+    refs = []
+    for f in range(nf):
+        o = oracle.NewHybridKF(np.zeros(n), P0, Q, R, m)
+        refs.append(_oracle_run(o, flags, Phi, Ht, real, comp, Gamma, f, F_MEAS, F_EKF, F_SNC))
+    _check(est, refs, ["state", "covar", "pred_covar", "gain", "innov", "obs_dev"], "hybrid")
+
+
+@pytest.mark.parametrize("n,m", [(6, 2), (4, 2), (3, 1)])
+def test_srif_matches_oracle(oracle, n, m):
+    """srif.go:101-160 with per-filter Phi / Htilde; State(), Covariance(), PredCovariance() read-outs."""
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS, F_EKF, F_SNC
+    rng = np.random.default_rng(77 + n)
+    nf, steps = 21, 40
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    P0 = np.diag(np.concatenate([np.full(n - n // 2, 50.0), np.full(n // 2, 1.0)]))
+    R = np.diag(np.full(m, 1e-2))
+    flags = np.array([F_MEAS if (k % 4 != 2) else 0 for k in range(steps)], dtype=np.uint8)
+    kf, est0 = gk.NewSRIF(np.zeros(n), P0, m, False, gk.NewNoiseless(np.zeros((n, n)), R), n_filters=nf)
+    est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=True)
+    assert np.all(est.status == 0)
+    refs = []
+    for f in range(nf):
+        o = oracle.NewSRIF(np.zeros(n), P0, m, False, R)
+        refs.append(_oracle_run(o, flags, Phi, Ht, real, comp, None, f, F_MEAS, F_EKF, F_SNC))
+    _check(est, refs, ["state", "covar", "pred_covar", "innov", "obs_dev"], "srif")
+
+
+def test_srif_kats_on_device(oracle):
+    """srif_test.go:15-29 (est0 covariance == P0) and the one-step drop-in API."""
+    gk = _gpu()
+    x0 = np.array([0, 0.35, 0])
+    P0 = 10.0 * np.eye(3)
+    R = np.diag([(5e-3) ** 2, (5e-6) ** 2])
+    kf, est0 = gk.NewSRIF(x0, P0, 2, True, gk.NewNoiseless(np.zeros((6, 6)), R))
+    assert np.max(np.abs(est0.Covariance() - P0)) <= 1e-12
+    vec, mat = kf.GetState()
+    o = oracle.NewSRIF(x0, P0, 2, True, R)
+    rv, rm, _ = o.InitialEstimate().raw()
+    assert fx.scaled_err(vec[:, 0], rv) <= 1e-14 and fx.scaled_err(mat[:, :, 0], rm) <= 1e-14
+    with pytest.raises(gk.GkbError) as ei:  # locked until Prepare() (srif.go:102-104)
+        kf.Update(np.zeros(2), np.zeros(2))
+    assert ei.value.code == -4
+    with pytest.raises(NotImplementedError):
+        kf.SetNoise(gk.NewNoiseless(np.zeros((3, 3)), R))
+
+
+def test_hybrid_basic_lock_and_toggle(oracle):
+    """hybrid_test.go:15-54 TestHybridBasic: lock, EKF toggle, one Predict and one Update."""
+    gk = _gpu()
+    rng = np.random.default_rng(5)
+    n, m = 6, 2
+    P0 = np.diag([10, 10, 10, 1, 1, 1.0])
+    R = np.diag([1e-6, 1e-6])
+    Q = np.diag([1e-12] * 3)
+    kf, _ = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R), m)
+    with pytest.raises(gk.GkbError):
+        kf.Update(np.zeros(2), np.zeros(2))
+    assert not kf.EKFEnabled()
+    kf.EnableEKF()
+    assert kf.EKFEnabled()
+    kf.DisableEKF()
+    o = oracle.NewHybridKF(np.zeros(n), P0, Q, R, m)
+    Phi = np.eye(n) + 0.01 * rng.standard_normal((n, n))
+    Ht = rng.standard_normal((m, n))
+    kf.Prepare(Phi, None)
+    o.Prepare(Phi, None)
+    eg, eo = kf.Predict(), o.Predict()
+    assert fx.scaled_err(eg.Covariance(), eo.Covariance()) <= TOL
+    with pytest.raises(gk.GkbError):  # locked again after the call
+        kf.Predict()
+    kf.Prepare(Phi, Ht)
+    o.Prepare(Phi, Ht)
+    real, comp = np.array([1.0, -2.0]), np.array([0.9, -2.1])
+    eg, eo = kf.Update(real, comp), o.UpdateNL(real, comp)
+    for a, b in ((eg.State(), eo.State()), (eg.Covariance(), eo.Covariance()), (eg.Gain(), eo.Gain()),
+                 (eg.Innovation(), eo.Innovation()), (eg.ObservationDev(), eo.ObservationDev())):
+        assert fx.scaled_err(a, b) <= TOL
+    assert eg.IsWithinNσ(1e6)
