@@ -233,7 +233,7 @@ def run_ours_mc(args, rank, world, local):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = float(trials) * steps * world * n_e2e / (float(e2e_ms.item()) * 1e-3)
     h2d = 8 * (9 + 3 + 3 + 9 + 1 + 3 + 3 + 9 + steps * 1)  # F,G,H,Q,R,x0,x0,P0 + controls
-    d2h = 8 * 2 * steps + 4 * trials                          # NIS, NEES means + per-trial status words
+    d2h = 8 * 2 * steps + 4                                   # NIS, NEES means + the error word
     assert np.allclose(nis_h.mean(), nis_mean, rtol=1e-9), (nis_h.mean(), nis_mean)
 
     if rank != 0:

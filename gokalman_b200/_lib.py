@@ -48,7 +48,7 @@ class McOutputs(C.Structure):
     _fields_ = [("mem", C.c_int), ("sums_only", C.c_int),
                 ("nis", C.c_void_p), ("nees", C.c_void_p), ("sum_d", C.c_void_p), ("sum_dd", C.c_void_p), ("x_ref", C.c_void_p),
                 ("truth_x", C.c_void_p), ("truth_y", C.c_void_p), ("noise_w", C.c_void_p), ("noise_v", C.c_void_p),
-                ("status", C.c_void_p)]
+                ("status", C.c_void_p), ("first_error", C.c_void_p)]
 
 
 # every symbol include/gokalman_b200.h declares: (name, restype, argtypes)

@@ -691,7 +691,7 @@ class MonteCarloRuns:
             cfg.noise_mode, cfg.seed = _lib.NOISE_PHILOX, self.noise.seed
         return cfg
 
-    def _run(self, cfg, want_stats=False, want_truth=False, want_noise=False):
+    def _run(self, cfg, want_stats=False, want_truth=False, want_noise=False, want_status=False):
         n, m, steps, runs = cfg.n, cfg.m, cfg.steps, cfg.trials
         out = _lib.McOutputs()
         out.mem, out.sums_only = _lib.HOST, 0
@@ -707,8 +707,11 @@ class MonteCarloRuns:
         if want_noise:
             res["noise_w"], res["noise_v"] = np.zeros((steps, n, runs)), np.zeros((steps, m, runs))
             out.noise_w, out.noise_v = res["noise_w"].ctypes.data, res["noise_v"].ctypes.data
-        res["status"] = np.zeros(runs, dtype=np.int32)
-        out.status = res["status"].ctypes.data
+        res["first_error"] = np.zeros(1, dtype=np.int32)
+        out.first_error = res["first_error"].ctypes.data
+        if want_status:
+            res["status"] = np.zeros(runs, dtype=np.int32)
+            out.status = res["status"].ctypes.data
         _lib.check(_lib.load().gkb_mc_chisquare(C.byref(cfg), C.byref(out)))
         return res
 
@@ -789,7 +792,6 @@ def NewChiSquare(kf, runs, controls, withNEES, withNIS):
         res = runs._run(cfg)
     finally:
         runs.controls = saved
-    bad = res["status"][res["status"] != 0]
-    if bad.size:
-        raise GkbError(int(bad[0]), "%d trial(s) failed during Update" % bad.size)
+    if res["first_error"][0] != 0:  # the reference panics (chisquare.go:40-42)
+        raise GkbError(int(res["first_error"][0]), "a trial failed during Update")
     return res["NIS"], res["NEES"]

@@ -120,14 +120,22 @@ __global__ void fill_state_kernel(double* vec, double* mat, const double* x0, in
 }
 
 int check_device(int device) {
-  int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
-    return fail(GKB_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
-  if (device < 0 || device >= count) return fail(GKB_ERR_ARG, "device %d out of range (0..%d)", device, count - 1);
-  cudaDeviceProp p;
-  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaGetDeviceProperties failed");
-  if (p.major != 10)
-    return fail(GKB_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, p.major, p.minor);
+  // cudaGetDeviceProperties costs milliseconds: validate each device once per process.
+  static int verdict[64] = {0};  // 0 = unknown, 1 = ok
+  if (device < 0 || device >= 64) return fail(GKB_ERR_ARG, "device %d out of range", device);
+  if (verdict[device] != 1) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      return fail(GKB_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
+    if (device >= count) return fail(GKB_ERR_ARG, "device %d out of range (0..%d)", device, count - 1);
+    int major = 0, minor = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess)
+      return fail(GKB_ERR_CUDA, "cannot query device %d", device);
+    if (major != 10)
+      return fail(GKB_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, major, minor);
+    verdict[device] = 1;
+  }
   if (cudaSetDevice(device) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   return 0;
 }
@@ -145,7 +153,7 @@ struct gkb_filter {
   DevBuf replay_w, replay_v;
   int replay_steps = 0;
   bool has_w = false, has_v = false;
-  DevBuf in_y, in_u, in_a, in_b, in_c, in_d, in_e, in_f;  // staging for host inputs
+  DevBuf in_y, in_u, in_gu, in_a, in_b, in_c, in_d, in_e, in_f;  // staging for host inputs
   DevBuf o_state, o_meas, o_innov, o_covar, o_pred, o_gain, o_obsdev;
 };
 
@@ -213,7 +221,7 @@ static int finish_create(gkb_filter* f, const double* x0, int x0_per_filter, con
 static void destroy_filter(gkb_filter* f) {
   if (!f) return;
   cudaSetDevice(f->device);
-  DevBuf* bufs[] = {&f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u,
+  DevBuf* bufs[] = {&f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
                     &f->in_a, &f->in_b, &f->in_c, &f->in_d, &f->in_e, &f->in_f, &f->o_state, &f->o_meas, &f->o_innov,
                     &f->o_covar, &f->o_pred, &f->o_gain, &f->o_obsdev};
   for (DevBuf* b : bufs) b->release();
@@ -563,7 +571,11 @@ int gkb_update(gkb_filter* f, int steps, const double* y, int y_shared, const do
     if ((rc = stage_in(f, f->in_u, u, sizeof(double) * (size_t)steps * hm.c, in_mem, &du))) return rc;
   io.y = static_cast<const double*>(dy);
   io.y_shared = y_shared;
-  io.u = static_cast<const double*>(du);
+  if (du && hm.need_ctrl) {
+    if ((rc = f->in_gu.ensure(sizeof(double) * (size_t)steps * n))) return rc;
+    launch_gu(hm.G, n, hm.c, static_cast<const double*>(du), steps, f->in_gu.as<double>(), f->stream);
+    io.gu = f->in_gu.as<double>();
+  }
   io.w = f->has_w ? f->replay_w.as<double>() : nullptr;
   io.v = f->has_v ? f->replay_v.as<double>() : nullptr;
   io.replay_steps = f->replay_steps;
@@ -660,8 +672,16 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
 // ---- Monte Carlo + chi-square ------------------------------------------------------------------------
 
 namespace {
+struct McSetupCache {
+  bool valid = false;
+  int ops = 0;
+  HostModel in_hm, out_hm;
+  double in_x0f[GKB_MAX_N], out_x0f[GKB_MAX_N];
+  double in_P0[GKB_MAX_N * GKB_MAX_N], out_P0[GKB_MAX_N * GKB_MAX_N];
+};
 struct McScratch {
-  DevBuf partial, out, u, w, v;
+  DevBuf partial, out, u, gu, w, v, err;
+  McSetupCache setup;
   int device = -1;
 };
 thread_local McScratch g_mc;
@@ -706,8 +726,30 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   int ops = kOpSqrtQ | kOpSqrtR;  // AWGN colouring (noise.go:146-153) and the sqrt filter's model
   if (cfg->kind == GKB_INFORMATION) ops |= kOpFinv | kOpQinv | kOpRinv | (cfg->info_raw_init ? 0 : kOpFromState);
   if (cfg->kind == GKB_SQRT) ops |= kOpCholA0;
-  rc = launch_model_setup(hm, ops, io.x0_filter, io.P0, s);
-  if (rc) return fail(rc, "model setup failed (%d)", rc);
+  // The derived matrices depend only on the model: redo the setup kernel only when it changes.
+  {
+    McSetupCache& cs = g_mc.setup;
+    const bool same = cs.valid && cs.ops == ops && memcmp(&cs.in_hm, &hm, sizeof hm) == 0 &&
+                      memcmp(cs.in_x0f, io.x0_filter, sizeof io.x0_filter) == 0 &&
+                      memcmp(cs.in_P0, io.P0, sizeof io.P0) == 0;
+    if (!same) {
+      cs.valid = false;
+      cs.ops = ops;
+      cs.in_hm = hm;
+      memcpy(cs.in_x0f, io.x0_filter, sizeof io.x0_filter);
+      memcpy(cs.in_P0, io.P0, sizeof io.P0);
+      rc = launch_model_setup(hm, ops, io.x0_filter, io.P0, s);
+      if (rc) return fail(rc, "model setup failed (%d)", rc);
+      cs.out_hm = hm;
+      memcpy(cs.out_x0f, io.x0_filter, sizeof io.x0_filter);
+      memcpy(cs.out_P0, io.P0, sizeof io.P0);
+      cs.valid = true;
+    } else {
+      hm = cs.out_hm;
+      memcpy(io.x0_filter, cs.out_x0f, sizeof io.x0_filter);
+      memcpy(io.P0, cs.out_P0, sizeof io.P0);
+    }
+  }
   memcpy(io.LQ, hm.sqrtQ, sizeof(double) * n * n);
   memcpy(io.LR, hm.sqrtR, sizeof(double) * m * m);
   if (cfg->noise_mode == GKB_NOISE_PHILOX) {
@@ -726,9 +768,17 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   io.want_xstats = (out->sum_d || out->sum_dd || out->x_ref) ? 1 : 0;
   const int cols = mc_cols(n, io.want_xstats);
   if (cfg->controls && c > 0 && hm.need_ctrl) {
-    if ((rc = g_mc.u.ensure(sizeof(double) * (size_t)steps * c))) return rc;
-    GKB_CUDA(cudaMemcpyAsync(g_mc.u.p, cfg->controls, sizeof(double) * (size_t)steps * c, cudaMemcpyHostToDevice, s));
-    io.u = g_mc.u.as<double>();
+    // montecarlo.go:98-104 replaces a single control vector by zeros: an all-zero control stream adds
+    // +0.0 to every prediction, so it is elided; otherwise G u is formed once per step for all trials.
+    bool any = false;
+    for (size_t i = 0; i < (size_t)steps * c && !any; ++i) any = cfg->controls[i] != 0.0;
+    if (any) {
+      if ((rc = g_mc.u.ensure(sizeof(double) * (size_t)steps * c))) return rc;
+      if ((rc = g_mc.gu.ensure(sizeof(double) * (size_t)steps * n))) return rc;
+      GKB_CUDA(cudaMemcpyAsync(g_mc.u.p, cfg->controls, sizeof(double) * (size_t)steps * c, cudaMemcpyHostToDevice, s));
+      launch_gu(hm.G, n, c, g_mc.u.as<double>(), steps, g_mc.gu.as<double>(), s);
+      io.gu = g_mc.gu.as<double>();
+    }
   }
   if (cfg->noise_mode == GKB_NOISE_REPLAY) {
     if (cfg->noise_mem == GKB_DEVICE) {
@@ -768,6 +818,9 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
     }
     GKB_CUDA(cudaMemsetAsync(io.status, 0, sizeof(int32_t) * cfg->trials, s));
   }
+  if ((rc = g_mc.err.ensure(sizeof(int32_t)))) return rc;
+  io.first_error = g_mc.err.as<int32_t>();
+  GKB_CUDA(cudaMemsetAsync(io.first_error, 0, sizeof(int32_t), s));
   const int max_grid = mc_max_grid(cfg->device);
   const size_t pbytes = sizeof(double) * (size_t)max_grid * steps * cols;
   if ((rc = g_mc.partial.ensure(pbytes))) return rc;

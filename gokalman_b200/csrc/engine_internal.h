@@ -42,7 +42,7 @@ struct LtiIo {
   double* mat;  // [n*n][nf]
   const double* y;
   int y_shared;
-  const double* u;  // [steps][c] or nullptr
+  const double* gu;  // [steps][n]: G u per step (gu_kernel), nullptr = no control term
   const double* w;  // replay noise [replay_steps][n][nf] or nullptr
   const double* v;  // [replay_steps][m_v][nf] or nullptr
   int replay_steps;
@@ -73,7 +73,7 @@ struct McIo {
   int64_t trials;
   int64_t trial_offset;
   int steps;
-  const double* u;  // device [steps][c] or nullptr
+  const double* gu;  // device [steps][n]: G u per step, nullptr = no (or all-zero) control
   int noise_mode;
   unsigned long long seed;
   const double* w;  // replay [steps][n][trials]
@@ -83,6 +83,7 @@ struct McIo {
   int want_xstats;
   double *truth_x, *truth_y, *noise_w, *noise_v;
   int32_t* status;
+  int32_t* first_error;  // one word: the most negative status any trial hit, 0 if none
   double x0_truth[GKB_MAX_N];
   double x0_filter[GKB_MAX_N];
   double P0[GKB_MAX_N * GKB_MAX_N];
@@ -109,6 +110,8 @@ enum SetupOps {
 // x0 [n] and A0 [n*n] are host arrays, updated in place where an op says so.  Dispatches on
 // (hm.n, hm.m_r).  Returns a gkb_status (GKB_ERR_SINGULAR_R when NewSRIF's inverse of L fails).
 int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStream_t s);
+// gu[k][i] = sum_j G[i][j] u[k][j]: the control term, identical for every filter of a batch.
+int launch_gu(const double* G_host, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s);
 int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s);
 int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s);
 // Upper bound on the CTAs launch_mc will use (rows of McIo::partial to allocate, zero-filled).

@@ -61,17 +61,6 @@ struct NlModel {  // hybrid.go:37-46 / srif.go:52-60 (shared part)
   int q;
 };
 
-// G u for a control vector shared by all filters (read through the uniform/constant path).
-template <int N>
-GKB_DEV void control_term(double (&gu)[N], const double* G, int c, const double* __restrict__ u) {
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double s = 0.0;
-    for (int j = 0; j < c; ++j) s = fma(G[i * c + j], __ldg(u + j), s);
-    gu[i] = s;
-  }
-}
-
 // What one Update() produces besides the new state (the Estimate fields, kalman.go:64-72).
 template <int N, int M>
 struct StepOut {
@@ -84,7 +73,10 @@ struct StepOut {
 
 // ---- vanilla.go:128-220 ---------------------------------------------------------------------------
 // x, P: previous posterior in, new posterior out (unchanged when an error is returned).
-template <int N, int M, bool PREDICTOR>
+// gu = G u (formed once per step for all filters by gu_kernel).  NOISY = false compiles out the
+// "+ Process(k)" / "+ Measurement(k)" additions for a Noiseless filter (they would add +0.0);
+// CHECK = false drops the engine's own non-finite guard (the reference has none).
+template <int N, int M, bool PREDICTOR, bool NOISY = true, bool CHECK = true>
 GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&P)[N * (N + 1) / 2],
                          const double (&y)[M], const double (&gu)[N], const double (&w)[N],
                          const double (&v)[M], StepOut<N, M>& o) {
@@ -97,7 +89,7 @@ GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&
 #pragma unroll
     for (int j = 1; j < N; ++j) s = fma(md.F[i * N + j], x[j], s);
     if (md.need_ctrl) s += gu[i];
-    xm[i] = s + w[i];
+    xm[i] = NOISY ? (s + w[i]) : s;
   }
   // 155-157: yhat = H x_prev + Measurement(k)
 #pragma unroll
@@ -105,7 +97,7 @@ GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&
     double s = md.H[a * N] * x[0];
 #pragma unroll
     for (int j = 1; j < N; ++j) s = fma(md.H[a * N + j], x[j], s);
-    o.yhat[a] = s + v[a];
+    o.yhat[a] = NOISY ? (s + v[a]) : s;
   }
   // 149-152: P- = (F P) F^T + Q, upper triangle only
   double Pm[SN];
@@ -188,7 +180,7 @@ GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&
       double s = o.K[i * M] * o.innov[0];
 #pragma unroll
       for (int a = 1; a < M; ++a) s = fma(o.K[i * M + a], o.innov[a], s);
-      xp[i] = (xm[i] + s) + w[i];
+      xp[i] = NOISY ? ((xm[i] + s) + w[i]) : (xm[i] + s);
     }
     // 197-205: Joseph form, restructured (see header)
     double Pp[SN];
@@ -220,10 +212,12 @@ GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&
         Pp[sym_idx<N>(i, j)] = s;
       }
     }
-    bool finite = true;
+    if constexpr (CHECK) {
+      bool finite = true;
 #pragma unroll
-    for (int i = 0; i < N; ++i) finite = finite && isfinite(xp[i]) && isfinite(Pp[sym_idx<N>(i, i)]);
-    if (!finite) return GKB_ERR_NONFINITE;
+      for (int i = 0; i < N; ++i) finite = finite && isfinite(xp[i]) && isfinite(Pp[sym_idx<N>(i, i)]);
+      if (!finite) return GKB_ERR_NONFINITE;
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = xp[i];
 #pragma unroll

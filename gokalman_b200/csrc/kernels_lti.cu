@@ -71,7 +71,10 @@ vanilla_update_kernel(const __grid_constant__ VanillaModel<N, M> md, const __gri
     for (int a = 0; a < M; ++a) v[a] = 0.0;
     int err = 0;
     load_inputs<N, M>(io, k, tid, y, w, v, err);
-    if (md.need_ctrl && io.u != nullptr) control_term<N>(gu, md.G, md.c, io.u + (int64_t)k * md.c);
+    if (md.need_ctrl && io.gu != nullptr) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) gu[i] = __ldg(io.gu + (int64_t)k * N + i);
+    }
     StepOut<N, M> o;
     if (err == 0) err = vanilla_step<N, M, PREDICTOR>(md, x, P, y, gu, w, v, o);
     if (err != 0) {
@@ -127,7 +130,10 @@ info_update_kernel(const __grid_constant__ InfoModel<N, M> md, const __grid_cons
     for (int a = 0; a < M; ++a) v[a] = 0.0;
     int err = 0;
     load_inputs<N, M>(io, k, tid, y, w, v, err);
-    if (md.need_ctrl && io.u != nullptr) control_term<N>(gu, md.G, md.c, io.u + (int64_t)k * md.c);
+    if (md.need_ctrl && io.gu != nullptr) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) gu[i] = __ldg(io.gu + (int64_t)k * N + i);
+    }
     InfoOut<N, M> o;
     if (err == 0) err = info_step<N, M>(md, iv, I, y, gu, v, o);
     if (err != 0) {
@@ -182,7 +188,10 @@ sqrt_update_kernel(const __grid_constant__ SqrtModel<N, M> md, const __grid_cons
     for (int a = 0; a < M; ++a) v[a] = 0.0;
     int err = 0;
     load_inputs<N, M>(io, k, tid, y, w, v, err);
-    if (md.need_ctrl && io.u != nullptr) control_term<N>(gu, md.G, md.c, io.u + (int64_t)k * md.c);
+    if (md.need_ctrl && io.gu != nullptr) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) gu[i] = __ldg(io.gu + (int64_t)k * N + i);
+    }
     SqrtOut<N, M> o;
     if (err == 0) err = sqrt_step<N, M>(md, x, S, y, gu, w, v, o);
     if (err != 0) {
@@ -209,6 +218,27 @@ sqrt_update_kernel(const __grid_constant__ SqrtModel<N, M> md, const __grid_cons
   store_soa<N>(io.vec, x, io.nf, tid);
   store_soa<N * N>(io.mat, S, io.nf, tid);
   if (io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
+}
+
+// ---- control term: gu[k][i] = sum_j G[i][j] u[k][j], once per step for the whole batch ----------------
+struct GuParams { double G[GKB_MAX_N * GKB_MAX_C]; };
+__global__ void gu_kernel_p(const __grid_constant__ GuParams p, int n, int c, const double* __restrict__ u, int steps,
+                            double* __restrict__ gu) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= steps * n) return;
+  const int k = idx / n, i = idx % n;
+  double s = 0.0;
+  for (int j = 0; j < c; ++j) s = fma(p.G[i * c + j], u[(int64_t)k * c + j], s);
+  gu[idx] = s;
+}
+
+int launch_gu(const double* G_host, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s) {
+  GuParams p;
+  for (int i = 0; i < GKB_MAX_N * GKB_MAX_C; ++i) p.G[i] = 0.0;
+  for (int i = 0; i < n * c; ++i) p.G[i] = G_host[i];
+  const int total = steps * n;
+  gu_kernel_p<<<(total + 127) / 128, 128, 0, s>>>(p, n, c, u_dev, steps, gu_dev);
+  return 0;
 }
 
 // ---- model marshalling + dispatch -------------------------------------------------------------------

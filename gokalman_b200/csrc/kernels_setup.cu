@@ -124,8 +124,13 @@ int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStrea
   for (int i = 0; i < m * m; ++i) h.R[i] = hm.R[i];
   if (x0) for (int i = 0; i < n; ++i) h.x0[i] = x0[i];
   if (A0) for (int i = 0; i < n * n; ++i) h.A0[i] = A0[i];
-  SetupData* dev = nullptr;
-  if (cudaMalloc(&dev, sizeof(SetupData)) != cudaSuccess) return GKB_ERR_CUDA;
+  // one small device scratch per (host thread, device), kept for the life of the thread
+  static thread_local SetupData* dev_cache[64] = {nullptr};
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur < 0 || cur >= 64) return GKB_ERR_CUDA;
+  if (!dev_cache[cur] && cudaMalloc(&dev_cache[cur], sizeof(SetupData)) != cudaSuccess) return GKB_ERR_CUDA;
+  SetupData* dev = dev_cache[cur];
   cudaMemcpyAsync(dev, &h, sizeof(SetupData), cudaMemcpyHostToDevice, s);
   int rc = GKB_ERR_UNSUPPORTED;
 #define GKB_CASE(NN, MM) \
@@ -136,7 +141,6 @@ int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStrea
     cudaMemcpyAsync(&h, dev, sizeof(SetupData), cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess) rc = GKB_ERR_CUDA;
   }
-  cudaFree(dev);
   if (rc != 0) return rc;
   if (ops & kOpFinv) for (int i = 0; i < n * n; ++i) hm.Finv[i] = h.Finv[i];
   if (ops & kOpQinv) for (int i = 0; i < n * n; ++i) hm.Qinv[i] = h.Qinv[i];

@@ -4,11 +4,14 @@
 // is irreproducible by design.  Here the standard normals of (trial, step) are a pure function of
 // (seed, global trial index, step): normals 4b..4b+3 come from Philox block
 //     counter = (trial_lo, trial_hi, step, b),  key = (seed_lo, seed_hi)
-// with u = (word + 0.5) * 2^-32 and (z0, z1) = sqrt(-2 ln u0) * (cos, sin)(2 pi u1).
+// with u = (word + 0.5) * 2^-32 and (z0, z1) = sqrt(-2 ln u0) * (cos, sin)(2 pi u1), evaluated by the
+// branch-free box_muller_fast (fastmath.cuh, ~1.5 ulp).
 // oracle/gko.c gko_philox_normals restates the same stream on the CPU.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "fastmath.cuh"
 
 namespace gkb {
 
@@ -27,19 +30,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double& z0, double& z1) {
-  double u0 = ((double)a + 0.5) * 2.3283064365386963e-10;
-  double u1 = ((double)b + 0.5) * 2.3283064365386963e-10;
-  double r = sqrt(-2.0 * log(u0));
-  double s, c;
-  sincospi(2.0 * u1, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
-}
-
 // COUNT standard normals for (seed, trial, step).
 template <int COUNT>
-__device__ __forceinline__ void philox_normals(uint64_t seed, uint64_t trial, uint32_t step, double (&z)[COUNT]) {
+__device__ __forceinline__ void philox_normals(const BmCoef& cf, uint64_t seed, uint64_t trial, uint32_t step,
+                                               double (&z)[COUNT]) {
   constexpr int BLOCKS = (COUNT + 3) / 4;
 #pragma unroll
   for (int b = 0; b < BLOCKS; ++b) {
@@ -50,7 +44,7 @@ __device__ __forceinline__ void philox_normals(uint64_t seed, uint64_t trial, ui
     for (int p = 0; p < 2; ++p) {
       if (4 * b + 2 * p < COUNT) {
         double z0, z1;
-        box_muller(o[2 * p], o[2 * p + 1], z0, z1);
+        box_muller_fast(cf, o[2 * p], o[2 * p + 1], z0, z1);
         z[4 * b + 2 * p] = z0;
         if (4 * b + 2 * p + 1 < COUNT) z[4 * b + 2 * p + 1] = z1;
       }

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "fastmath.cuh"
+
 #define GKB_DEV __device__ __forceinline__
 
 namespace gkb {
@@ -117,10 +119,8 @@ template <int N>
 GKB_DEV int inverse_lu(double (&a)[N * N]) {
   if constexpr (N == 1) {
     if (a[0] == 0.0) return 1;
-    double an = fabs(a[0]);
-    a[0] = 1.0 / a[0];
-    double c = an * fabs(a[0]);
-    return (c <= 1e16) ? 0 : 2;
+    a[0] = rcp_nr(a[0]);  // the condition number of a 1 x 1 matrix is 1: only an exact zero is an error
+    return 0;
   } else {
     double anorm = 0.0;
 #pragma unroll
@@ -153,7 +153,7 @@ GKB_DEV int inverse_lu(double (&a)[N * N]) {
             a[i * N + l] = sw ? t0 : t1;
           }
         }
-        double rinv = 1.0 / a[j * N + j];
+        double rinv = rcp_nr(a[j * N + j]);
 #pragma unroll
         for (int i = j + 1; i < N; ++i) a[i * N + j] *= rinv;
       } else {
@@ -170,7 +170,7 @@ GKB_DEV int inverse_lu(double (&a)[N * N]) {
     // inv(U) in place (dtrti2 upper, non-unit)
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      a[j * N + j] = 1.0 / a[j * N + j];
+      a[j * N + j] = rcp_nr(a[j * N + j]);
       double ajj = -a[j * N + j];
 #pragma unroll
       for (int i = 0; i < j; ++i) {
@@ -237,7 +237,7 @@ GKB_DEV bool chol_lower(double (&L)[N * N], const double (&A)[N * N]) {
 #pragma unroll
     for (int l = 0; l < j; ++l) ajj = fma(-L[j * N + l], L[j * N + l], ajj);
     if (!(ajj > 0.0)) ok = false;
-    ajj = sqrt(ajj);
+    ajj = sqrt(ajj);  // constructor-time only: keep the IEEE sqrt (NaN for a non-PD input, like dpotf2)
     L[j * N + j] = ajj;
 #pragma unroll
     for (int i = j + 1; i < N; ++i) {
@@ -267,7 +267,7 @@ GKB_DEV double spd_quadform(const double (&P)[N * (N + 1) / 2], const double (&e
     for (int l = 0; l < j; ++l) d = fma(-L[j * N + l] * L[j * N + l], L[l * N + l], d);
     L[j * N + j] = d;
     if (!(d > 0.0)) ok = false;
-    dinv[j] = 1.0 / d;
+    dinv[j] = rcp_nr(d);
 #pragma unroll
     for (int i = j + 1; i < N; ++i) {
       double s = P[sym_idx<N>(j, i)];
@@ -301,10 +301,10 @@ GKB_DEV void qr_r_inplace(double (&a)[ROWS * COLS]) {
 #pragma unroll
       for (int r = i + 1; r < ROWS; ++r) ss = fma(a[r * COLS + i], a[r * COLS + i], ss);
       if (ss != 0.0) {
-        double nrm = sqrt(fma(alpha, alpha, ss));
+        double nrm = sqrt_nr(fma(alpha, alpha, ss));
         double beta = -copysign(nrm, alpha);
-        double tau = (beta - alpha) / beta;
-        double sc = 1.0 / (alpha - beta);
+        double tau = (beta - alpha) * rcp_nr(beta);
+        double sc = rcp_nr(alpha - beta);
 #pragma unroll
         for (int r = i + 1; r < ROWS; ++r) a[r * COLS + i] *= sc;
         a[i * COLS + i] = beta;
@@ -324,7 +324,7 @@ GKB_DEV void qr_r_inplace(double (&a)[ROWS * COLS]) {
 }
 
 // ---- helper.go:133-172 ---------------------------------------------------------------------------
-GKB_DEV double ref_sign(double v) { return (fabs(v) <= 1e-12) ? 1.0 : (v / fabs(v)); }
+GKB_DEV double ref_sign(double v) { return (fabs(v) <= 1e-12) ? 1.0 : copysign(1.0, v); }
 
 // HouseholderTransf on A[(N+M) x (N+1)], in place.
 template <int N, int M>
@@ -335,10 +335,10 @@ GKB_DEV void householder_transf(double (&A)[(N + M) * (N + 1)]) {
     double sigma = 0.0;
 #pragma unroll
     for (int i = k; i < ROWS; ++i) sigma = fma(A[i * COLS + k], A[i * COLS + k], sigma);
-    sigma = sqrt(sigma) * ref_sign(A[k * COLS + k]);
+    sigma = sqrt_nr(sigma) * ref_sign(A[k * COLS + k]);
     double uk = A[k * COLS + k] + sigma;
     A[k * COLS + k] = -sigma;
-    double beta = 1.0 / (sigma * uk);
+    double beta = rcp_nr(sigma * uk);
 #pragma unroll
     for (int j = k + 1; j < COLS; ++j) {
       double gamma = uk * A[k * COLS + j];

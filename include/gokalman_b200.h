@@ -201,7 +201,9 @@ typedef struct gkb_mc_outputs {
   double* truth_y;      /* optional dump [steps][m][trials]                                      */
   double* noise_w;      /* optional dump of the coloured noise actually used [steps][n][trials]  */
   double* noise_v;      /* optional dump [steps][m][trials]                                      */
-  int32_t* status;      /* optional [trials]                                                     */
+  int32_t* status;      /* optional [trials]: per-trial first error                               */
+  int32_t* first_error; /* optional, ONE word: 0, or the status of a failed trial (the reference
+                           panics when the tested filter's Update fails, chisquare.go:40-42)      */
 } gkb_mc_outputs;
 
 int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out);
