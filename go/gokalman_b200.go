@@ -1,0 +1,166 @@
+// Package gokalmanb200 is the cgo shim that puts the B200 engine (libgokalman_b200.so, C-ABI in
+// include/gokalman_b200.h) behind gokalman's own interfaces.  SOURCE ONLY: the build image has no Go
+// toolchain, so this file is never compiled or tested here; the Python mirror
+// (gokalman_b200/api.py) is the tested caller of the same C-ABI.
+//
+// Build (on a machine with Go, CUDA 12.9 and the built library):
+//   CGO_CFLAGS="-I${REPO}/include" CGO_LDFLAGS="-L${REPO}/gokalman_b200 -lgokalman_b200" go build
+package gokalmanb200
+
+/*
+#include <stdlib.h>
+#include "gokalman_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"unsafe"
+
+	"github.com/ChristopherRabotin/gokalman"
+	"github.com/gonum/matrix/mat64"
+)
+
+func raw(m mat64.Matrix) []float64 { // row-major copy, like mat64.DenseCopyOf(m).RawMatrix().Data
+	r, c := m.Dims()
+	out := make([]float64, r*c)
+	for i := 0; i < r; i++ {
+		for j := 0; j < c; j++ {
+			out[i*c+j] = m.At(i, j)
+		}
+	}
+	return out
+}
+
+func ptr(v []float64) *C.double {
+	if len(v) == 0 {
+		return nil
+	}
+	return (*C.double)(unsafe.Pointer(&v[0]))
+}
+
+func lastErr(rc C.int) error {
+	if rc == 0 {
+		return nil
+	}
+	return errors.New(C.GoString(C.gkb_last_error()))
+}
+
+// Vanilla is a batch of N vanilla Kalman filters on one GPU; N = 1 implements gokalman.LDKF.
+type Vanilla struct {
+	h          *C.gkb_filter
+	n, m, c, N int
+	noise      gokalman.Noise
+	F, G, H    mat64.Matrix
+}
+
+// NewVanilla mirrors gokalman.NewVanilla (vanilla.go:21-40) plus the batch size and device.
+func NewVanilla(x0 *mat64.Vector, Covar0 mat64.Symmetric, F, G, H mat64.Matrix, noise gokalman.Noise, nFilters, device int) (*Vanilla, error) {
+	n, _ := F.Dims()
+	m, _ := H.Dims()
+	_, c := G.Dims()
+	kf := &Vanilla{n: n, m: m, c: c, N: nFilters, noise: noise, F: F, G: G, H: H}
+	rc := C.gkb_create_lti(C.GKB_VANILLA, C.int(n), C.int(m), C.int(c), C.int64_t(nFilters), C.int(device),
+		ptr(raw(x0)), 0, ptr(raw(Covar0)), ptr(raw(F)), ptr(raw(G)), ptr(raw(H)),
+		ptr(raw(noise.ProcessMatrix())), ptr(raw(noise.MeasurementMatrix())), &kf.h)
+	return kf, lastErr(rc)
+}
+
+// Update implements LDKF.Update(measurement, control) (kalman.go:36) for N = 1.
+func (kf *Vanilla) Update(measurement, control *mat64.Vector) (gokalman.Estimate, error) {
+	y, u := raw(measurement), raw(control)
+	est := &Estimate{n: kf.n, m: kf.m,
+		state: make([]float64, kf.n), meas: make([]float64, kf.m), innov: make([]float64, kf.m),
+		covar: make([]float64, kf.n*kf.n), pred: make([]float64, kf.n*kf.n), gain: make([]float64, kf.n*kf.m)}
+	var status C.int32_t
+	out := C.gkb_outputs{mem: C.GKB_HOST, every_step: 0, state: ptr(est.state), meas: ptr(est.meas),
+		innov: ptr(est.innov), covar: ptr(est.covar), pred_covar: ptr(est.pred), gain: ptr(est.gain), status: &status}
+	if rc := C.gkb_update(kf.h, 1, ptr(y), 1, ptr(u), C.GKB_HOST, &out); rc != 0 {
+		return nil, lastErr(rc)
+	}
+	if status != 0 {
+		return nil, errors.New("could not invert `H*P_kp1_minus*H' + R`") // vanilla.go:164-167
+	}
+	return est, nil
+}
+
+// UpdateBatch is the new batched entry point: `steps` updates of all N filters in one launch.
+// y is [steps][m][N] (filter index fastest), u is [steps][c]; outputs as requested in `out`.
+func (kf *Vanilla) UpdateBatch(steps int, y, u []float64, out *C.gkb_outputs) error {
+	return lastErr(C.gkb_update(kf.h, C.int(steps), ptr(y), 0, ptr(u), C.GKB_HOST, out))
+}
+
+func (kf *Vanilla) SetMeasurementMatrix(H mat64.Matrix) {
+	m, _ := H.Dims()
+	kf.H, kf.m = H, m
+	C.gkb_set_measurement_matrix(kf.h, C.int(m), ptr(raw(H)))
+}
+func (kf *Vanilla) SetNoise(n gokalman.Noise) {
+	r, _ := n.MeasurementMatrix().Dims()
+	kf.noise = n
+	C.gkb_set_noise(kf.h, ptr(raw(n.ProcessMatrix())), C.int(r), ptr(raw(n.MeasurementMatrix())))
+}
+func (kf *Vanilla) SetStateTransition(F mat64.Matrix) { kf.F = F; C.gkb_set_state_transition(kf.h, ptr(raw(F))) }
+func (kf *Vanilla) SetInputControl(G mat64.Matrix) {
+	_, c := G.Dims()
+	kf.G, kf.c = G, c
+	C.gkb_set_input_control(kf.h, C.int(c), ptr(raw(G)))
+}
+func (kf *Vanilla) GetNoise() gokalman.Noise            { return kf.noise }
+func (kf *Vanilla) GetStateTransition() mat64.Matrix    { return kf.F }
+func (kf *Vanilla) GetInputControl() mat64.Matrix       { return kf.G }
+func (kf *Vanilla) GetMeasurementMatrix() mat64.Matrix  { return kf.H }
+func (kf *Vanilla) Reset()                              { C.gkb_reset(kf.h); kf.noise.Reset() }
+func (kf *Vanilla) String() string                      { return "gokalman_b200.Vanilla" }
+func (kf *Vanilla) Close()                              { C.gkb_destroy(kf.h) }
+
+// Estimate implements gokalman.Estimate (kalman.go:64-72) over the arrays gkb_update filled.
+type Estimate struct {
+	n, m                                   int
+	state, meas, innov, covar, pred, gain []float64
+}
+
+func (e *Estimate) State() *mat64.Vector            { return mat64.NewVector(e.n, e.state) }
+func (e *Estimate) Measurement() *mat64.Vector      { return mat64.NewVector(e.m, e.meas) }
+func (e *Estimate) Innovation() *mat64.Vector       { return mat64.NewVector(e.m, e.innov) }
+func (e *Estimate) Covariance() mat64.Symmetric     { return mat64.NewSymDense(e.n, e.covar) }
+func (e *Estimate) PredCovariance() mat64.Symmetric { return mat64.NewSymDense(e.n, e.pred) }
+func (e *Estimate) Gain() mat64.Matrix              { return mat64.NewDense(e.n, e.m, e.gain) }
+func (e *Estimate) String() string                  { return "gokalman_b200.Estimate" }
+func (e *Estimate) IsWithinNσ(N float64) bool { // vanilla.go:231-239
+	for i := 0; i < e.n; i++ {
+		b := N * sqrt(e.covar[i*e.n+i])
+		if e.state[i] > b || e.state[i] < -b {
+			return false
+		}
+	}
+	return true
+}
+
+// ChiSquare runs NewMonteCarloRuns + NewChiSquare (montecarlo.go:92-119, chisquare.go:16-95) fused on
+// the GPU and returns (NISmeans, NEESmeans) in the reference's order.
+func ChiSquare(kind int, n, m, c int, F, G, H, Q, R, x0Truth, x0Filter, P0 []float64, trials int64, steps int,
+	controls []float64, seed uint64, device int) (nis, nees []float64, err error) {
+	nis, nees = make([]float64, steps), make([]float64, steps)
+	cfg := C.gkb_mc_config{kind: C.int(kind), n: C.int(n), m: C.int(m), c: C.int(c), F: ptr(F), G: ptr(G), H: ptr(H),
+		Q: ptr(Q), R: ptr(R), x0_truth: ptr(x0Truth), x0_filter: ptr(x0Filter), P0: ptr(P0), trials: C.int64_t(trials),
+		steps: C.int(steps), controls: ptr(controls), noise_mode: C.GKB_NOISE_PHILOX, seed: C.uint64_t(seed),
+		with_nees: 1, with_nis: 1, device: C.int(device)}
+	var first C.int32_t
+	out := C.gkb_mc_outputs{mem: C.GKB_HOST, nis: ptr(nis), nees: ptr(nees), first_error: &first}
+	if rc := C.gkb_mc_chisquare(&cfg, &out); rc != 0 {
+		return nil, nil, lastErr(rc)
+	}
+	if first != 0 {
+		panic("a trial's Update failed") // chisquare.go:40-42 panics
+	}
+	return nis, nees, nil
+}
+
+func sqrt(x float64) float64 { // avoid importing math for one call in this sketch
+	z := x
+	for i := 0; i < 60 && z > 0; i++ {
+		z = 0.5 * (z + x/z)
+	}
+	return z
+}

@@ -691,10 +691,10 @@ class MonteCarloRuns:
             cfg.noise_mode, cfg.seed = _lib.NOISE_PHILOX, self.noise.seed
         return cfg
 
-    def _run(self, cfg, want_stats=False, want_truth=False, want_noise=False, want_status=False):
+    def _run(self, cfg, want_stats=False, want_truth=False, want_noise=False, want_status=False, sums=False):
         n, m, steps, runs = cfg.n, cfg.m, cfg.steps, cfg.trials
         out = _lib.McOutputs()
-        out.mem, out.sums_only = _lib.HOST, 0
+        out.mem, out.sums_only = _lib.HOST, int(sums)
         res = {"NIS": np.zeros(steps), "NEES": np.zeros(steps)}
         out.nis, out.nees = res["NIS"].ctypes.data, res["NEES"].ctypes.data
         if want_stats:
@@ -777,8 +777,10 @@ def NewMonteCarloRuns(samples, steps, rowsH, controls, kf, trial_offset=0):
 _KIND_OF = {Vanilla: _lib.VANILLA, Information: _lib.INFORMATION, SquareRoot: _lib.SQRT}
 
 
-def NewChiSquare(kf, runs, controls, withNEES, withNIS):
-    """chisquare.go:16-95.  Returns (NISmeans, NEESmeans) -- in that order, like the reference."""
+def NewChiSquare(kf, runs, controls, withNEES, withNIS, sums=False):
+    """chisquare.go:16-95.  Returns (NISmeans, NEESmeans) -- in that order, like the reference.
+    sums=True returns the per-step SUMS over this object's runs instead (for a multi-GPU all-reduce,
+    see gokalman_b200.sharding)."""
     if not withNEES and not withNIS:
         raise GkbError(-10, "Chi Square requires either NEES or NIS or both")
     ctrl = _controls(controls, runs.steps)  # raises like chisquare.go:33-35 returns an error
@@ -789,7 +791,7 @@ def NewChiSquare(kf, runs, controls, withNEES, withNIS):
     runs.controls = ctrl if ctrl is not None else saved
     try:
         cfg = runs._config(kind, kf, withNEES, withNIS)
-        res = runs._run(cfg)
+        res = runs._run(cfg, sums=sums)
     finally:
         runs.controls = saved
     if res["first_error"][0] != 0:  # the reference panics (chisquare.go:40-42)

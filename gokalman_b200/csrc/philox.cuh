@@ -6,7 +6,7 @@
 //     counter = (trial_lo, trial_hi, step, b),  key = (seed_lo, seed_hi)
 // with u = (word + 0.5) * 2^-32 and (z0, z1) = sqrt(-2 ln u0) * (cos, sin)(2 pi u1), evaluated by the
 // branch-free box_muller_fast (fastmath.cuh, ~1.5 ulp).
-// oracle/gko.c gko_philox_normals restates the same stream on the CPU.
+// The CPU oracle (test infrastructure) restates the same stream.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

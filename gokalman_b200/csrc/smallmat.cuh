@@ -113,7 +113,7 @@ GKB_DEV void sym_pack_upper(double (&P)[N * (N + 1) / 2], const double (&full)[N
 
 // ---- explicit inverse by LU with partial pivoting (dgetf2 + dtrti2 + dgetri) --------------------
 // Returns 0 ok, 1 exactly singular, 2 cond_inf > 1e16 (output still the computed inverse), like
-// mat64.Dense.Inverse as restated in oracle/gko_linalg.c.  Row swaps are predicated register
+// mat64.Dense.Inverse (the CPU oracle restates the same recipe).  Row swaps are predicated register
 // swaps (static indexing); column swaps at the end likewise.
 template <int N>
 GKB_DEV int inverse_lu(double (&a)[N * N]) {
