@@ -149,7 +149,7 @@ def run_ours_hybrid(args, rank, world, local):
         "roofline": {"bound": "hbm" if bound_hbm else "fp64", "achieved": gbs if bound_hbm else tf,
                      "peak": hbm if bound_hbm else peak_tf, "unit": "GB/s" if bound_hbm else "TFLOP/s",
                      "frac": (gbs / hbm) if bound_hbm else (tf / peak_tf), "traffic": None,
-                     "kernel": "hybrid_run_kernel<6,2>", "kernel_ms": main_ms,
+                     "kernel": "hybrid_run_wtma_kernel<6,2> (warp-private TMA tensor-map pipelines)", "kernel_ms": main_ms,
                      "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm, "bytes_per_unit": BYTES_IN, "source": hbm_src},
                      "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf, "frac": tf / peak_tf, "flops_per_unit": FLOPS_EKF,
                               "source": peak_src}},

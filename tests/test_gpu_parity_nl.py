@@ -99,6 +99,50 @@ def test_hybrid_ckf_ekf_snc_matches_oracle(oracle, n, m, q):
     _check(est, refs, ["state", "covar", "pred_covar", "gain", "innov", "obs_dev"], "hybrid")
 
 
+@pytest.mark.parametrize("n,m,nf", [(6, 2, 130), (6, 2, 2), (4, 2, 258), (6, 3, 128)])
+def test_hybrid_tma_staged_path_matches_oracle(oracle, n, m, nf):
+    """The production path of the hybrid filter (final-estimate outputs, per-filter streams, no SNC)
+    runs the warp-private TMA kernel (cp.async.bulk.tensor boxes -> shared memory, mbarrier ring per
+    warp).  Ragged last warp / CTA (130 = 128 + 2 filters), Predict epochs (fewer boxes per epoch) and
+    the CKF -> EKF switch are all covered; the result must equal the oracle (1e-10) and the plain-load
+    and bulk-row kernels bit for bit."""
+    import os
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS, F_EKF, F_SNC
+    rng = np.random.default_rng(900 + n + nf)
+    steps = 37
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    P0 = np.diag(np.concatenate([np.full(n - n // 2, 10.0), np.full(n // 2, 1.0)]))
+    R = np.diag(np.full(m, 1e-2))
+    Q = np.diag(np.full(3, 1e-3))
+    flags = np.array([(F_MEAS if (k % 6 != 4) else 0) | (F_EKF if k >= 15 else 0) for k in range(steps)], dtype=np.uint8)
+
+    def run(path):
+        if path:
+            os.environ["GKB_NL_PATH"] = path
+        try:
+            kf, _ = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R), m, n_filters=nf)
+            est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=False, want=("state", "covar"))
+            vec, mat = kf.GetState()
+        finally:
+            os.environ.pop("GKB_NL_PATH", None)
+        return est, vec, mat
+    est, vec, mat = run(None)
+    assert np.all(est.status == 0)
+    for path in ("plain", "bulk"):
+        est2, vec2, mat2 = run(path)
+        assert np.array_equal(vec, vec2) and np.array_equal(mat, mat2), path
+        assert np.array_equal(np.asarray(est.State()), np.asarray(est2.State())), path
+    for f in sorted(set([0, 1, nf // 2, nf - 2, nf - 1])):
+        o = oracle.NewHybridKF(np.zeros(n), P0, Q, R, m)
+        ref = _oracle_run(o, flags, Phi, Ht, real, comp, None, f, F_MEAS, F_EKF, F_SNC)[-1]
+        xs = np.asarray(est.State()).reshape(n, nf)[:, f]
+        Pc = np.asarray(est.Covariance()).reshape(n, n, nf)[:, :, f]
+        assert fx.scaled_err(xs, ref.State()) <= TOL, (f, fx.scaled_err(xs, ref.State()))
+        assert fx.scaled_err(Pc, ref.Covariance()) <= TOL
+        assert fx.scaled_err(vec[:, f], ref.State()) <= TOL and fx.scaled_err(mat[:, :, f], ref.Covariance()) <= TOL
+
+
 @pytest.mark.parametrize("n,m", [(6, 2), (4, 2), (3, 1)])
 def test_srif_matches_oracle(oracle, n, m):
     """srif.go:101-160 with per-filter Phi / Htilde; State(), Covariance(), PredCovariance() read-outs."""

@@ -1,6 +1,6 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_r01_b.json
-ncu --target-processes application-only --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_r01_b.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-tail -2 gpurun_out/ncu_launch.log
+python -m pytest tests/test_gpu_parity_nl.py -m gpu -x -q 2>&1 | tail -5
+for p in tensor bulk plain; do
+  GKB_NL_PATH=$p python bench.py --workload hybrid6 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/hyb_$p.json
+  python -c "import json;d=json.load(open('gpurun_out/hyb_$p.json'));print('$p',d['value'],d['roofline']['kernel_ms'],d['roofline']['hbm']['frac'])"
+done
