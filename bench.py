@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mc_jerk3", choices=["mc_jerk3", "hybrid6"])
+    ap.add_argument("--workload", default="mc_jerk3", choices=["mc_jerk3", "hybrid6", "vanilla32"])
     ap.add_argument("--trials", type=int, default=1000000, help="Monte Carlo trials (filters) per GPU")
     ap.add_argument("--filter-steps", type=int, default=1000, help="filter steps per trial")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -335,6 +335,9 @@ def main():
     if args.workload == "hybrid6":
         from bench_hybrid import run_ours_hybrid
         line = run_ours_hybrid(args, rank, world, local)
+    elif args.workload == "vanilla32":
+        from bench_tile import run_ours_tile
+        line = run_ours_tile(args, rank, world, local)
     else:
         line = run_ours_mc(args, rank, world, local)
     if line is not None:

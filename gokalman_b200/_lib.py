@@ -71,6 +71,7 @@ SYMBOLS = [
     ("gkb_reset", _i, [_vp]),
     ("gkb_set_stream", _i, [_vp, _vp]),
     ("gkb_n_filters", _i64, [_vp]),
+    ("gkb_filter_major", _i, [_vp]),
     ("gkb_step", _i, [_vp]),
     ("gkb_update", _i, [_vp, _i, _vp, _i, _vp, _i, C.POINTER(Outputs)]),
     ("gkb_nl_run", _i, [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(Outputs)]),

@@ -234,6 +234,8 @@ _OUT_FIELDS = ("state", "meas", "innov", "covar", "pred_covar", "gain", "obs_dev
 class _Filter:
     """Common handle plumbing."""
 
+    _fm = False  # large-state handles use filter-major arrays at the C-ABI (gkb_filter_major)
+
     def __init__(self):
         self._h = None
 
@@ -254,7 +256,8 @@ class _Filter:
         rows = steps if every_step else 1
         sizes = {"state": n, "meas": m, "innov": innov_len, "covar": n * n, "pred_covar": n * n, "gain": n * m,
                  "obs_dev": m}
-        fields = {k: np.zeros((rows, sizes[k], nf)) for k in _OUT_FIELDS if k in want and sizes[k] > 0}
+        shape = (lambda c: (rows, nf, c)) if self._fm else (lambda c: (rows, c, nf))
+        fields = {k: np.zeros(shape(sizes[k])) for k in _OUT_FIELDS if k in want and sizes[k] > 0}
         status = np.zeros(nf, dtype=np.int32)
         out = _lib.Outputs()
         out.mem, out.every_step = _lib.HOST, int(every_step)
@@ -270,6 +273,10 @@ class _Filter:
 
     def GetState(self):
         """raw (vector [n, N], matrix [n, n, N]) of the filters: x,P / i,I / x,S / b,R by kind"""
+        if self._fm:
+            vec, mat = np.zeros((self._nf, self._n)), np.zeros((self._nf, self._n * self._n))
+            _lib.check(_lib.load().gkb_get_state(self._h, _ptr(vec), _ptr(mat)))
+            return np.ascontiguousarray(vec.T), np.ascontiguousarray(mat.T).reshape(self._n, self._n, self._nf)
         vec, mat = np.zeros((self._n, self._nf)), np.zeros((self._n * self._n, self._nf))
         _lib.check(_lib.load().gkb_get_state(self._h, _ptr(vec), _ptr(mat)))
         return vec, mat.reshape(self._n, self._n, self._nf)
@@ -299,13 +306,17 @@ class _LDKF(_Filter):
         c = 0 if G is None else G.shape[1]
         Q, R = _mat(noise.ProcessMatrix()), _mat(noise.MeasurementMatrix())
         per_filter = 1 if x0.ndim == 2 else 0
+        x0_abi = x0
+        if per_filter and kind == _lib.VANILLA and n > 8:  # large-state handles are filter-major at the C-ABI
+            x0_abi = np.ascontiguousarray(x0.T)
         h = C.c_void_p()
         if from_state:
             _lib.check(lib.gkb_create_information_from_state(n, m, c, n_filters, device, _ptr(x0), _ptr(P0), _ptr(F),
                                                              _ptr(G), _ptr(H), _ptr(Q), _ptr(R), C.byref(h)))
         else:
-            _lib.check(lib.gkb_create_lti(kind, n, m, c, n_filters, device, _ptr(x0), per_filter, _ptr(P0), _ptr(F),
+            _lib.check(lib.gkb_create_lti(kind, n, m, c, n_filters, device, _ptr(x0_abi), per_filter, _ptr(P0), _ptr(F),
                                           _ptr(G), _ptr(H), _ptr(Q), _ptr(R), C.byref(h)))
+        self._fm = bool(lib.gkb_filter_major(h))
         self._h, self._n, self._m, self._c, self._nf, self._device = h, n, m, c, n_filters, device
         self.F, self.G, self.H = F, G, H
         self.needCtrl = not (G is None or not np.any(G))
@@ -406,8 +417,12 @@ class _LDKF(_Filter):
         if self.needCtrl and (u is None or u.shape[1] != self._c):
             raise GkbError(-1, "control (u) G(...x%d)" % self._c)
         out, fields, status = self._alloc_out(steps, every_step, want or self._want, self._innov_len())
+        if self._fm and not shared:
+            y = np.ascontiguousarray(y.transpose(0, 2, 1))  # [steps, n_filters, m] at the C-ABI
         _lib.check(lib.gkb_update(self._h, steps, _ptr(y), shared, _ptr(u), _lib.HOST, C.byref(out)))
         self._raise_status(status)
+        if self._fm:  # back to the [steps, component, n_filters] convention of Estimate
+            fields = {k: np.ascontiguousarray(a.transpose(0, 2, 1)) for k, a in fields.items()}
         return Estimate(self._n, self._m, fields, status)
 
 

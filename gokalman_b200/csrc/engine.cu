@@ -156,6 +156,9 @@ struct gkb_filter {
   bool has_w = false, has_v = false;
   DevBuf in_y, in_u, in_gu, in_a, in_b, in_c, in_d, in_e, in_f;  // staging for host inputs
   DevBuf o_state, o_meas, o_innov, o_covar, o_pred, o_gain, o_obsdev;
+  // large-state handles (kernels_tile.cu): filter-major arrays, model kept on the device
+  bool tile = false;
+  DevBuf tile_model;  // F [n*n], Q [n*n], H [8][n], R [8][8]
 };
 
 extern "C" {
@@ -185,6 +188,7 @@ int gkb_device_count(void) {
 
 int gkb_shape_supported(int kind, int n, int m) {
   if (kind < GKB_VANILLA || kind > GKB_SRIF) return 0;
+  if (kind == GKB_VANILLA && tile_shape_supported(n, m)) return 1;
 #define GKB_CASE(NN, MM) \
   if (n == NN && m == MM) return 1;
   GKB_FOR_EACH_SHAPE(GKB_CASE)
@@ -222,12 +226,77 @@ static int finish_create(gkb_filter* f, const double* x0, int x0_per_filter, con
 static void destroy_filter(gkb_filter* f) {
   if (!f) return;
   cudaSetDevice(f->device);
-  DevBuf* bufs[] = {&f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
+  DevBuf* bufs[] = {&f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
                     &f->in_a, &f->in_b, &f->in_c, &f->in_d, &f->in_e, &f->in_f, &f->o_state, &f->o_meas, &f->o_innov,
                     &f->o_covar, &f->o_pred, &f->o_gain, &f->o_obsdev};
   for (DevBuf* b : bufs) b->release();
   delete f;
 }
+
+// vec[f][i] = x0[i] (or the per-filter copy), mat[f][i*n+j] = A0[i*n+j]: filter-major (large-state handles)
+__global__ void fill_state_tile_kernel(double* vec, double* mat, const double* x0, int x0_per_filter, const double* A0,
+                                       int n, int64_t nf) {
+  const int64_t total = nf * n * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    mat[idx] = A0[idx % (n * n)];
+    if (idx < nf * n) vec[idx] = x0_per_filter ? x0[idx] : x0[idx % n];
+  }
+}
+
+// NewVanilla for n in {16, 24, 32}, m <= 8: the warp-per-filter tensor-core path (kernels_tile.cu).
+static int create_tile(int n, int m, int c, int64_t n_filters, int device, const double* x0, int x0_per_filter,
+                       const double* P0, const double* F, const double* G, const double* H, const double* Q,
+                       const double* R, gkb_filter** out) {
+  if (!(G == nullptr || c == 0 || is_nil(G, n * c)))
+    return fail(GKB_ERR_UNSUPPORTED, "large-state filters (n=%d) do not take an input control yet", n);
+  int rc = check_device(device);
+  if (rc) return rc;
+  gkb_filter* f = new gkb_filter();
+  f->nf = n_filters;
+  f->device = device;
+  f->tile = true;
+  memset(&f->hm, 0, sizeof f->hm);
+  f->hm.kind = GKB_VANILLA; f->hm.n = n; f->hm.m = m; f->hm.m_r = m;  // dimensions only: the arrays of hm are too small
+  std::vector<double> model((size_t)2 * n * n + 8 * n + 64, 0.0), A0((size_t)n * n);
+  double* mF = model.data();
+  double* mQ = mF + n * n;
+  double* mH = mQ + n * n;
+  double* mR = mH + 8 * n;
+  memcpy(mF, F, sizeof(double) * n * n);
+  sym_from_upper(mQ, Q, n);
+  memcpy(mH, H, sizeof(double) * m * n);
+  for (int a = 0; a < 8; ++a)
+    for (int b = 0; b < 8; ++b) mR[a * 8 + b] = (a < m && b < m) ? (b >= a ? R[a * m + b] : R[b * m + a]) : (a == b ? 1.0 : 0.0);
+  sym_from_upper(A0.data(), P0, n);
+  const size_t xbytes = sizeof(double) * (x0_per_filter ? (size_t)n * n_filters : (size_t)n);
+  DevBuf dx, dA;
+  if ((rc = f->tile_model.ensure(sizeof(double) * model.size())) || (rc = f->vec.ensure(sizeof(double) * n * n_filters)) ||
+      (rc = f->mat.ensure(sizeof(double) * n * n * n_filters)) || (rc = f->vec0.ensure(sizeof(double) * n * n_filters)) ||
+      (rc = f->mat0.ensure(sizeof(double) * n * n * n_filters)) || (rc = f->status.ensure(sizeof(int32_t) * n_filters)) ||
+      (rc = dx.ensure(xbytes)) || (rc = dA.ensure(sizeof(double) * n * n))) {
+    dx.release(); dA.release(); destroy_filter(f);
+    return rc;
+  }
+  cudaMemcpyAsync(f->tile_model.p, model.data(), sizeof(double) * model.size(), cudaMemcpyHostToDevice, f->stream);
+  cudaMemcpyAsync(dx.p, x0, xbytes, cudaMemcpyHostToDevice, f->stream);
+  cudaMemcpyAsync(dA.p, A0.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, f->stream);
+  fill_state_tile_kernel<<<1184, 256, 0, f->stream>>>(f->vec0.as<double>(), f->mat0.as<double>(), dx.as<double>(),
+                                                      x0_per_filter, dA.as<double>(), n, n_filters);
+  cudaMemcpyAsync(f->vec.p, f->vec0.p, sizeof(double) * n * n_filters, cudaMemcpyDeviceToDevice, f->stream);
+  cudaMemcpyAsync(f->mat.p, f->mat0.p, sizeof(double) * n * n * n_filters, cudaMemcpyDeviceToDevice, f->stream);
+  cudaMemsetAsync(f->status.p, 0, sizeof(int32_t) * n_filters, f->stream);
+  cudaError_t e = cudaStreamSynchronize(f->stream);
+  dx.release();
+  dA.release();
+  if (e != cudaSuccess) {
+    destroy_filter(f);
+    return fail(GKB_ERR_CUDA, "state initialisation failed: %s", cudaGetErrorString(e));
+  }
+  *out = f;
+  return 0;
+}
+
+int gkb_filter_major(const gkb_filter* f) { return (f && f->tile) ? 1 : 0; }
 
 int gkb_create_lti(int kind, int n, int m, int c, int64_t n_filters, int device, const double* x0, int x0_per_filter,
                    const double* P0, const double* F, const double* G, const double* H, const double* Q,
@@ -238,6 +307,8 @@ int gkb_create_lti(int kind, int n, int m, int c, int64_t n_filters, int device,
     return fail(GKB_ERR_ARG, "gkb_create_lti: kind %d is not an LDKF kind", kind);
   if (!x0 || !P0 || !F || !H || !Q || !R) return fail(GKB_ERR_ARG, "gkb_create_lti: NULL model array");
   if (n_filters < 1) return fail(GKB_ERR_ARG, "n_filters must be >= 1");
+  if (kind == GKB_VANILLA && tile_shape_supported(n, m))
+    return create_tile(n, m, c, n_filters, device, x0, x0_per_filter, P0, F, G, H, Q, R, out);
   if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
   if (!gkb_shape_supported(kind, n, m))
     return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d (kind %d)", n, m, kind);
@@ -361,6 +432,7 @@ int gkb_set_stream(gkb_filter* f, void* stream) {
 
 int gkb_set_state_transition(gkb_filter* f, const double* F) {
   if (!f || !F) return fail(GKB_ERR_ARG, "NULL argument");
+  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
   cudaSetDevice(f->device);
   memcpy(f->hm.F, F, sizeof(double) * f->hm.n * f->hm.n);
   if (f->hm.kind == GKB_INFORMATION) {  // information.go:117-123
@@ -372,6 +444,7 @@ int gkb_set_state_transition(gkb_filter* f, const double* F) {
 
 int gkb_set_input_control(gkb_filter* f, int c, const double* G) {
   if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
   if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
   f->hm.c = c;  // needCtrl is not re-evaluated (vanilla.go:99-101)
   if (G && c > 0) memcpy(f->hm.G, G, sizeof(double) * f->hm.n * c);
@@ -380,6 +453,7 @@ int gkb_set_input_control(gkb_filter* f, int c, const double* G) {
 
 int gkb_set_measurement_matrix(gkb_filter* f, int m, const double* H) {
   if (!f || !H) return fail(GKB_ERR_ARG, "NULL argument");
+  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
   if (!gkb_shape_supported(f->hm.kind, f->hm.n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", f->hm.n, m);
   f->hm.m = m;
   memcpy(f->hm.H, H, sizeof(double) * m * f->hm.n);
@@ -388,6 +462,7 @@ int gkb_set_measurement_matrix(gkb_filter* f, int m, const double* H) {
 
 int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R) {
   if (!f || !R) return fail(GKB_ERR_ARG, "NULL argument");
+  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
   if (m_r < 1 || m_r > GKB_MAX_M) return fail(GKB_ERR_UNSUPPORTED, "R dimension %d outside 1..%d", m_r, GKB_MAX_M);
   if (f->hm.kind == GKB_SRIF) return fail(GKB_ERR_UNSUPPORTED, "noise not yet supported for SRIF (srif.go:77-79 panics)");
   cudaSetDevice(f->device);
@@ -408,6 +483,7 @@ int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R) {
 
 int gkb_set_replay_noise(gkb_filter* f, int steps, const double* w, const double* v, int mem) {
   if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
   if (steps < 1) return fail(GKB_ERR_ARG, "steps must be >= 1");
   cudaSetDevice(f->device);
   const cudaMemcpyKind kind = mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -557,6 +633,37 @@ int gkb_update(gkb_filter* f, int steps, const double* y, int y_shared, const do
   int rc = 0;
   if (cudaSetDevice(f->device) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaSetDevice failed");
   const int n = hm.n, m = hm.m;
+  if (f->tile) {
+    TileIo tio;
+    memset(&tio, 0, sizeof tio);
+    tio.nf = f->nf; tio.steps = steps; tio.m = m;
+    tio.x = f->vec.as<double>();
+    tio.P = f->mat.as<double>();
+    const void* dy = nullptr;
+    if ((rc = stage_in(f, f->in_y, y, sizeof(double) * (size_t)steps * m * (y_shared ? 1 : f->nf), in_mem, &dy))) return rc;
+    tio.y = static_cast<const double*>(dy);
+    tio.y_shared = y_shared;
+    tio.F = f->tile_model.as<double>();
+    tio.Q = tio.F + n * n;
+    tio.H = tio.Q + n * n;
+    tio.R = tio.H + 8 * n;
+    OutPlan pl;
+    if ((rc = plan_outputs(f, out, steps, m, pl))) return rc;
+    tio.every_step = out ? out->every_step : 0;
+    tio.o_state = pl.state; tio.o_meas = pl.meas; tio.o_innov = pl.innov; tio.o_covar = pl.covar;
+    tio.o_pred = pl.pred; tio.o_gain = pl.gain;
+    tio.status = f->status.as<int32_t>();
+    const bool tsync = !(in_mem == GKB_DEVICE && (!out || out->mem == GKB_DEVICE));
+    Timer tm(f->stream);
+    rc = launch_tile_update(tio, n, f->device, f->stream);
+    if (rc) return fail(rc, "no large-state kernel for n=%d m=%d", n, m);
+    tm.stop(1, tsync);
+    GKB_CUDA(cudaGetLastError());
+    f->step += steps;
+    if ((rc = copy_back(f, out, pl))) return rc;
+    if (tsync) GKB_CUDA(cudaStreamSynchronize(f->stream));
+    return 0;
+  }
   LtiIo io;
   memset(&io, 0, sizeof io);
   io.nf = f->nf;

@@ -69,6 +69,24 @@ struct NlIo {
   int32_t* status;
 };
 
+// Large-state (warp-per-filter, tensor-core) Vanilla update: FILTER-MAJOR arrays, model in device memory.
+struct TileIo {
+  int64_t nf;
+  int steps;
+  int m;            // true measurement size (<= 8); the kernel pads to one 8-wide tile
+  double* x;        // [nf][n]
+  double* P;        // [nf][n*n]
+  const double* y;  // [steps][nf][m], or [steps][m] when y_shared
+  int y_shared;
+  const double* F;  // [n*n]
+  const double* Q;  // [n*n]
+  const double* H;  // [8][n], rows >= m zero
+  const double* R;  // [8][8], unit diagonal beyond m
+  int every_step;
+  double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain;  // [rows][nf][C]
+  int32_t* status;
+};
+
 struct McIo {
   int64_t trials;
   int64_t trial_offset;
@@ -114,6 +132,9 @@ int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStrea
 int launch_gu(const double* G_host, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s);
 int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s);
 int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s);
+// Large-state Vanilla (kernels_tile.cu): n in {16, 24, 32}, m <= 8.
+int tile_shape_supported(int n, int m);
+int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s);
 // Upper bound on the CTAs launch_mc will use (rows of McIo::partial to allocate, zero-filled).
 int mc_max_grid(int device);
 // Picks a persistent grid (SM count x resident CTAs per SM, capped by the work) and launches.

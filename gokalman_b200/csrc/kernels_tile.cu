@@ -1,0 +1,405 @@
+// kernels_tile.cu -- large-state Vanilla.Update (vanilla.go:128-220) for n = 16 / 24 / 32, m <= 8:
+// one WARP per filter, covariance resident in shared memory for all the steps of a call, every dense
+// product on the FP64 tensor-core path (mma.sync m8n8k4 f64, "DMMA").
+//
+// BASELINE configs[4]: synthetic 32-state filters with a shared LTI model and a
+// per-filter measurement stream.  Per update the reference does 8n^3 + ... = 331 k flop at n = 32, m = 8
+// (SURVEY App. B); the only HBM traffic is the 8 m bytes of measurement per step, so the path is bound
+// by the FP64 pipe.  Layout of one step of one warp (g = lane / 4, t = lane % 4: the DMMA fragment
+// coordinates; all shared-memory matrices have a row pitch = 4 or 12 (mod 16) doubles, which makes the
+// A / B fragment loads and the C stores bank-conflict free):
+//
+//   T    = F P                   4x4 tiles x 8 k-steps = 128 DMMA   (bufA -> bufB); F x rides on the A fragments
+//   P-   = T F^T + Q             upper 10 tiles x 8     =  80 DMMA   (bufB -> bufA, mirrored)
+//   PHt  = P- H^T                4 tiles x 8            =  32 DMMA   (H x, H x- ride on the B fragments)
+//   S    = H PHt + R             1 tile x 8             =   8 DMMA   -> registers (C fragment)
+//   S^-1                         Gauss-Jordan on the C fragment, warp shuffles only (S is SPD: no pivoting)
+//   K    = PHt S^-1              4 tiles x 2            =   8 DMMA   (S^-1 reaches the B fragment by shuffles)
+//   T2   = P- - K PHt^T          16 tiles x 2           =  32 DMMA   (Joseph form with the products by I removed,
+//   V    = T2 H^T - K R          4 tiles x (8 + 2)      =  40 DMMA    as in filters.cuh: vanilla_step)
+//   P+   = T2 - V K^T            upper 10 tiles x 2     =  20 DMMA   (-> bufA, mirrored)
+//
+// 348 DMMA = 89 k FMA per update instead of the 166 k of the literal sequence.  m < 8 is handled by
+// padding H with zero rows and R with a unit diagonal (the padded block of S is I and contributes nothing).
+// Large-state handles use FILTER-MAJOR arrays (each filter's vector / matrix contiguous), see the header.
+#include "engine_internal.h"
+#include "fastmath.cuh"
+
+namespace gkb {
+
+namespace {
+
+constexpr int kMP = 8;     // padded measurement size (one DMMA tile)
+constexpr int kLdS = 12;   // row pitch of the n x 8 and 8 x 8 matrices
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double quad_sum(double v) {  // sum over the 4 lanes of a quad (t = 0..3)
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// Store an upper-tile result (tiles ti <= tj of an n x n symmetric matrix held as C fragments) into a
+// full shared-memory matrix, mirroring it: the lower triangle is a copy of the upper one, which is what
+// AsSymDense (helper.go:65-84) keeps of the reference's dense product.
+template <int TM, int LD>
+__device__ __forceinline__ void store_sym(double* __restrict__ dst, const double (&c)[TM * TM][2], int g, int t) {
+#pragma unroll
+  for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+    for (int tj = ti; tj < TM; ++tj) {
+      const int r = ti * 8 + g, c0 = tj * 8 + 2 * t;
+      if (ti != tj) {
+        *reinterpret_cast<double2*>(dst + r * LD + c0) = make_double2(c[ti * TM + tj][0], c[ti * TM + tj][1]);
+        dst[c0 * LD + r] = c[ti * TM + tj][0];
+        dst[(c0 + 1) * LD + r] = c[ti * TM + tj][1];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (c0 + e >= r) {
+            dst[r * LD + c0 + e] = c[ti * TM + tj][e];
+            dst[(c0 + e) * LD + r] = c[ti * TM + tj][e];
+          }
+      }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void copy_out_mat(double* __restrict__ dst, const double* __restrict__ src, int ld, int rows,
+                                             int cols, int lane) {
+  for (int idx = lane; idx < rows * cols; idx += 32) dst[idx] = src[(idx / cols) * ld + idx % cols];
+}
+
+}  // namespace
+
+template <int N>
+__global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_constant__ TileIo io) {
+  constexpr int TM = N / 8, KS = N / 4, LD = N + 4;
+  static_assert(N % 8 == 0 && (LD % 16 == 4 || LD % 16 == 12), "row pitch must keep fragment loads conflict free");
+  extern __shared__ __align__(16) double smem[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  // CTA-shared model
+  double* sF = smem;                 // [N][LD]
+  double* sQ = sF + N * LD;          // [N][LD]
+  double* sH = sQ + N * LD;          // [8][LD]   rows >= m are zero
+  double* sR = sH + kMP * LD;        // [8][12]   padded with a unit diagonal
+  double* wbase = sR + kMP * kLdS;
+  constexpr int kPerWarp = 2 * N * LD + 2 * N * kLdS + 2 * N + 2 * kMP;
+  double* bufA = wbase + (size_t)warp * kPerWarp;  // P, then P-, then P+
+  double* bufB = bufA + N * LD;                    // T, then T2
+  double* sPH = bufB + N * LD;                     // P- H^T, later V
+  double* sK = sPH + N * kLdS;                     // gain
+  double* xs = sK + N * kLdS;                      // posterior state
+  double* xms = xs + N;                            // predicted state
+  double* sinn = xms + N;                          // innovation (8), y-hat (8)
+
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    sF[(idx / N) * LD + idx % N] = io.F[idx];
+    sQ[(idx / N) * LD + idx % N] = io.Q[idx];
+  }
+  for (int idx = threadIdx.x; idx < kMP * N; idx += blockDim.x) sH[(idx / N) * LD + idx % N] = io.H[idx];
+  for (int idx = threadIdx.x; idx < kMP * kMP; idx += blockDim.x) sR[(idx / kMP) * kLdS + idx % kMP] = io.R[idx];
+  __syncthreads();
+
+  const int m = io.m;
+  for (int64_t f = (int64_t)blockIdx.x * warps + warp; f < io.nf; f += (int64_t)gridDim.x * warps) {
+    // ---- state in: x -> xs, P -> bufA (coalesced: a filter's matrix is contiguous)
+    for (int idx = lane; idx < N; idx += 32) xs[idx] = io.x[f * N + idx];
+    {
+      const double* Pg = io.P + f * (int64_t)(N * N);
+      for (int idx = lane; idx < N * N; idx += 32) bufA[(idx / N) * LD + idx % N] = Pg[idx];
+    }
+    __syncwarp();
+    int status = 0;
+    for (int k = 0; k < io.steps; ++k) {
+      // this lane's slice of the previous posterior, x[ks*4 + t]
+      double xq[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) xq[ks] = xs[ks * 4 + t];
+      double c[TM * TM][2];
+      // ---- T = F P (vanilla.go:149-150) and x- = F x (138-146; Noiseless, no control)
+      {
+        double xpart[TM];
+#pragma unroll
+        for (int i = 0; i < TM * TM; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) xpart[i] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          double a[TM], b[TM];
+#pragma unroll
+          for (int ti = 0; ti < TM; ++ti) a[ti] = sF[(ti * 8 + g) * LD + ks * 4 + t];
+#pragma unroll
+          for (int tj = 0; tj < TM; ++tj) b[tj] = bufA[(ks * 4 + t) * LD + tj * 8 + g];
+#pragma unroll
+          for (int ti = 0; ti < TM; ++ti) {
+            xpart[ti] = fma(a[ti], xq[ks], xpart[ti]);
+#pragma unroll
+            for (int tj = 0; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+          }
+        }
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) {
+          const double s = quad_sum(xpart[ti]);
+          if (t == 0) xms[ti * 8 + g] = s;
+        }
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+          for (int tj = 0; tj < TM; ++tj)
+            *reinterpret_cast<double2*>(bufB + (ti * 8 + g) * LD + tj * 8 + 2 * t) =
+                make_double2(c[ti * TM + tj][0], c[ti * TM + tj][1]);
+      }
+      __syncwarp();
+      // ---- P- = T F^T + Q (150-152): upper tiles only, mirrored into bufA
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < TM; ++tj) {
+          const double2 q = *reinterpret_cast<const double2*>(sQ + (ti * 8 + g) * LD + tj * 8 + 2 * t);
+          c[ti * TM + tj][0] = q.x;
+          c[ti * TM + tj][1] = q.y;
+        }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        double a[TM], b[TM];
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) a[ti] = bufB[(ti * 8 + g) * LD + ks * 4 + t];
+#pragma unroll
+        for (int tj = 0; tj < TM; ++tj) b[tj] = sF[(tj * 8 + g) * LD + ks * 4 + t];  // B[k][j] = F[j][k]
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+          for (int tj = ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+      }
+      store_sym<TM, LD>(bufA, c, g, t);
+      __syncwarp();
+      if (io.o_pred != nullptr && (io.every_step || k == io.steps - 1))
+        copy_out_mat<N>(io.o_pred + ((io.every_step ? (int64_t)k * io.nf : 0) + f) * (N * N), bufA, LD, N, N, lane);
+      // ---- PHt = P- H^T (160-161), y-hat = H x (155-157), H x- for the innovation (182-184)
+      double yhat, hxm;
+      {
+        double xmq[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) xmq[ks] = xms[ks * 4 + t];
+        double ph[TM][2];
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) ph[ti][0] = ph[ti][1] = 0.0;
+        double hx = 0.0, hm = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const double b = sH[g * LD + ks * 4 + t];  // B[k][a] = H[a][k]
+          hx = fma(b, xq[ks], hx);
+          hm = fma(b, xmq[ks], hm);
+#pragma unroll
+          for (int ti = 0; ti < TM; ++ti) dmma(ph[ti], bufA[(ti * 8 + g) * LD + ks * 4 + t], b);
+        }
+        yhat = quad_sum(hx);
+        hxm = quad_sum(hm);
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti)
+          *reinterpret_cast<double2*>(sPH + (ti * 8 + g) * kLdS + 2 * t) = make_double2(ph[ti][0], ph[ti][1]);
+      }
+      __syncwarp();
+      // ---- S = H PHt + R (162-163), in the C-fragment layout: this lane holds S[g][2t], S[g][2t+1]
+      double s[2];
+      {
+        const double2 r = *reinterpret_cast<const double2*>(sR + g * kLdS + 2 * t);
+        s[0] = r.x;
+        s[1] = r.y;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) dmma(s, sH[g * LD + ks * 4 + t], sPH[(ks * 4 + t) * kLdS + g]);
+      }
+      // ---- S <- inv(S) (164-167): in-place Gauss-Jordan; S is symmetric positive definite, so the
+      //      diagonal pivots are safe; a non-positive pivot is the reference's singular-S error
+      bool bad = false;
+#pragma unroll
+      for (int p = 0; p < kMP; ++p) {
+        const double mine = (p & 1) ? s[1] : s[0];
+        const double fcol = __shfl_sync(0xffffffffu, mine, (lane & ~3) | (p >> 1));  // S[g][p]
+        const double d = __shfl_sync(0xffffffffu, mine, p * 4 + (p >> 1));           // S[p][p]
+        const double p0 = __shfl_sync(0xffffffffu, s[0], p * 4 + t);                 // S[p][2t]
+        const double p1 = __shfl_sync(0xffffffffu, s[1], p * 4 + t);                 // S[p][2t+1]
+        bad = bad || !(d > 0.0) || !(d < 1e300);
+        const double dinv = rcp_nr(d);
+        const double r0 = (2 * t == p) ? dinv : p0 * dinv;
+        const double r1 = (2 * t + 1 == p) ? dinv : p1 * dinv;
+        if (g == p) {
+          s[0] = r0;
+          s[1] = r1;
+        } else {
+          s[0] = fma(-fcol, r0, (2 * t == p) ? 0.0 : s[0]);
+          s[1] = fma(-fcol, r1, (2 * t + 1 == p) ? 0.0 : s[1]);
+        }
+      }
+      if (bad) {  // warp-uniform: d is the same in every lane
+        status = GKB_ERR_SINGULAR_S;
+        break;
+      }
+      // ---- K = PHt inv(S) (168): inv(S) is symmetric, so B[k][a] = Sinv[a][k] sits in this lane's own row
+      double kc[TM][2];
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti) kc[ti][0] = kc[ti][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int col = ks * 4 + t;
+        const double e0 = __shfl_sync(0xffffffffu, s[0], (lane & ~3) | (col >> 1));
+        const double e1 = __shfl_sync(0xffffffffu, s[1], (lane & ~3) | (col >> 1));
+        const double b = (col & 1) ? e1 : e0;
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) dmma(kc[ti], sPH[(ti * 8 + g) * kLdS + ks * 4 + t], b);
+      }
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti)
+        *reinterpret_cast<double2*>(sK + (ti * 8 + g) * kLdS + 2 * t) = make_double2(kc[ti][0], kc[ti][1]);
+      // ---- innovation nu = y - H x- (182-184) and x+ = x- + K nu (186-195)
+      double yv = 0.0;
+      if (t == 0 && g < m) yv = io.y_shared ? __ldg(io.y + (int64_t)k * m + g) : __ldg(io.y + ((int64_t)k * io.nf + f) * m + g);
+      const double innov = (g < m) ? (yv - hxm) : 0.0;  // valid in the t == 0 lane of quad g
+      {
+        const double i0 = __shfl_sync(0xffffffffu, innov, (2 * t) * 4);
+        const double i1 = __shfl_sync(0xffffffffu, innov, (2 * t + 1) * 4);
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) {
+          const double dx = quad_sum(fma(kc[ti][0], i0, kc[ti][1] * i1));
+          if (t == 0) xs[ti * 8 + g] = xms[ti * 8 + g] + dx;
+        }
+      }
+      if (t == 0) {
+        sinn[g] = innov;
+        sinn[kMP + g] = (g < m) ? yhat : 0.0;
+      }
+      __syncwarp();
+      // ---- Joseph form (197-205), restructured: T2 = P- - K PHt^T
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < TM; ++tj) {
+          const double2 v = *reinterpret_cast<const double2*>(bufA + (ti * 8 + g) * LD + tj * 8 + 2 * t);
+          c[ti * TM + tj][0] = v.x;
+          c[ti * TM + tj][1] = v.y;
+        }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        double a[TM], b[TM];
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) a[ti] = -sK[(ti * 8 + g) * kLdS + ks * 4 + t];
+#pragma unroll
+        for (int tj = 0; tj < TM; ++tj) b[tj] = sPH[(tj * 8 + g) * kLdS + ks * 4 + t];  // B[k][j] = PHt[j][k]
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+          for (int tj = 0; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+      }
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < TM; ++tj)
+          *reinterpret_cast<double2*>(bufB + (ti * 8 + g) * LD + tj * 8 + 2 * t) =
+              make_double2(c[ti * TM + tj][0], c[ti * TM + tj][1]);
+      __syncwarp();
+      // ---- V = T2 H^T - K R
+      double vc[TM][2];
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti) vc[ti][0] = vc[ti][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const double b = sH[g * LD + ks * 4 + t];
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) dmma(vc[ti], bufB[(ti * 8 + g) * LD + ks * 4 + t], b);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const double b = sR[(ks * 4 + t) * kLdS + g];
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) dmma(vc[ti], -sK[(ti * 8 + g) * kLdS + ks * 4 + t], b);
+      }
+      // V takes the place of PHt (every lane is past its last read of sPH: the __syncwarp above)
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti)
+        *reinterpret_cast<double2*>(sPH + (ti * 8 + g) * kLdS + 2 * t) = make_double2(vc[ti][0], vc[ti][1]);
+      __syncwarp();
+      // ---- P+ = T2 - V K^T, upper tiles (c still holds T2), mirrored into bufA
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        double a[TM], b[TM];
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti) a[ti] = -sPH[(ti * 8 + g) * kLdS + ks * 4 + t];
+#pragma unroll
+        for (int tj = 0; tj < TM; ++tj) b[tj] = sK[(tj * 8 + g) * kLdS + ks * 4 + t];  // B[k][j] = K[j][k]
+#pragma unroll
+        for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+          for (int tj = ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+      }
+      store_sym<TM, LD>(bufA, c, g, t);
+      __syncwarp();
+      // ---- Estimate fields of this step
+      if (io.every_step || k == io.steps - 1) {
+        const int64_t row = (io.every_step ? (int64_t)k * io.nf : 0) + f;
+        if (io.o_state != nullptr)
+          for (int idx = lane; idx < N; idx += 32) io.o_state[row * N + idx] = xs[idx];
+        if (io.o_innov != nullptr && lane < m) io.o_innov[row * m + lane] = sinn[lane];
+        if (io.o_meas != nullptr && lane < m) io.o_meas[row * m + lane] = sinn[kMP + lane];
+        if (io.o_gain != nullptr) copy_out_mat<N>(io.o_gain + row * (int64_t)(N * m), sK, kLdS, N, m, lane);
+        if (io.o_covar != nullptr) copy_out_mat<N>(io.o_covar + row * (int64_t)(N * N), bufA, LD, N, N, lane);
+      }
+    }
+    // ---- state out (a failed filter keeps the state it had when the call started)
+    if (status == 0) {
+      bool finite = true;
+      for (int idx = lane; idx < N; idx += 32) finite = finite && isfinite(xs[idx]) && isfinite(bufA[idx * LD + idx]);
+      finite = __all_sync(0xffffffffu, finite);
+      if (!finite) status = GKB_ERR_NONFINITE;
+    }
+    if (status == 0) {
+      for (int idx = lane; idx < N; idx += 32) io.x[f * N + idx] = xs[idx];
+      double* Pg = io.P + f * (int64_t)(N * N);
+      for (int idx = lane; idx < N * N; idx += 32) Pg[idx] = bufA[(idx / N) * LD + idx % N];
+    } else if (lane == 0 && io.status != nullptr && io.status[f] == 0) {
+      io.status[f] = status;
+    }
+    __syncwarp();
+  }
+}
+
+template <int N>
+static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
+  constexpr int LD = N + 4;
+  constexpr size_t kShared = sizeof(double) * (2 * N * LD + kMP * LD + kMP * kLdS);
+  constexpr size_t kPerWarp = sizeof(double) * (2 * N * LD + 2 * N * kLdS + 2 * N + 2 * kMP);
+  static thread_local int cached_device = -1, sms = 148, max_smem = 227 * 1024;
+  if (cached_device != device) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaFuncSetAttribute(vanilla_tile_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cached_device = device;
+  }
+  int warps = (int)(((size_t)max_smem - kShared) / kPerWarp);
+  if (warps > 8) warps = 8;
+  if (warps < 1) return GKB_ERR_UNSUPPORTED;
+  int64_t ctas = (io.nf + warps - 1) / warps;
+  if (ctas > sms) ctas = sms;  // persistent: one CTA per SM, warps stride over the filters
+  const size_t smem = kShared + kPerWarp * warps;
+  vanilla_tile_kernel<N><<<(unsigned)ctas, warps * 32, smem, s>>>(io);
+  return 0;
+}
+
+int tile_shape_supported(int n, int m) { return (n == 16 || n == 24 || n == 32) && m >= 1 && m <= kMP; }
+
+int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s) {
+  switch (n) {
+    case 16: return launch_tile_shape<16>(io, device, s);
+    case 24: return launch_tile_shape<24>(io, device, s);
+    case 32: return launch_tile_shape<32>(io, device, s);
+    default: return GKB_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace gkb

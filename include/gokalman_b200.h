@@ -28,6 +28,8 @@ extern "C" {
 #endif
 
 #define GKB_MAX_N 8  /* one-filter-per-thread register kernels */
+#define GKB_TILE_MAX_N 32 /* large-state (warp-per-filter, FP64 tensor-core) Vanilla: n in {16, 24, 32}, m <= 8 */
+#define GKB_TILE_MAX_M 8
 #define GKB_MAX_M 3
 #define GKB_MAX_C 4
 #define GKB_MAX_Q 3
@@ -72,6 +74,11 @@ int gkb_shape_supported(int kind, int n, int m);
  *      x0_per_filter != 0, [n][n_filters].  P0 is n x n (for GKB_INFORMATION x0/P0 are the
  *      information state i0 and matrix I0).  G may be NULL (c = 0).  Arrays are host pointers and
  *      are copied.  Only the upper triangle of P0, Q, R is read (mat64.SymDense semantics). */
+/* Large-state handles: GKB_VANILLA with n in {16, 24, 32} and m <= 8 (no control, Noiseless noise,
+ * fixed model) runs one WARP per filter on the FP64 tensor-core path with the covariance resident in
+ * shared memory.  Such a handle uses FILTER-MAJOR arrays everywhere -- x0 (per filter) [N][n],
+ * state [N][n], covar [N][n*n], y [steps][N][m], outputs [steps][N][C] -- so that one filter's
+ * matrix is contiguous; gkb_filter_major() tells the caller which layout a handle uses. */
 int gkb_create_lti(int kind, int n, int m, int c, int64_t n_filters, int device,
                    const double* x0, int x0_per_filter, const double* P0,
                    const double* F, const double* G, const double* H, const double* Q, const double* R,
@@ -106,6 +113,8 @@ int gkb_reset(gkb_filter* f);
  * default stream, which is the default). */
 int gkb_set_stream(gkb_filter* f, void* stream);
 int64_t gkb_n_filters(const gkb_filter* f);
+/* 1 when the handle's per-filter arrays are filter-major [N][C] (large-state handles), 0 for SoA [C][N]. */
+int gkb_filter_major(const gkb_filter* f);
 int gkb_step(const gkb_filter* f);
 
 /* ---- outputs of an update call: the fields of Estimate (kalman.go:64-72), any pointer may be

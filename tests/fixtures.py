@@ -116,3 +116,19 @@ def scaled_err(a, ref):
     if floor == 0.0:
         return float(np.max(np.abs(a)))
     return float(np.max(np.abs(a - ref) / np.maximum(np.abs(ref), floor)))
+
+
+def synth_lti(n, m, seed=5):
+    """BASELINE configs[4]: seeded synthetic LTI model, shared by all filters.
+    F = I + dt A with A ~ U(-1, 1)/n; Q = 1e-3 L L^T; R = diag U(0.1, 1); H = first m rows of a seeded
+    orthogonal matrix; P0 = I; x0 = 0."""
+    rng = np.random.default_rng(seed)
+    dt = 0.1
+    F = np.eye(n) + dt * rng.uniform(-1.0, 1.0, (n, n)) / n
+    L = np.tril(rng.uniform(-1.0, 1.0, (n, n))) + np.eye(n)
+    Q = 1e-3 * (L @ L.T)
+    Q = 0.5 * (Q + Q.T)
+    R = np.diag(rng.uniform(0.1, 1.0, m))
+    Hfull, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    H = np.ascontiguousarray(Hfull[:m])
+    return dict(F=F, G=None, H=H, Q=Q, R=R, x0=np.zeros(n), P0=np.eye(n))

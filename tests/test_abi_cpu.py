@@ -43,7 +43,8 @@ def test_shape_table_and_version():
     for n, m in ((2, 1), (3, 1), (4, 1), (4, 2), (6, 2)):  # every BASELINE config shape of the register kernels
         for kind in range(6):
             assert lib.gkb_shape_supported(kind, n, m) == 1
-    assert lib.gkb_shape_supported(0, 32, 8) == 0
+    assert lib.gkb_shape_supported(0, 32, 8) == 1  # large-state Vanilla (kernels_tile.cu)
+    assert lib.gkb_shape_supported(2, 32, 8) == 0 and lib.gkb_shape_supported(0, 64, 8) == 0
 
 
 def _has_gpu():

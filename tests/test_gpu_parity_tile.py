@@ -1,0 +1,86 @@
+"""GPU parity, large-state Vanilla (BASELINE configs[4]: synthetic 32-state filters; warp-per-filter
+FP64 tensor-core kernel, kernels_tile.cu) against the CPU oracle's Vanilla.Update (vanilla.go:128-220)
+on the same inputs.  Tolerance 1e-10 of each array's max-abs, every Estimate field of every step."""
+import numpy as np
+import pytest
+
+import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+FIELDS = ("State", "Measurement", "Innovation", "Covariance", "PredCovariance", "Gain")
+
+
+def _gpu():
+    import gokalman_b200 as gk
+    gk.load()
+    return gk
+
+
+def _oracle_run(oracle, f, ys, x0=None):
+    kf = oracle.NewVanilla(f["x0"] if x0 is None else x0, f["P0"], f["F"], None, f["H"], f["Q"], f["R"])
+    return [kf.Update(y, None) for y in ys]
+
+
+@pytest.mark.parametrize("n,m,nf", [(32, 8, 19), (32, 3, 9), (16, 8, 40), (16, 1, 5), (24, 5, 11)])
+def test_tile_vanilla_every_step_matches_oracle(oracle, n, m, nf):
+    gk = _gpu()
+    f = fx.synth_lti(n, m, seed=100 + n + m)
+    rng = np.random.default_rng(n * 100 + m)
+    steps = 25
+    y = rng.standard_normal((steps, m, nf))
+    kf, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], None, f["H"], gk.NewNoiseless(f["Q"], f["R"]), n_filters=nf)
+    assert kf._fm  # the large-state (filter-major, warp-per-filter) path
+    est = kf.UpdateBatch(y, None, every_step=True)
+    assert np.all(est.status == 0)
+    for fi in sorted(set([0, 1, nf // 2, nf - 1])):
+        refs = _oracle_run(oracle, f, y[:, :, fi])
+        for name in FIELDS:
+            got = np.asarray(getattr(est, name)())
+            for k in (0, 1, steps // 2, steps - 1):
+                ref = np.asarray(getattr(refs[k], name)())
+                g = got[k][..., fi]
+                err = fx.scaled_err(g, ref.reshape(g.shape))
+                assert err <= TOL, (name, fi, k, err)
+
+
+def test_tile_vanilla_state_carries_over_calls_and_reset(oracle):
+    """Two calls of 10 steps == one call of 20 (state written back between calls), per-filter x0,
+    final-only outputs, GetState, Reset."""
+    gk = _gpu()
+    n, m, nf, steps = 32, 8, 300, 20  # 300 filters: more than one round of the persistent grid's first CTA
+    f = fx.synth_lti(n, m, seed=7)
+    rng = np.random.default_rng(77)
+    y = rng.standard_normal((steps, m, nf))
+    x0 = rng.standard_normal((n, nf))
+    kf, _ = gk.NewVanilla(x0, f["P0"], f["F"], None, f["H"], gk.NewNoiseless(f["Q"], f["R"]), n_filters=nf)
+    e1 = kf.UpdateBatch(y[:10], None, every_step=False, want=("state",))
+    e2 = kf.UpdateBatch(y[10:], None, every_step=False, want=("state", "covar"))
+    vec, mat = kf.GetState()
+    kf.Reset()
+    e3 = kf.UpdateBatch(y, None, every_step=False, want=("state", "covar"))
+    assert np.array_equal(np.asarray(e2.State()), np.asarray(e3.State()))
+    assert np.array_equal(np.asarray(e2.Covariance()), np.asarray(e3.Covariance()))
+    assert np.array_equal(vec, np.asarray(e3.State())) and np.array_equal(mat, np.asarray(e3.Covariance()))
+    for fi in (0, 150, 299):
+        refs = _oracle_run(oracle, f, y[:, :, fi], x0=x0[:, fi])
+        assert fx.scaled_err(np.asarray(e1.State())[:, fi], refs[9].State()) <= TOL
+        assert fx.scaled_err(np.asarray(e3.State())[:, fi], refs[-1].State()) <= TOL
+        assert fx.scaled_err(np.asarray(e3.Covariance())[:, :, fi], refs[-1].Covariance()) <= TOL
+
+
+def test_tile_vanilla_shared_measurement_and_singular_s(oracle):
+    gk = _gpu()
+    n, m, nf = 16, 8, 6
+    f = fx.synth_lti(n, m, seed=3)
+    y = np.random.default_rng(1).standard_normal((12, m))
+    kf, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], None, f["H"], gk.NewNoiseless(f["Q"], f["R"]), n_filters=nf)
+    est = kf.UpdateBatch(y, None, every_step=False, want=("state", "covar"))
+    refs = _oracle_run(oracle, f, y)
+    for fi in range(nf):
+        assert fx.scaled_err(np.asarray(est.State())[:, fi], refs[-1].State()) <= TOL
+    # H = 0, R = 0 -> S = 0: the reference fails with "could not invert" (vanilla.go:164-167)
+    kf2, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], None, np.zeros((m, n)), gk.NewNoiseless(f["Q"], np.zeros((m, m))),
+                           n_filters=nf)
+    est2 = kf2.UpdateBatch(y, None, every_step=False, want=("state",))
+    assert np.all(est2.status == -2)
