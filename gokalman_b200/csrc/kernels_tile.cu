@@ -6,20 +6,21 @@
 // per-filter measurement stream.  Per update the reference does 8n^3 + ... = 331 k flop at n = 32, m = 8
 // (SURVEY App. B); the only HBM traffic is the 8 m bytes of measurement per step, so the path is bound
 // by the FP64 pipe.  Layout of one step of one warp (g = lane / 4, t = lane % 4: the DMMA fragment
-// coordinates; all shared-memory matrices have a row pitch = 4 or 12 (mod 16) doubles, which makes the
-// A / B fragment loads and the C stores bank-conflict free):
+// coordinates; every shared-memory matrix is XOR-swizzled so that A / B fragment loads and C-fragment
+// loads / stores are all bank-conflict free; symmetric matrices keep only their upper triangle and the
+// lower one is read through the transposed address):
 //
 //   T    = F P                   4x4 tiles x 8 k-steps = 128 DMMA   (bufA -> bufB); F x rides on the A fragments
-//   P-   = T F^T + Q             upper 10 tiles x 8     =  80 DMMA   (bufB -> bufA, mirrored)
+//   P-   = T F^T + Q             upper 10 tiles x 8     =  80 DMMA   (bufB -> bufA)
 //   PHt  = P- H^T                4 tiles x 8            =  32 DMMA   (H x, H x- ride on the B fragments)
 //   S    = H PHt + R             1 tile x 8             =   8 DMMA   -> registers (C fragment)
 //   S^-1                         Gauss-Jordan on the C fragment, warp shuffles only (S is SPD: no pivoting)
 //   K    = PHt S^-1              4 tiles x 2            =   8 DMMA   (S^-1 reaches the B fragment by shuffles)
-//   T2   = P- - K PHt^T          16 tiles x 2           =  32 DMMA   (Joseph form with the products by I removed,
+//   T2   = P- - K PHt^T          upper 10 tiles x 2     =  20 DMMA   (Joseph form with the products by I removed,
 //   V    = T2 H^T - K R          4 tiles x (8 + 2)      =  40 DMMA    as in filters.cuh: vanilla_step)
-//   P+   = T2 - V K^T            upper 10 tiles x 2     =  20 DMMA   (-> bufA, mirrored)
+//   P+   = T2 - V K^T            upper 10 tiles x 2     =  20 DMMA   (-> bufA)
 //
-// 348 DMMA = 89 k FMA per update instead of the 166 k of the literal sequence.  m < 8 is handled by
+// 336 DMMA = 86 k FMA per update instead of the 166 k of the literal sequence.  m < 8 is handled by
 // padding H with zero rows and R with a unit diagonal (the padded block of S is I and contributes nothing).
 // Large-state handles use FILTER-MAJOR arrays (each filter's vector / matrix contiguous), see the header.
 #include "engine_internal.h"
@@ -29,8 +30,7 @@ namespace gkb {
 
 namespace {
 
-constexpr int kMP = 8;     // padded measurement size (one DMMA tile)
-constexpr int kLdS = 12;   // row pitch of the n x 8 and 8 x 8 matrices
+constexpr int kMP = 8;  // padded measurement size (one DMMA tile)
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -44,67 +44,96 @@ __device__ __forceinline__ double quad_sum(double v) {  // sum over the 4 lanes 
   return v;
 }
 
-// Store an upper-tile result (tiles ti <= tj of an n x n symmetric matrix held as C fragments) into a
-// full shared-memory matrix, mirroring it: the lower triangle is a copy of the upper one, which is what
-// AsSymDense (helper.go:65-84) keeps of the reference's dense product.
-template <int TM, int LD>
-__device__ __forceinline__ void store_sym(double* __restrict__ dst, const double (&c)[TM * TM][2], int g, int t) {
-#pragma unroll
-  for (int ti = 0; ti < TM; ++ti)
-#pragma unroll
-    for (int tj = ti; tj < TM; ++tj) {
-      const int r = ti * 8 + g, c0 = tj * 8 + 2 * t;
-      if (ti != tj) {
-        *reinterpret_cast<double2*>(dst + r * LD + c0) = make_double2(c[ti * TM + tj][0], c[ti * TM + tj][1]);
-        dst[c0 * LD + r] = c[ti * TM + tj][0];
-        dst[(c0 + 1) * LD + r] = c[ti * TM + tj][1];
-      } else {
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-          if (c0 + e >= r) {
-            dst[r * LD + c0 + e] = c[ti * TM + tj][e];
-            dst[(c0 + e) * LD + r] = c[ti * TM + tj][e];
-          }
-      }
-    }
-}
+// ---- shared-memory layouts ------------------------------------------------------------------------------
+// Every matrix is XOR-swizzled so that all three DMMA access patterns are bank-conflict free:
+//   A pattern  (lane -> row g, col k0 + t)         LDS.64, 16 lanes per wavefront = 4 rows x 4 columns
+//   B pattern  (lane -> row k0 + t, col n0 + g)    LDS.64, 4 rows x 4 columns
+//   C pattern  (lane -> row g, cols n0 + 2t, +1)   LDS/STS.128, 8 lanes per wavefront = 2 rows x 8 columns
+// n x n matrices: pitch LDB (multiple of 16), column c of row r lives at c ^ {0, 8, 4, 12}[r & 3];
+// n x 8 matrices: pitch 8, column c of row r lives at c ^ (4 * ((r >> 1) & 1)).
+__device__ __forceinline__ int swz_big(int r) { return ((r & 1) << 3) | ((r & 2) << 1); }
+__device__ __forceinline__ int swz_small(int r) { return (r & 2) << 1; }
+template <int LDB>
+__device__ __forceinline__ int idx_big(int r, int c) { return r * LDB + (c ^ swz_big(r)); }
+__device__ __forceinline__ int idx_small(int r, int c) { return r * 8 + (c ^ swz_small(r)); }
 
-template <int N>
-__device__ __forceinline__ void copy_out_mat(double* __restrict__ dst, const double* __restrict__ src, int ld, int rows,
-                                             int cols, int lane) {
-  for (int idx = lane; idx < rows * cols; idx += 32) dst[idx] = src[(idx / cols) * ld + idx % cols];
+// Per-lane constants of the fragment addressing (g = lane / 4, t = lane % 4).
+template <int LDB>
+struct Frag {
+  int g, t, swA, swB, sA8, sB8;
+  bool up_a0, up_a1, up_b0, up_b1;  // diagonal tiles of an upper-stored symmetric matrix: is (row, col) upper?
+  __device__ __forceinline__ explicit Frag(int lane) {
+    g = lane >> 2;
+    t = lane & 3;
+    swA = swz_big(g);
+    swB = swz_big(t);
+    sA8 = swz_small(g);
+    sB8 = swz_small(t);
+    up_a0 = g <= t;       // A pattern, even k-step: local (row g, col t)
+    up_a1 = g <= 4 + t;   //            odd k-step:  local (row g, col 4 + t)
+    up_b0 = t <= g;       // B pattern, even k-step: local (row t, col g)
+    up_b1 = 4 + t <= g;   //            odd k-step:  local (row 4 + t, col g)
+  }
+  // n x n matrices
+  __device__ __forceinline__ int a(int rt, int ks) const { return (rt * 8 + g) * LDB + ((ks * 4) ^ swA) + t; }
+  __device__ __forceinline__ int b(int ks, int ct) const { return (ks * 4 + t) * LDB + ((ct * 8 + g) ^ swB); }
+  __device__ __forceinline__ int c(int rt, int ct) const { return (rt * 8 + g) * LDB + ((ct * 8 + 2 * t) ^ swA); }
+  // symmetric n x n matrix of which only the upper triangle (tiles rt <= ct, and within the diagonal tiles
+  // row <= col) is stored: element (row, col) with row > col is read at (col, row)
+  __device__ __forceinline__ int sym_a(int rt, int ks) const {
+    const int kt = ks >> 1;
+    if (rt < kt) return a(rt, ks);
+    if (rt > kt) return b(ks, rt);
+    return ((ks & 1) ? up_a1 : up_a0) ? a(rt, ks) : b(ks, rt);
+  }
+  __device__ __forceinline__ int sym_b(int ks, int ct) const {
+    const int kt = ks >> 1;
+    if (kt < ct) return b(ks, ct);
+    if (kt > ct) return a(ct, ks);
+    return ((ks & 1) ? up_b1 : up_b0) ? b(ks, ct) : a(ct, ks);
+  }
+  // n x 8 matrices
+  __device__ __forceinline__ int a8(int rt, int ks) const { return (rt * 8 + g) * 8 + ((ks * 4) ^ sA8) + t; }
+  __device__ __forceinline__ int b8(int ks) const { return (ks * 4 + t) * 8 + (g ^ sB8); }
+  __device__ __forceinline__ int c8(int rt) const { return (rt * 8 + g) * 8 + ((2 * t) ^ sA8); }
+};
+
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void sts2(double* p, const double (&v)[2]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
 }
 
 }  // namespace
 
 template <int N>
 __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_constant__ TileIo io) {
-  constexpr int TM = N / 8, KS = N / 4, LD = N + 4;
-  static_assert(N % 8 == 0 && (LD % 16 == 4 || LD % 16 == 12), "row pitch must keep fragment loads conflict free");
+  constexpr int TM = N / 8, KS = N / 4, LDB = (N + 15) / 16 * 16;
+  static_assert(N % 8 == 0 && N <= 32, "tile kernel shapes");
   extern __shared__ __align__(16) double smem[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
+  const Frag<LDB> fr(lane);
+  const int g = fr.g, t = fr.t;
   // CTA-shared model
-  double* sF = smem;                 // [N][LD]
-  double* sQ = sF + N * LD;          // [N][LD]
-  double* sH = sQ + N * LD;          // [8][LD]   rows >= m are zero
-  double* sR = sH + kMP * LD;        // [8][12]   padded with a unit diagonal
-  double* wbase = sR + kMP * kLdS;
-  constexpr int kPerWarp = 2 * N * LD + 2 * N * kLdS + 2 * N + 2 * kMP;
-  double* bufA = wbase + (size_t)warp * kPerWarp;  // P, then P-, then P+
-  double* bufB = bufA + N * LD;                    // T, then T2
-  double* sPH = bufB + N * LD;                     // P- H^T, later V
-  double* sK = sPH + N * kLdS;                     // gain
-  double* xs = sK + N * kLdS;                      // posterior state
+  double* sF = smem;                // [N][LDB]
+  double* sQ = sF + N * LDB;        // [N][LDB]
+  double* sH = sQ + N * LDB;        // [8][LDB]  rows >= m are zero
+  double* sR = sH + kMP * LDB;      // [8][8]    padded with a unit diagonal
+  double* wbase = sR + kMP * 8;
+  constexpr int kPerWarp = 2 * N * LDB + 2 * N * 8 + 2 * N + 2 * kMP;
+  double* bufA = wbase + (size_t)warp * kPerWarp;  // P, then P-, then P+  (symmetric: upper triangle valid)
+  double* bufB = bufA + N * LDB;                   // T (full), then T2 (upper)
+  double* sPH = bufB + N * LDB;                    // P- H^T, later V
+  double* sK = sPH + N * 8;                        // gain
+  double* xs = sK + N * 8;                         // posterior state
   double* xms = xs + N;                            // predicted state
   double* sinn = xms + N;                          // innovation (8), y-hat (8)
 
   for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
-    sF[(idx / N) * LD + idx % N] = io.F[idx];
-    sQ[(idx / N) * LD + idx % N] = io.Q[idx];
+    sF[idx_big<LDB>(idx / N, idx % N)] = io.F[idx];
+    sQ[idx_big<LDB>(idx / N, idx % N)] = io.Q[idx];
   }
-  for (int idx = threadIdx.x; idx < kMP * N; idx += blockDim.x) sH[(idx / N) * LD + idx % N] = io.H[idx];
-  for (int idx = threadIdx.x; idx < kMP * kMP; idx += blockDim.x) sR[(idx / kMP) * kLdS + idx % kMP] = io.R[idx];
+  for (int idx = threadIdx.x; idx < kMP * N; idx += blockDim.x) sH[idx_big<LDB>(idx / N, idx % N)] = io.H[idx];
+  for (int idx = threadIdx.x; idx < kMP * kMP; idx += blockDim.x) sR[idx_small(idx / kMP, idx % kMP)] = io.R[idx];
   __syncthreads();
 
   const int m = io.m;
@@ -113,7 +142,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
     for (int idx = lane; idx < N; idx += 32) xs[idx] = io.x[f * N + idx];
     {
       const double* Pg = io.P + f * (int64_t)(N * N);
-      for (int idx = lane; idx < N * N; idx += 32) bufA[(idx / N) * LD + idx % N] = Pg[idx];
+      for (int idx = lane; idx < N * N; idx += 32) bufA[idx_big<LDB>(idx / N, idx % N)] = Pg[idx];
     }
     __syncwarp();
     int status = 0;
@@ -134,9 +163,9 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
         for (int ks = 0; ks < KS; ++ks) {
           double a[TM], b[TM];
 #pragma unroll
-          for (int ti = 0; ti < TM; ++ti) a[ti] = sF[(ti * 8 + g) * LD + ks * 4 + t];
+          for (int ti = 0; ti < TM; ++ti) a[ti] = sF[fr.a(ti, ks)];
 #pragma unroll
-          for (int tj = 0; tj < TM; ++tj) b[tj] = bufA[(ks * 4 + t) * LD + tj * 8 + g];
+          for (int tj = 0; tj < TM; ++tj) b[tj] = bufA[fr.sym_b(ks, tj)];
 #pragma unroll
           for (int ti = 0; ti < TM; ++ti) {
             xpart[ti] = fma(a[ti], xq[ks], xpart[ti]);
@@ -152,17 +181,15 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
 #pragma unroll
         for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
-          for (int tj = 0; tj < TM; ++tj)
-            *reinterpret_cast<double2*>(bufB + (ti * 8 + g) * LD + tj * 8 + 2 * t) =
-                make_double2(c[ti * TM + tj][0], c[ti * TM + tj][1]);
+          for (int tj = 0; tj < TM; ++tj) sts2(bufB + fr.c(ti, tj), c[ti * TM + tj]);
       }
       __syncwarp();
-      // ---- P- = T F^T + Q (150-152): upper tiles only, mirrored into bufA
+      // ---- P- = T F^T + Q (150-152): upper tiles only (AsSymDense keeps the upper triangle, helper.go:65-84)
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
         for (int tj = ti; tj < TM; ++tj) {
-          const double2 q = *reinterpret_cast<const double2*>(sQ + (ti * 8 + g) * LD + tj * 8 + 2 * t);
+          const double2 q = lds2(sQ + fr.c(ti, tj));
           c[ti * TM + tj][0] = q.x;
           c[ti * TM + tj][1] = q.y;
         }
@@ -170,18 +197,26 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
       for (int ks = 0; ks < KS; ++ks) {
         double a[TM], b[TM];
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) a[ti] = bufB[(ti * 8 + g) * LD + ks * 4 + t];
+        for (int ti = 0; ti < TM; ++ti) a[ti] = bufB[fr.a(ti, ks)];
 #pragma unroll
-        for (int tj = 0; tj < TM; ++tj) b[tj] = sF[(tj * 8 + g) * LD + ks * 4 + t];  // B[k][j] = F[j][k]
+        for (int tj = 0; tj < TM; ++tj) b[tj] = sF[fr.a(tj, ks)];  // B[k][j] = F[j][k]
 #pragma unroll
         for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
           for (int tj = ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
       }
-      store_sym<TM, LD>(bufA, c, g, t);
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < TM; ++tj) sts2(bufA + fr.c(ti, tj), c[ti * TM + tj]);
       __syncwarp();
-      if (io.o_pred != nullptr && (io.every_step || k == io.steps - 1))
-        copy_out_mat<N>(io.o_pred + ((io.every_step ? (int64_t)k * io.nf : 0) + f) * (N * N), bufA, LD, N, N, lane);
+      if (io.o_pred != nullptr && (io.every_step || k == io.steps - 1)) {
+        double* dst = io.o_pred + ((io.every_step ? (int64_t)k * io.nf : 0) + f) * (N * N);
+        for (int idx = lane; idx < N * N; idx += 32) {
+          const int r = idx / N, cc = idx % N;
+          dst[idx] = bufA[r <= cc ? idx_big<LDB>(r, cc) : idx_big<LDB>(cc, r)];
+        }
+      }
       // ---- PHt = P- H^T (160-161), y-hat = H x (155-157), H x- for the innovation (182-184)
       double yhat, hxm;
       {
@@ -194,27 +229,26 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
         double hx = 0.0, hm = 0.0;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          const double b = sH[g * LD + ks * 4 + t];  // B[k][a] = H[a][k]
+          const double b = sH[fr.a(0, ks)];  // B[k][a] = H[a][k]
           hx = fma(b, xq[ks], hx);
           hm = fma(b, xmq[ks], hm);
 #pragma unroll
-          for (int ti = 0; ti < TM; ++ti) dmma(ph[ti], bufA[(ti * 8 + g) * LD + ks * 4 + t], b);
+          for (int ti = 0; ti < TM; ++ti) dmma(ph[ti], bufA[fr.sym_a(ti, ks)], b);
         }
         yhat = quad_sum(hx);
         hxm = quad_sum(hm);
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti)
-          *reinterpret_cast<double2*>(sPH + (ti * 8 + g) * kLdS + 2 * t) = make_double2(ph[ti][0], ph[ti][1]);
+        for (int ti = 0; ti < TM; ++ti) sts2(sPH + fr.c8(ti), ph[ti]);
       }
       __syncwarp();
       // ---- S = H PHt + R (162-163), in the C-fragment layout: this lane holds S[g][2t], S[g][2t+1]
       double s[2];
       {
-        const double2 r = *reinterpret_cast<const double2*>(sR + g * kLdS + 2 * t);
+        const double2 r = lds2(sR + fr.c8(0));
         s[0] = r.x;
         s[1] = r.y;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) dmma(s, sH[g * LD + ks * 4 + t], sPH[(ks * 4 + t) * kLdS + g]);
+        for (int ks = 0; ks < KS; ++ks) dmma(s, sH[fr.a(0, ks)], sPH[fr.b8(ks)]);
       }
       // ---- S <- inv(S) (164-167): in-place Gauss-Jordan; S is symmetric positive definite, so the
       //      diagonal pivots are safe; a non-positive pivot is the reference's singular-S error
@@ -253,11 +287,10 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
         const double e1 = __shfl_sync(0xffffffffu, s[1], (lane & ~3) | (col >> 1));
         const double b = (col & 1) ? e1 : e0;
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) dmma(kc[ti], sPH[(ti * 8 + g) * kLdS + ks * 4 + t], b);
+        for (int ti = 0; ti < TM; ++ti) dmma(kc[ti], sPH[fr.a8(ti, ks)], b);
       }
 #pragma unroll
-      for (int ti = 0; ti < TM; ++ti)
-        *reinterpret_cast<double2*>(sK + (ti * 8 + g) * kLdS + 2 * t) = make_double2(kc[ti][0], kc[ti][1]);
+      for (int ti = 0; ti < TM; ++ti) sts2(sK + fr.c8(ti), kc[ti]);
       // ---- innovation nu = y - H x- (182-184) and x+ = x- + K nu (186-195)
       double yv = 0.0;
       if (t == 0 && g < m) yv = io.y_shared ? __ldg(io.y + (int64_t)k * m + g) : __ldg(io.y + ((int64_t)k * io.nf + f) * m + g);
@@ -276,12 +309,12 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
         sinn[kMP + g] = (g < m) ? yhat : 0.0;
       }
       __syncwarp();
-      // ---- Joseph form (197-205), restructured: T2 = P- - K PHt^T
+      // ---- Joseph form (197-205), restructured: T2 = P- - K PHt^T (symmetric: upper tiles)
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
-        for (int tj = 0; tj < TM; ++tj) {
-          const double2 v = *reinterpret_cast<const double2*>(bufA + (ti * 8 + g) * LD + tj * 8 + 2 * t);
+        for (int tj = ti; tj < TM; ++tj) {
+          const double2 v = lds2(bufA + fr.c(ti, tj));
           c[ti * TM + tj][0] = v.x;
           c[ti * TM + tj][1] = v.y;
         }
@@ -289,20 +322,18 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
       for (int ks = 0; ks < 2; ++ks) {
         double a[TM], b[TM];
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) a[ti] = -sK[(ti * 8 + g) * kLdS + ks * 4 + t];
+        for (int ti = 0; ti < TM; ++ti) a[ti] = -sK[fr.a8(ti, ks)];
 #pragma unroll
-        for (int tj = 0; tj < TM; ++tj) b[tj] = sPH[(tj * 8 + g) * kLdS + ks * 4 + t];  // B[k][j] = PHt[j][k]
+        for (int tj = 0; tj < TM; ++tj) b[tj] = sPH[fr.a8(tj, ks)];  // B[k][j] = PHt[j][k]
 #pragma unroll
         for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
-          for (int tj = 0; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+          for (int tj = ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
       }
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
-        for (int tj = 0; tj < TM; ++tj)
-          *reinterpret_cast<double2*>(bufB + (ti * 8 + g) * LD + tj * 8 + 2 * t) =
-              make_double2(c[ti * TM + tj][0], c[ti * TM + tj][1]);
+        for (int tj = ti; tj < TM; ++tj) sts2(bufB + fr.c(ti, tj), c[ti * TM + tj]);
       __syncwarp();
       // ---- V = T2 H^T - K R
       double vc[TM][2];
@@ -310,35 +341,37 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
       for (int ti = 0; ti < TM; ++ti) vc[ti][0] = vc[ti][1] = 0.0;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        const double b = sH[g * LD + ks * 4 + t];
+        const double b = sH[fr.a(0, ks)];
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) dmma(vc[ti], bufB[(ti * 8 + g) * LD + ks * 4 + t], b);
+        for (int ti = 0; ti < TM; ++ti) dmma(vc[ti], bufB[fr.sym_a(ti, ks)], b);
       }
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        const double b = sR[(ks * 4 + t) * kLdS + g];
+        const double b = sR[fr.b8(ks)];
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) dmma(vc[ti], -sK[(ti * 8 + g) * kLdS + ks * 4 + t], b);
+        for (int ti = 0; ti < TM; ++ti) dmma(vc[ti], -sK[fr.a8(ti, ks)], b);
       }
       // V takes the place of PHt (every lane is past its last read of sPH: the __syncwarp above)
 #pragma unroll
-      for (int ti = 0; ti < TM; ++ti)
-        *reinterpret_cast<double2*>(sPH + (ti * 8 + g) * kLdS + 2 * t) = make_double2(vc[ti][0], vc[ti][1]);
+      for (int ti = 0; ti < TM; ++ti) sts2(sPH + fr.c8(ti), vc[ti]);
       __syncwarp();
-      // ---- P+ = T2 - V K^T, upper tiles (c still holds T2), mirrored into bufA
+      // ---- P+ = T2 - V K^T, upper tiles (c still holds T2)
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         double a[TM], b[TM];
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) a[ti] = -sPH[(ti * 8 + g) * kLdS + ks * 4 + t];
+        for (int ti = 0; ti < TM; ++ti) a[ti] = -sPH[fr.a8(ti, ks)];
 #pragma unroll
-        for (int tj = 0; tj < TM; ++tj) b[tj] = sK[(tj * 8 + g) * kLdS + ks * 4 + t];  // B[k][j] = K[j][k]
+        for (int tj = 0; tj < TM; ++tj) b[tj] = sK[fr.a8(tj, ks)];  // B[k][j] = K[j][k]
 #pragma unroll
         for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
           for (int tj = ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
       }
-      store_sym<TM, LD>(bufA, c, g, t);
+#pragma unroll
+      for (int ti = 0; ti < TM; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < TM; ++tj) sts2(bufA + fr.c(ti, tj), c[ti * TM + tj]);
       __syncwarp();
       // ---- Estimate fields of this step
       if (io.every_step || k == io.steps - 1) {
@@ -347,21 +380,31 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
           for (int idx = lane; idx < N; idx += 32) io.o_state[row * N + idx] = xs[idx];
         if (io.o_innov != nullptr && lane < m) io.o_innov[row * m + lane] = sinn[lane];
         if (io.o_meas != nullptr && lane < m) io.o_meas[row * m + lane] = sinn[kMP + lane];
-        if (io.o_gain != nullptr) copy_out_mat<N>(io.o_gain + row * (int64_t)(N * m), sK, kLdS, N, m, lane);
-        if (io.o_covar != nullptr) copy_out_mat<N>(io.o_covar + row * (int64_t)(N * N), bufA, LD, N, N, lane);
+        if (io.o_gain != nullptr)
+          for (int idx = lane; idx < N * m; idx += 32) io.o_gain[row * (int64_t)(N * m) + idx] = sK[idx_small(idx / m, idx % m)];
+        if (io.o_covar != nullptr) {
+          double* dst = io.o_covar + row * (int64_t)(N * N);
+          for (int idx = lane; idx < N * N; idx += 32) {
+            const int r = idx / N, cc = idx % N;
+            dst[idx] = bufA[r <= cc ? idx_big<LDB>(r, cc) : idx_big<LDB>(cc, r)];
+          }
+        }
       }
     }
     // ---- state out (a failed filter keeps the state it had when the call started)
     if (status == 0) {
       bool finite = true;
-      for (int idx = lane; idx < N; idx += 32) finite = finite && isfinite(xs[idx]) && isfinite(bufA[idx * LD + idx]);
+      for (int idx = lane; idx < N; idx += 32) finite = finite && isfinite(xs[idx]) && isfinite(bufA[idx_big<LDB>(idx, idx)]);
       finite = __all_sync(0xffffffffu, finite);
       if (!finite) status = GKB_ERR_NONFINITE;
     }
     if (status == 0) {
       for (int idx = lane; idx < N; idx += 32) io.x[f * N + idx] = xs[idx];
       double* Pg = io.P + f * (int64_t)(N * N);
-      for (int idx = lane; idx < N * N; idx += 32) Pg[idx] = bufA[(idx / N) * LD + idx % N];
+      for (int idx = lane; idx < N * N; idx += 32) {
+        const int r = idx / N, cc = idx % N;
+        Pg[idx] = bufA[r <= cc ? idx_big<LDB>(r, cc) : idx_big<LDB>(cc, r)];
+      }
     } else if (lane == 0 && io.status != nullptr && io.status[f] == 0) {
       io.status[f] = status;
     }
@@ -371,9 +414,9 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
 
 template <int N>
 static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
-  constexpr int LD = N + 4;
-  constexpr size_t kShared = sizeof(double) * (2 * N * LD + kMP * LD + kMP * kLdS);
-  constexpr size_t kPerWarp = sizeof(double) * (2 * N * LD + 2 * N * kLdS + 2 * N + 2 * kMP);
+  constexpr int LDB = (N + 15) / 16 * 16;
+  constexpr size_t kShared = sizeof(double) * (2 * N * LDB + kMP * LDB + kMP * 8);
+  constexpr size_t kPerWarp = sizeof(double) * (2 * N * LDB + 2 * N * 8 + 2 * N + 2 * kMP);
   static thread_local int cached_device = -1, sms = 148, max_smem = 227 * 1024;
   if (cached_device != device) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

@@ -1,4 +1,4 @@
 set -x
 python -m pytest tests/test_gpu_parity_tile.py -m gpu -x -q 2>&1 | tail -15
-python bench.py --workload vanilla32 --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/tile_a.json
-python -c "import json;d=json.load(open('gpurun_out/tile_a.json'));print(d['value'],d['roofline'])"
+python bench.py --workload vanilla32 --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/tile_b.json
+python -c "import json;d=json.load(open('gpurun_out/tile_b.json'));print(d['value'],d['roofline'])"
