@@ -83,6 +83,7 @@ struct TileIo {
   const double* H;  // [8][n], rows >= m zero
   const double* R;  // [8][8], unit diagonal beyond m
   int every_step;
+  int stagger_ns;
   double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain;  // [rows][nf][C]
   int32_t* status;
 };

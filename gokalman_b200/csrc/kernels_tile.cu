@@ -23,6 +23,8 @@
 // 336 DMMA = 86 k FMA per update instead of the 166 k of the literal sequence.  m < 8 is handled by
 // padding H with zero rows and R with a unit diagonal (the padded block of S is I and contributes nothing).
 // Large-state handles use FILTER-MAJOR arrays (each filter's vector / matrix contiguous), see the header.
+#include <cstdlib>
+
 #include "engine_internal.h"
 #include "fastmath.cuh"
 
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
   __syncthreads();
 
   const int m = io.m;
+  if (io.stagger_ns > 0 && warp >= 4) __nanosleep(io.stagger_ns);  // experiment: de-phase the two warps of an SMSP
   for (int64_t f = (int64_t)blockIdx.x * warps + warp; f < io.nf; f += (int64_t)gridDim.x * warps) {
     // ---- state in: x -> xs, P -> bufA (coalesced: a filter's matrix is contiguous)
     for (int idx = lane; idx < N; idx += 32) xs[idx] = io.x[f * N + idx];
@@ -430,7 +433,10 @@ static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
   int64_t ctas = (io.nf + warps - 1) / warps;
   if (ctas > sms) ctas = sms;  // persistent: one CTA per SM, warps stride over the filters
   const size_t smem = kShared + kPerWarp * warps;
-  vanilla_tile_kernel<N><<<(unsigned)ctas, warps * 32, smem, s>>>(io);
+  TileIo io2 = io;
+  if (const char* e = getenv("GKB_TILE_STAGGER_NS")) io2.stagger_ns = atoi(e);
+  if (const char* e = getenv("GKB_TILE_WARPS")) { int w = atoi(e); if (w >= 1 && w <= warps) warps = w; }
+  vanilla_tile_kernel<N><<<(unsigned)ctas, warps * 32, kShared + kPerWarp * warps, s>>>(io2);
   return 0;
 }
 
