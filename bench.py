@@ -35,6 +35,23 @@ FLOPS_PER_UNIT = {"mc_jerk3": 537.0, "hybrid6": 2526.0}
 BYTES_PER_UNIT = {"mc_jerk3": 0.0, "hybrid6": 416.0}
 SEED = 0x5EED
 
+# Monte Carlo + chi-square workloads: (fixture, tested kind, NEES, NIS, controls, algorithmic flop per (trial, step))
+#   mc_jerk3       BASELINE configs[1]: truth 51 + vanilla 374 + NEES 81 + NIS 31 = 537
+#   mc_robot_info  BASELINE configs[2]: truth 29 + information 173 + NEES 30 = 232 (NIS of an information filter needs
+#                  n == m in the reference, information.go:272-274 -- the robot has n = 2, m = 1, so NEES only)
+#   mc_robot_sqrt  BASELINE configs[2]: truth 29 + square-root 123 + P = S S^T 16 + NEES 30 + NIS 19 = 217
+MC_WORKLOADS = {
+    "mc_jerk3": dict(fixture="jerk3", kind="VANILLA", nees=1, nis=1, controls="zero", flops=537.0,
+                     label="mc_jerk3: jerkcar 3-state vanilla KF Monte Carlo + chi-square (BASELINE configs[1])",
+                     kernel="mc_chisquare_kernel<3,1,VanillaTested>"),
+    "mc_robot_info": dict(fixture="robot_1d", kind="INFORMATION", nees=1, nis=0, controls="robot", flops=232.0,
+                          label="mc_robot_info: examples/robot 2-state information filter Monte Carlo + NEES (BASELINE configs[2])",
+                          kernel="mc_chisquare_kernel<2,1,InfoTested>"),
+    "mc_robot_sqrt": dict(fixture="robot_1d", kind="SQRT", nees=1, nis=1, controls="robot", flops=217.0,
+                          label="mc_robot_sqrt: examples/robot 2-state square-root filter Monte Carlo + chi-square (BASELINE configs[2])",
+                          kernel="mc_chisquare_kernel<2,1,SqrtTested>"),
+}
+
 
 # ------------------------------------------------------------------------------------------------
 # helpers
@@ -124,24 +141,31 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
-def mc_model():
-    f = fx.jerk3()  # helper_test.go:17-22 + montecarlo_test.go:12-19
-    return f
+def mc_model(workload="mc_jerk3"):
+    # jerk3: helper_test.go:17-22 + montecarlo_test.go:12-19; robot_1d: examples/robot/main.go:16-26
+    return getattr(fx, MC_WORKLOADS[workload]["fixture"])()
 
 
-def mc_config_struct(L, f, trials, trial_offset, steps, device):
-    """gkb_mc_config for the device-resident leg (PHILOX noise, zero controls like montecarlo.go:98-104)."""
+def mc_controls(workload, steps):
+    if MC_WORKLOADS[workload]["controls"] == "robot":
+        return fx.robot_controls(steps)  # examples/robot/main.go:36-39
+    return np.zeros((steps, 1))          # montecarlo.go:98-104: a single control vector means zero controls
+
+
+def mc_config_struct(L, f, trials, trial_offset, steps, device, workload="mc_jerk3"):
+    """gkb_mc_config for the device-resident leg (PHILOX noise)."""
+    spec = MC_WORKLOADS[workload]
     cfg = L.McConfig()
     keep = {k: np.ascontiguousarray(np.asarray(f[k], dtype=np.float64)) for k in ("F", "G", "H", "Q", "R", "x0", "P0")}
-    keep["u"] = np.zeros((steps, 1))
-    cfg.kind, cfg.n, cfg.m, cfg.c = L.VANILLA, 3, 1, 1
+    keep["u"] = np.ascontiguousarray(mc_controls(workload, steps))
+    cfg.kind, cfg.n, cfg.m, cfg.c = getattr(L, spec["kind"]), keep["F"].shape[0], keep["H"].shape[0], 1
     cfg.F, cfg.G, cfg.H, cfg.Q, cfg.R = (keep[k].ctypes.data for k in ("F", "G", "H", "Q", "R"))
     cfg.x0_truth = cfg.x0_filter = keep["x0"].ctypes.data
     cfg.P0 = keep["P0"].ctypes.data
     cfg.trials, cfg.trial_offset, cfg.steps = trials, trial_offset, steps
     cfg.controls = keep["u"].ctypes.data
     cfg.noise_mode, cfg.seed = L.NOISE_PHILOX, SEED
-    cfg.with_nees = cfg.with_nis = 1
+    cfg.with_nees, cfg.with_nis = spec["nees"], spec["nis"]
     cfg.device = device
     return cfg, keep
 
@@ -157,8 +181,10 @@ def run_ours_mc(args, rank, world, local):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     trials, steps = args.trials, args.filter_steps
-    f = mc_model()
-    cfg, keep = mc_config_struct(L, f, trials, rank * trials, steps, local)
+    wl = args.workload
+    spec = MC_WORKLOADS[wl]
+    f = mc_model(wl)
+    cfg, keep = mc_config_struct(L, f, trials, rank * trials, steps, local, wl)
     sums = torch.zeros(2, steps, dtype=torch.float64, device="cuda")
     out = L.McOutputs()
     out.mem, out.sums_only = L.DEVICE, 1
@@ -207,10 +233,10 @@ def run_ours_mc(args, rank, world, local):
     nis_mean, nees_mean = float(means[0].mean().item()), float(means[1].mean().item())
 
     # ---- e2e: the public API with HOST buffers (model + controls in, NIS/NEES means out), every step
-    controls = [np.zeros(1)]
+    controls = [np.zeros(1)] if spec["controls"] == "zero" else list(mc_controls(wl, steps))
     def step_e2e():
         runs = gk.NewMonteCarloRuns(trials, steps, 1, controls, mckf, trial_offset=rank * trials)
-        nis, nees = gk.NewChiSquare(chikf, runs, controls, True, True)
+        nis, nees = gk.NewChiSquare(chikf, runs, controls, bool(spec["nees"]), bool(spec["nis"]))
         if world > 1:
             t = torch.from_numpy(np.stack([nis, nees]) * trials).cuda()
             dist.all_reduce(t)
@@ -218,7 +244,8 @@ def run_ours_mc(args, rank, world, local):
         return nis, nees
     mckf, _ = gk.NewPurePredictorVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewAWGN(f["Q"], f["R"], seed=SEED),
                                          device=local)
-    chikf, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewNoiseless(f["Q"], f["R"]), device=local)
+    make_tested = {"VANILLA": gk.NewVanilla, "INFORMATION": gk.NewInformationFromState, "SQRT": gk.NewSquareRoot}[spec["kind"]]
+    chikf, _ = make_tested(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewNoiseless(f["Q"], f["R"]), device=local)
     step_e2e()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,32 +259,34 @@ def run_ours_mc(args, rank, world, local):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = float(trials) * steps * world * n_e2e / (float(e2e_ms.item()) * 1e-3)
-    h2d = 8 * (9 + 3 + 3 + 9 + 1 + 3 + 3 + 9 + steps * 1)  # F,G,H,Q,R,x0,x0,P0 + controls
+    nn, mm = keep["F"].shape[0], keep["H"].shape[0]
+    h2d = 8 * (nn * nn + nn + mm * nn + nn * nn + mm * mm + nn + nn + nn * nn + steps * 1)  # F,G,H,Q,R,x0,x0,P0 + controls
     d2h = 8 * 2 * steps + 4                                   # NIS, NEES means + the error word
-    assert np.allclose(nis_h.mean(), nis_mean, rtol=1e-9), (nis_h.mean(), nis_mean)
+    assert np.allclose(nees_h.mean(), nees_mean, rtol=1e-9), (nees_h.mean(), nees_mean)
 
     if rank != 0:
         return None
     main_ms = statistics.mean(kern_ms)
-    achieved_tf = FLOPS_PER_UNIT["mc_jerk3"] * float(trials) * steps / (main_ms * 1e-3) / 1e12
+    achieved_tf = spec["flops"] * float(trials) * steps / (main_ms * 1e-3) / 1e12
     line = {
         "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "mc_jerk3: jerkcar 3-state vanilla KF Monte Carlo + chi-square (BASELINE configs[1])",
-                   "trials_per_gpu": trials, "filter_steps": steps, "n": 3, "m": 1, "c": 1, "noise": "philox4x32-10 in-kernel",
+        "config": {"workload": spec["label"],
+                   "trials_per_gpu": trials, "filter_steps": steps, "n": nn, "m": mm, "c": 1, "noise": "philox4x32-10 in-kernel",
                    "sharding": "trials split by rank, one NCCL all-reduce of 2 x %d doubles per step" % steps,
                    "l2": "flushed between timed iterations (256 MiB memset)", "nis_mean": nis_mean, "nees_mean": nees_mean},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": None,
-                     "kernel": "mc_chisquare_kernel<3,1,VanillaTested>", "kernel_ms": main_ms,
-                     "flops_per_unit": FLOPS_PER_UNIT["mc_jerk3"], "peak_source": peak_src,
-                     "note": "537 algorithmic flop per (trial, step) per BASELINE.md s3; RNG/Box-Muller work not counted"},
+                     "kernel": spec["kernel"], "kernel_ms": main_ms,
+                     "flops_per_unit": spec["flops"], "peak_source": peak_src,
+                     "note": "%g algorithmic flop per (trial, step) per SURVEY App. B; RNG/Box-Muller work not counted" % spec["flops"]},
         "e2e": {"value": e2e_value, "unit": "filter-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "NewMonteCarloRuns + NewChiSquare (host buffers)"},
         "gpu_launches": 3 * args.steps,  # setup + fused MC kernel + finish per step (ours; torch memset/NCCL not counted)
         "clocks": clocks,
         "wall_s": wall,
+        "step_ms": [round(x, 3) for x in step_ms],
     }
     return line
 
@@ -265,26 +294,29 @@ def run_ours_mc(args, rank, world, local):
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm
 # ------------------------------------------------------------------------------------------------
-def oracle_mc_rate(trials, steps, threads):
+def oracle_mc_rate(trials, steps, threads, workload="mc_jerk3"):
     from oracle import gko
     gko.build()
-    f = mc_model()
+    spec = MC_WORKLOADS[workload]
+    f = mc_model(workload)
+    ctrl = None if spec["controls"] == "zero" else mc_controls(workload, steps)
     t0 = time.perf_counter()
-    r = gko.mc_chisquare(gko.VANILLA, f["F"], f["G"], f["H"], f["Q"], f["R"], f["x0"], f["x0"], f["P0"], trials, steps,
-                         controls=None, seed=SEED, threads=threads)
+    r = gko.mc_chisquare(getattr(gko, spec["kind"]), f["F"], f["G"], f["H"], f["Q"], f["R"], f["x0"], f["x0"], f["P0"],
+                         trials, steps, controls=ctrl, seed=SEED, threads=threads, with_nees=bool(spec["nees"]),
+                         with_nis=bool(spec["nis"]))
     dt = time.perf_counter() - t0
-    return trials * steps / dt, dt, float(r["NIS"].mean())
+    return trials * steps / dt, dt, float(r["NEES"].mean())
 
 
-def cpu_baseline(target_s=12.0):
+def cpu_baseline(target_s=12.0, workload="mc_jerk3"):
     cores = os.cpu_count() or 1
     steps = 1000
-    rate, _, _ = oracle_mc_rate(cores * 4, steps, cores)  # calibration
+    rate, _, _ = oracle_mc_rate(cores * 4, steps, cores, workload)  # calibration
     trials = max(cores, int(rate * target_s / steps / cores) * cores)
-    rate, dt, _ = oracle_mc_rate(trials, steps, cores)
+    rate, dt, _ = oracle_mc_rate(trials, steps, cores, workload)
     return {"value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port",
-            "sample": "%d trials x %d steps of mc_jerk3 (%.1f s), C oracle restatement with OpenMP over trials; "
-                      "the Go/gonum reference cannot be built here (no Go toolchain)" % (trials, steps, dt)}
+            "sample": "%d trials x %d steps of %s (%.1f s), C oracle restatement with OpenMP over trials; "
+                      "the Go/gonum reference cannot be built here (no Go toolchain)" % (trials, steps, workload, dt)}
 
 
 def run_reference(args, rank, world):
@@ -292,11 +324,13 @@ def run_reference(args, rank, world):
         return None
     cores = os.cpu_count() or 1
     steps = args.filter_steps
-    rate, _, _ = oracle_mc_rate(cores * 4, steps, cores)
+    wl = args.workload if args.workload in MC_WORKLOADS else "mc_jerk3"
+    f = mc_model(wl)
+    rate, _, _ = oracle_mc_rate(cores * 4, steps, cores, wl)
     trials = max(cores, int(rate * 6.0 / steps / cores) * cores)  # ~6 s of CPU per step
     times = []
     for i in range(args.warmup + args.steps):
-        r, dt, _ = oracle_mc_rate(trials, steps, cores)
+        r, dt, _ = oracle_mc_rate(trials, steps, cores, wl)
         if i >= args.warmup:
             times.append(dt)
     total = sum(times)
@@ -306,8 +340,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "mc_jerk3: jerkcar 3-state vanilla KF Monte Carlo + chi-square (BASELINE configs[1])",
-                   "filter_steps": steps, "n": 3, "m": 1, "c": 1},
+        "config": {"workload": MC_WORKLOADS[wl]["label"], "filter_steps": steps, "n": int(np.asarray(f["F"]).shape[0]),
+                   "m": int(np.asarray(f["H"]).shape[0]), "c": 1},
         "cpu_baseline": {"value": value, "unit": "filter-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "filter-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU oracle port (C, OpenMP); the reference is Go + un-vendored gonum and cannot be built in this image",
@@ -320,7 +354,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mc_jerk3", choices=["mc_jerk3", "hybrid6", "vanilla32"])
+    ap.add_argument("--workload", default="mc_jerk3", choices=["mc_jerk3", "mc_robot_info", "mc_robot_sqrt", "hybrid6", "srif6", "vanilla32"])
     ap.add_argument("--trials", type=int, default=1000000, help="Monte Carlo trials (filters) per GPU")
     ap.add_argument("--filter-steps", type=int, default=1000, help="filter steps per trial")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -332,7 +366,7 @@ def main():
         if line is not None:
             print(json.dumps(line), flush=True)
         return
-    if args.workload == "hybrid6":
+    if args.workload in ("hybrid6", "srif6"):
         from bench_hybrid import run_ours_hybrid
         line = run_ours_hybrid(args, rank, world, local)
     elif args.workload == "vanilla32":
@@ -341,8 +375,8 @@ def main():
     else:
         line = run_ours_mc(args, rank, world, local)
     if line is not None:
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_cpu_baseline and args.workload in MC_WORKLOADS:
+            line["cpu_baseline"] = cpu_baseline(workload=args.workload)
         elif "cpu_baseline" not in line:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -60,7 +60,15 @@ def run_ours_hybrid(args, rank, world, local):
     P0 = np.diag([10, 10, 10, 1, 1, 1.0])
     R = np.diag([1e-6, 1e-6])
     Q = np.diag([1e-12] * 3)
-    kf, _ = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R), m, n_filters=nf, device=local)
+    srif = args.workload == "srif6"
+    if srif:  # srif_test.go:70-80: P0 = diag(50,50,50,1,1,1)
+        P0 = np.diag([50, 50, 50, 1, 1, 1.0])
+        flags_np = np.full(steps, L.F_MEAS, dtype=np.uint8)
+        flags = torch.from_numpy(flags_np).to(dev)
+        make = lambda: gk.NewSRIF(np.zeros(n), P0, m, False, gk.NewNoiseless(Q, R), n_filters=nf, device=local)[0]
+    else:
+        make = lambda: gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R), m, n_filters=nf, device=local)[0]
+    kf = make()
     out_state = torch.zeros(n, nf, dtype=torch.float64, device=dev)
     out_cov = torch.zeros(n * n, nf, dtype=torch.float64, device=dev)
     status = torch.zeros(nf, dtype=torch.int32, device=dev)
@@ -114,7 +122,7 @@ def run_ours_hybrid(args, rank, world, local):
     hHt = Ht[:e_steps].cpu().pin_memory().numpy()
     hreal = real[:e_steps].cpu().pin_memory().numpy()
     hcomp = comp[:e_steps].cpu().pin_memory().numpy()
-    kf2, _ = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R), m, n_filters=nf, device=local)
+    kf2 = make()
     kf2.RunBatch(flags_np[:e_steps], hPhi, hHt, hreal, hcomp, None, every_step=False, want=("state", "covar"))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -136,22 +144,24 @@ def run_ours_hybrid(args, rank, world, local):
     main_ms = statistics.mean(kern_ms)
     ups = float(nf) * steps / (main_ms * 1e-3)
     gbs = ups * BYTES_IN / 1e9
-    tf = ups * FLOPS_EKF / 1e12
+    flops = 2168.0 if srif else FLOPS_EKF
+    tf = ups * flops / 1e12
     bound_hbm = (gbs / hbm) >= (tf / peak_tf)
     line = {
         "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams "
-                               "(BASELINE configs[3])", "filters_per_gpu": nf, "epochs": steps, "n": 6, "m": 2,
+        "config": {"workload": ("srif6: 6-state SRIF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])" if srif else
+                                "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams "
+                                "(BASELINE configs[3])"), "filters_per_gpu": nf, "epochs": steps, "n": 6, "m": 2,
                    "ekf_after": 15, "outputs": "final state + covariance only", "failed_filters": bad,
                    "l2": "inputs (%.1f GB) exceed L2; flushed anyway" % (nf * steps * BYTES_IN / 1e9)},
         "roofline": {"bound": "hbm" if bound_hbm else "fp64", "achieved": gbs if bound_hbm else tf,
                      "peak": hbm if bound_hbm else peak_tf, "unit": "GB/s" if bound_hbm else "TFLOP/s",
                      "frac": (gbs / hbm) if bound_hbm else (tf / peak_tf), "traffic": None,
-                     "kernel": "hybrid_run_wtma_kernel<6,2> (warp-private TMA tensor-map pipelines)", "kernel_ms": main_ms,
+                     "kernel": "srif_run_kernel<6,2>" if srif else "hybrid_run_wtma_kernel<6,2> (warp-private TMA tensor-map pipelines)", "kernel_ms": main_ms,
                      "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm, "bytes_per_unit": BYTES_IN, "source": hbm_src},
-                     "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf, "frac": tf / peak_tf, "flops_per_unit": FLOPS_EKF,
+                     "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf, "frac": tf / peak_tf, "flops_per_unit": flops,
                               "source": peak_src}},
         "e2e": {"value": e2e_value, "unit": "filter-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "HybridKF.RunBatch (pinned host buffers), %d epochs" % e_steps},
