@@ -568,7 +568,51 @@ class _NLDKF(_Filter):
         _lib.check(lib.gkb_nl_run(self._h, steps, _ptr(flags), _ptr(Phi), phi_shared, _ptr(Htilde), h_shared,
                                   _ptr(real_obs), _ptr(computed_obs), _ptr(Gamma), _lib.HOST, C.byref(out)))
         self._raise_status(status)
-        return Estimate(n, m, fields, status)
+        est = Estimate(n, m, fields, status)
+        # what the reference's estimates carry for smoothing (hybrid.go:193-196: copies of Phi and Gamma)
+        est._Phi, est._phi_shared, est._every_step = Phi, phi_shared, bool(every_step)
+        est._snc = bool(flags is not None and np.any(flags & _lib.F_SNC) and Gamma is not None)
+        self._steps_run = getattr(self, "_steps_run", 0) + steps
+        return est
+
+    def SmoothAll(self, estimates):
+        """hybrid.go:209-238 / srif.go:165-192: smooths, in place, the estimates of every epoch run so far.
+        `estimates` is the batched Estimate of ONE RunBatch(every_step=True) call covering all the filter's
+        epochs, or the list of single-epoch estimates returned by Update()/Predict()."""
+        lib = _lib.load()
+        n, nf = self._n, self._nf
+        if isinstance(estimates, (list, tuple)):
+            parts = list(estimates)
+            count = len(parts)
+        else:
+            parts = None
+            count = estimates._f["state"].shape[0] if estimates._every_step else 1
+        expected = _lib.load().gkb_step(self._h)
+        if count != expected:  # hybrid.go:210-212
+            raise GkbError(-10, "incorrect number of estimates provided: %d instead of expected %d" % (count, expected))
+        if parts is not None:
+            if any(e._snc for e in parts[1:]):
+                raise NotImplementedError("not yet implemented")  # hybrid.go:234 panics
+            shared = all(e._phi_shared for e in parts)
+            Phi = np.ascontiguousarray(np.concatenate(
+                [e._Phi if e._phi_shared == shared else np.repeat(e._Phi[:, :, None], nf, axis=2) for e in parts]))
+            xs = np.ascontiguousarray(np.concatenate([e._f["state"] for e in parts]))
+            Ps = np.ascontiguousarray(np.concatenate([e._f["covar"] for e in parts]))
+        else:
+            if estimates._snc:
+                raise NotImplementedError("not yet implemented")
+            Phi, shared = estimates._Phi, estimates._phi_shared
+            xs, Ps = estimates._f["state"], estimates._f["covar"]
+        status = np.zeros(nf, dtype=np.int32)
+        _lib.check(lib.gkb_smooth_all(n, count, nf, self._device, _ptr(Phi), int(shared), _ptr(xs), _ptr(Ps), _lib.HOST,
+                                      status.ctypes.data))
+        if np.any(status != 0):
+            raise GkbError(int(status[status != 0][0]), "provided STM is not invertible")
+        if parts is not None:
+            for k, e in enumerate(parts):
+                e._f["state"][...] = xs[k:k + 1]
+                e._f["covar"][...] = Ps[k:k + 1]
+        return None
 
 
 class HybridKF(_NLDKF):

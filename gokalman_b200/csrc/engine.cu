@@ -777,6 +777,44 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
   return 0;
 }
 
+// ---- SmoothAll -----------------------------------------------------------------------------------------
+int gkb_smooth_all(int n, int steps, int64_t n_filters, int device, const double* Phi, int phi_shared, double* state,
+                   double* covar, int mem, int32_t* status) {
+  if (!Phi || !state || !covar) return fail(GKB_ERR_ARG, "NULL argument");
+  if (n < 1 || n > 6) return fail(GKB_ERR_UNSUPPORTED, "no compiled smoothing kernel for n=%d", n);
+  if (steps < 1 || n_filters < 1) return fail(GKB_ERR_ARG, "steps and n_filters must be >= 1");
+  int rc = check_device(device);
+  if (rc) return rc;
+  cudaStream_t s = cudaStreamLegacy;
+  const size_t pb = sizeof(double) * (size_t)steps * n * n * (phi_shared ? 1 : n_filters);
+  const size_t xb = sizeof(double) * (size_t)steps * n * n_filters, cb = xb * n, sb = sizeof(int32_t) * n_filters;
+  Timer tm(s);
+  if (mem == GKB_DEVICE) {
+    if (status) GKB_CUDA(cudaMemsetAsync(status, 0, sb, s));
+    rc = launch_smooth_all(n, n_filters, steps, Phi, phi_shared, state, covar, status, s);
+    tm.stop(1, false);
+    GKB_CUDA(cudaGetLastError());
+    return rc ? fail(rc, "no smoothing kernel for n=%d", n) : 0;
+  }
+  DevBuf dphi, dx, dP, dst;
+  auto cleanup = [&]() { dphi.release(); dx.release(); dP.release(); dst.release(); };
+  if ((rc = dphi.ensure(pb)) || (rc = dx.ensure(xb)) || (rc = dP.ensure(cb)) || (rc = dst.ensure(sb))) { cleanup(); return rc; }
+  cudaMemcpyAsync(dphi.p, Phi, pb, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dx.p, state, xb, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dP.p, covar, cb, cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(dst.p, 0, sb, s);
+  rc = launch_smooth_all(n, n_filters, steps, dphi.as<double>(), phi_shared, dx.as<double>(), dP.as<double>(), dst.as<int32_t>(), s);
+  tm.stop(1, true);
+  cudaMemcpyAsync(state, dx.p, xb, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(covar, dP.p, cb, cudaMemcpyDeviceToHost, s);
+  if (status) cudaMemcpyAsync(status, dst.p, sb, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cleanup();
+  if (rc) return fail(rc, "no smoothing kernel for n=%d", n);
+  if (e != cudaSuccess) return fail(GKB_ERR_CUDA, "smoothing failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---- Monte Carlo + chi-square ------------------------------------------------------------------------
 
 namespace {

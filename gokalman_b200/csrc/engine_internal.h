@@ -133,6 +133,9 @@ int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStrea
 int launch_gu(const double* G_host, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s);
 int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s);
 int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s);
+// SmoothAll (hybrid.go:209-238, srif.go:165-192) over stored [steps][C][nf] histories, in place.
+int launch_smooth_all(int n, int64_t nf, int steps, const double* Phi, int phi_shared, double* xs, double* Ps,
+                      int32_t* status, cudaStream_t s);
 // Large-state Vanilla (kernels_tile.cu): n in {16, 24, 32}, m <= 8.
 int tile_shape_supported(int n, int m);
 int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s);

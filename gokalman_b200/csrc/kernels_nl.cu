@@ -162,6 +162,84 @@ srif_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant_
   if (io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
 }
 
+// ---- SmoothAll (hybrid.go:209-238, srif.go:165-192) ---------------------------------------------------------
+// Backward sweep over a stored history: for k = steps-2 .. 0:  S = inv(Phi_{k+1}),  x_k = S x_{k+1},
+// P_k = (S P_{k+1}) S^T (upper triangle kept, AsSymDense).  x_{k+1} / P_{k+1} are the values the previous
+// iteration wrote, so every estimate is the final one mapped back through the STMs -- exactly what the
+// reference's in-place loop does.  One filter per thread; per (filter, step) the kernel reads one Phi and
+// writes one state + covariance: HBM-bound streaming, no reuse.
+template <int N>
+__global__ void __launch_bounds__(kThreads)
+smooth_all_kernel(int64_t nf, int steps, const double* __restrict__ Phi, int phi_shared, double* __restrict__ xs,
+                  double* __restrict__ Ps, int32_t* __restrict__ status) {
+  constexpr int SN = N * (N + 1) / 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= nf) return;
+  double x[N], P[SN];
+  {
+    const double* xl = xs + (int64_t)(steps - 1) * N * nf + tid;
+    const double* Pl = Ps + (int64_t)(steps - 1) * N * N * nf + tid;
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = xl[(int64_t)i * nf];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = i; j < N; ++j) P[sym_idx<N>(i, j)] = Pl[(int64_t)(i * N + j) * nf];
+  }
+  for (int k = steps - 2; k >= 0; --k) {
+    double S[N * N];
+    nl_load<N * N>(S, Phi, phi_shared, k + 1, nf, tid);
+    if (inverse_lu<N>(S) != 0) {  // "provided STM is not invertible": the reference stops here
+      if (status != nullptr && status[tid] == 0) status[tid] = GKB_ERR_SINGULAR_PHI;
+      return;
+    }
+    double xn[N];
+    mulvec<N, N>(xn, S, x);
+    double Pn[SN];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double row[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double acc = S[i * N] * P[sym_idx<N>(0, j)];
+#pragma unroll
+        for (int l = 1; l < N; ++l) acc = fma(S[i * N + l], P[sym_idx<N>(l, j)], acc);
+        row[j] = acc;
+      }
+#pragma unroll
+      for (int j = i; j < N; ++j) {
+        double acc = row[0] * S[j * N];
+#pragma unroll
+        for (int l = 1; l < N; ++l) acc = fma(row[l], S[j * N + l], acc);
+        Pn[sym_idx<N>(i, j)] = acc;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = xn[i];
+#pragma unroll
+    for (int i = 0; i < SN; ++i) P[i] = Pn[i];
+    double* xo = xs + (int64_t)k * N * nf + tid;
+    double* Po = Ps + (int64_t)k * N * N * nf + tid;
+#pragma unroll
+    for (int i = 0; i < N; ++i) __stcs(xo + (int64_t)i * nf, x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) __stcs(Po + (int64_t)(i * N + j) * nf, P[sym_idx<N>(i, j)]);
+  }
+}
+
+int launch_smooth_all(int n, int64_t nf, int steps, const double* Phi, int phi_shared, double* xs, double* Ps,
+                      int32_t* status, cudaStream_t s) {
+  const unsigned grid = (unsigned)((nf + kThreads - 1) / kThreads);
+  switch (n) {
+#define GKB_SM(NN) case NN: smooth_all_kernel<NN><<<grid, kThreads, 0, s>>>(nf, steps, Phi, phi_shared, xs, Ps, status); return 0;
+    GKB_SM(1) GKB_SM(2) GKB_SM(3) GKB_SM(4) GKB_SM(5) GKB_SM(6)
+#undef GKB_SM
+    default: return GKB_ERR_UNSUPPORTED;
+  }
+}
+
 // ---- TMA-staged hybrid kernel --------------------------------------------------------------------------
 // Production configuration of the hybrid filter (per-filter Phi / Htilde / observation streams, no
 // SNC, outputs after the last epoch only).  A CTA owns 128 consecutive filters; the 52 (n=6, m=2)

@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
     __syncwarp();
     int status = 0;
     for (int k = 0; k < io.steps; ++k) {
+      // this step's measurement: requested now, consumed after the gain (HBM latency hidden by the DMMA stages)
+      double yv = 0.0;
+      if (t == 0 && g < m) yv = io.y_shared ? __ldg(io.y + (int64_t)k * m + g) : __ldg(io.y + ((int64_t)k * io.nf + f) * m + g);
       // this lane's slice of the previous posterior, x[ks*4 + t]
       double xq[KS];
 #pragma unroll
@@ -295,8 +298,6 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti) sts2(sK + fr.c8(ti), kc[ti]);
       // ---- innovation nu = y - H x- (182-184) and x+ = x- + K nu (186-195)
-      double yv = 0.0;
-      if (t == 0 && g < m) yv = io.y_shared ? __ldg(io.y + (int64_t)k * m + g) : __ldg(io.y + ((int64_t)k * io.nf + f) * m + g);
       const double innov = (g < m) ? (yv - hxm) : 0.0;  // valid in the t == 0 lane of quad g
       {
         const double i0 = __shfl_sync(0xffffffffu, innov, (2 * t) * 4);

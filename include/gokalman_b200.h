@@ -157,6 +157,17 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
                const double* Htilde, int h_shared, const double* real_obs, const double* computed_obs,
                const double* Gamma, int in_mem, const gkb_outputs* out);
 
+/* ---- SmoothAll (hybrid.go:209-238, srif.go:165-192): backward sweep over the stored estimates of a
+ *      run, in place.  For k = steps-2 .. 0:  S = inv(Phi[k+1]);  state[k] = S state[k+1];
+ *      covar[k] = S covar[k+1] S^T -- each step reads the values the previous one wrote, like the
+ *      reference's loop.  Phi [steps][n*n][N] (or [steps][n*n] shared), state [steps][n][N], covar
+ *      [steps][n*n][N]; `mem` says where all of them live.  status [N] (optional) gets
+ *      GKB_ERR_SINGULAR_PHI where an STM cannot be inverted (the reference returns an error there).
+ *      Epochs that used SNC (Gamma) are "not yet implemented" in the reference (hybrid.go:234 panics):
+ *      the caller must not pass such histories. */
+int gkb_smooth_all(int n, int steps, int64_t n_filters, int device, const double* Phi, int phi_shared,
+                   double* state, double* covar, int mem, int32_t* status);
+
 /* Raw filter state: x-like vector [n][N] and matrix [n*n][N] (vanilla/hybrid: x, P; information:
  * i, I; sqrt: x, S; SRIF: b, R).  Host pointers. */
 int gkb_get_state(const gkb_filter* f, double* vec, double* mat);

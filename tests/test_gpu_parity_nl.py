@@ -215,3 +215,38 @@ def test_hybrid_basic_lock_and_toggle(oracle):
                  (eg.Innovation(), eo.Innovation()), (eg.ObservationDev(), eo.ObservationDev())):
         assert fx.scaled_err(a, b) <= TOL
     assert eg.IsWithinNσ(1e6)
+
+
+@pytest.mark.parametrize("kind,n,m,nf,shared", [("hybrid", 6, 2, 37, False), ("hybrid", 4, 2, 5, True), ("srif", 6, 2, 9, False)])
+def test_smooth_all_matches_oracle(oracle, kind, n, m, nf, shared):
+    """SmoothAll (hybrid.go:209-238, srif.go:165-192): backward sweep over the stored estimates of a
+    batched run, every smoothed state / covariance of every step against the oracle's restatement."""
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS
+    rng = np.random.default_rng(4242 + n + nf)
+    steps = 23
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    if shared:
+        Phi = np.ascontiguousarray(Phi[:, :, :, 0])
+    P0 = np.diag(np.concatenate([np.full(n - n // 2, 10.0), np.full(n // 2, 1.0)]))
+    R = np.diag(np.full(m, 1e-2))
+    flags = np.array([F_MEAS if k % 5 != 3 else 0 for k in range(steps)], dtype=np.uint8)
+    if kind == "hybrid":
+        kf, _ = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(np.diag(np.full(3, 1e-3)), R), m, n_filters=nf)
+    else:
+        kf, _ = gk.NewSRIF(0.1 * np.ones(n), P0, m, False, gk.NewNoiseless(np.eye(n), R), n_filters=nf)
+    est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=True, want=("state", "covar"))
+    x_fwd = np.asarray(est.State()).reshape(steps, n, nf).copy()
+    P_fwd = np.asarray(est.Covariance()).reshape(steps, n, n, nf).copy()
+    with pytest.raises(gk.GkbError):  # hybrid.go:210-212: wrong number of estimates
+        kf.SmoothAll([est])
+    assert kf.SmoothAll(est) is None
+    xs = np.asarray(est.State()).reshape(steps, n, nf)
+    Ps = np.asarray(est.Covariance()).reshape(steps, n, n, nf)
+    assert np.array_equal(xs[-1], x_fwd[-1]) and np.array_equal(Ps[-1], P_fwd[-1])  # the last estimate is untouched
+    for f in range(nf):
+        Phi_f = Phi if shared else Phi[:, :, :, f]
+        xr, Pr = oracle.smooth_all(np.ascontiguousarray(Phi_f), x_fwd[:, :, f], P_fwd[:, :, :, f])
+        for k in range(steps):
+            assert fx.scaled_err(xs[k, :, f], xr[k]) <= TOL, (f, k)
+            assert fx.scaled_err(Ps[k, :, :, f], Pr[k]) <= TOL, (f, k)
