@@ -406,11 +406,11 @@ struct NlTensorMaps {
 };
 constexpr int kWStages = 2;
 
-template <int N, int M>
+template <int N, int M, bool SRIF>
 __global__ void __launch_bounds__(kThreads)
-hybrid_run_wtma_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant__ NlIo io,
-                       const __grid_constant__ NlTensorMaps maps) {
-  constexpr int SN = N * (N + 1) / 2;
+nl_run_wtma_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant__ NlIo io,
+                   const __grid_constant__ NlTensorMaps maps) {
+  constexpr int SN = SRIF ? N * N : N * (N + 1) / 2;  // SRIF keeps the full sqrt-information matrix R
   constexpr int ROWS_PHI = N * N, ROWS_H = M * N, ROWS = ROWS_PHI + ROWS_H + 2 * M;
   constexpr int kWarpsPerCta = kThreads / 32;
   constexpr uint32_t kBytesPhi = ROWS_PHI * 32 * 8, kBytesAll = ROWS * 32 * 8;
@@ -448,19 +448,28 @@ hybrid_run_wtma_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_co
       if (s < io.steps) issue(s, s);
   }
 
-  double x[N], P[SN];
+  double x[N], P[SN];  // hybrid: x, P (packed upper);  SRIF: b, R
   if (active) {
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = io.vec[(int64_t)i * io.nf + tid];
+    if constexpr (SRIF) {
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+      for (int i = 0; i < N * N; ++i) P[i] = io.mat[(int64_t)i * io.nf + tid];
+    } else {
 #pragma unroll
-      for (int j = i; j < N; ++j) P[sym_idx<N>(i, j)] = io.mat[(int64_t)(i * N + j) * io.nf + tid];
-  } else {
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i; j < N; ++j) P[sym_idx<N>(i, j)] = io.mat[(int64_t)(i * N + j) * io.nf + tid];
+    }
+  } else {  // lanes past the last filter run on an identity problem (the TMA zero-fills their columns)
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < SN; ++i) P[i] = 0.0;
+    if constexpr (SRIF) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) P[i * N + i] = 1.0;
+    }
   }
   int status = 0;
   int s = 0;
@@ -491,10 +500,47 @@ hybrid_run_wtma_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_co
     if (lane == 0 && k + kWStages < io.steps) issue(k + kWStages, s);
     if (++s == kWStages) { s = 0; phase ^= 1u; }
     NlOut<N, M> o;
-    int err = hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, nullptr, has_meas, ekf, false, o);
+    int err;
+    if constexpr (SRIF) {
+      if (!active) {  // keep the padding lanes' Phi invertible (zero-filled by the TMA)
+#pragma unroll
+        for (int i = 0; i < N; ++i) Phi[i * N + i] = 1.0;
+      }
+      err = srif_step<N, M>(md, x, P, Phi, Ht, ro, co, has_meas, o);
+    } else {
+      err = hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, nullptr, has_meas, ekf, false, o);
+    }
     if (err != 0 && status == 0) status = err;
   }
-  if (active) {
+  if constexpr (SRIF) {
+    // read-outs of the last estimate: State() = inv(R) b (srif.go:223-235), Covariance() = inv(R) inv(R)^T (253-265)
+    if (io.o_state != nullptr) {
+      double xs[N];
+      if (!srif_state<N>(xs, P, x)) {
+        if (status == 0) status = GKB_ERR_SINGULAR_R;
+#pragma unroll
+        for (int i = 0; i < N; ++i) xs[i] = 0.0;
+      }
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) io.o_state[(int64_t)i * io.nf + tid] = xs[i];
+      }
+    }
+    if (io.o_covar != nullptr) {
+      double Pc[N * N];
+      srif_covariance<N>(Pc, P);
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) io.o_covar[(int64_t)i * io.nf + tid] = Pc[i];
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) io.vec[(int64_t)i * io.nf + tid] = x[i];
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) io.mat[(int64_t)i * io.nf + tid] = P[i];
+    }
+  } else if (active) {
     if (io.o_state != nullptr) {
 #pragma unroll
       for (int i = 0; i < N; ++i) io.o_state[(int64_t)i * io.nf + tid] = x[i];
@@ -509,8 +555,8 @@ hybrid_run_wtma_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_co
         io.mat[(int64_t)(i * N + j) * io.nf + tid] = v;
         if (io.o_covar != nullptr) io.o_covar[(int64_t)(i * N + j) * io.nf + tid] = v;
       }
-    if (io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
   }
+  if (active && io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
 }
 
 // cuTensorMapEncodeTiled, fetched through the runtime so the library carries no link-time libcuda dependency.
@@ -549,57 +595,52 @@ static int launch_nl_shape(const HostModel& hm, const NlIo& io, cudaStream_t s) 
   for (int i = 0; i < hm.q * hm.q; ++i) md.Q[i] = hm.Q[i];
   for (int i = 0; i < M * M; ++i) { md.R[i] = hm.R[i]; md.L[i] = hm.L[i]; }
   md.q = hm.q;
-  if (hm.kind == GKB_HYBRID) {
-    // TMA-staged fast path: per-filter streams, no SNC epochs, final-estimate outputs only, rows that
-    // satisfy cp.async.bulk's 16-byte rules (even filter count, 16-byte aligned bases).
-    constexpr int ROWS = N * N + M * N + 2 * M;
-    const size_t smem = sizeof(double) * 2 * ROWS * kThreads + 2 * sizeof(uint64_t);
-    auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    const bool fast = !io.phi_shared && !io.h_shared && io.Gamma == nullptr && !io.every_step && io.Htilde != nullptr &&
-                      io.real_obs != nullptr && io.computed_obs != nullptr && (io.nf % 2 == 0) && aligned(io.Phi) &&
-                      aligned(io.Htilde) && aligned(io.real_obs) && aligned(io.computed_obs) && io.o_meas == nullptr &&
-                      io.o_innov == nullptr && io.o_pred == nullptr && io.o_gain == nullptr && io.o_obsdev == nullptr &&
-                      smem <= 110 * 1024 && io.steps >= 2 && io.nf < 0x7fffffffLL;
-    const char* path = getenv("GKB_NL_PATH");  // A/B switch for tests and profiling: plain | bulk | tensor
-    const bool want_bulk = path && !strcmp(path, "bulk"), want_plain = path && !strcmp(path, "plain");
-    if (fast && !want_plain && !want_bulk) {
-      NlTensorMaps maps;
-      const int64_t st = io.steps;
-      if (make_stream_map(&maps.phi, io.Phi, io.nf, st * N * N, N * N) &&
-          make_stream_map(&maps.h, io.Htilde, io.nf, st * M * N, M * N) &&
-          make_stream_map(&maps.real_obs, io.real_obs, io.nf, st * M, M) &&
-          make_stream_map(&maps.computed_obs, io.computed_obs, io.nf, st * M, M)) {
-        auto kern = hybrid_run_wtma_kernel<N, M>;
-        const size_t wsmem = sizeof(double) * (kThreads / 32) * kWStages * ROWS * 32 + (kThreads / 32) * kWStages * sizeof(uint64_t);
-        static thread_local bool wattr_set = false;
-        if (!wattr_set) {
-          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
-          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-          wattr_set = true;
-        }
-        kern<<<grid, kThreads, wsmem, s>>>(md, io, maps);
-        return 0;
-      }
-    }
-    if (fast && want_bulk) {
-      auto kern = hybrid_run_tma_kernel<N, M>;
-      static thread_local bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // TMA-staged fast path (the production configuration of both NLDKF kinds): per-filter streams, no SNC
+  // epochs, final-estimate outputs only, streams that satisfy the TMA's 16-byte rules (even filter count,
+  // 16-byte aligned bases).
+  constexpr int ROWS = N * N + M * N + 2 * M;
+  const size_t smem = sizeof(double) * 2 * ROWS * kThreads + 2 * sizeof(uint64_t);
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool fast = !io.phi_shared && !io.h_shared && io.Gamma == nullptr && !io.every_step && io.Htilde != nullptr &&
+                    io.real_obs != nullptr && io.computed_obs != nullptr && (io.nf % 2 == 0) && aligned(io.Phi) &&
+                    aligned(io.Htilde) && aligned(io.real_obs) && aligned(io.computed_obs) && io.o_meas == nullptr &&
+                    io.o_innov == nullptr && io.o_pred == nullptr && io.o_gain == nullptr && io.o_obsdev == nullptr &&
+                    smem <= 110 * 1024 && io.steps >= 2 && io.nf < 0x7fffffffLL;
+  const char* path = getenv("GKB_NL_PATH");  // A/B switch for tests and profiling: plain | bulk | tensor
+  const bool want_bulk = path && !strcmp(path, "bulk"), want_plain = path && !strcmp(path, "plain");
+  const bool srif = hm.kind == GKB_SRIF;
+  if (hm.kind != GKB_HYBRID && !srif) return GKB_ERR_UNSUPPORTED;
+  if (fast && !want_plain && !(want_bulk && !srif)) {
+    NlTensorMaps maps;
+    const int64_t st = io.steps;
+    if (make_stream_map(&maps.phi, io.Phi, io.nf, st * N * N, N * N) &&
+        make_stream_map(&maps.h, io.Htilde, io.nf, st * M * N, M * N) &&
+        make_stream_map(&maps.real_obs, io.real_obs, io.nf, st * M, M) &&
+        make_stream_map(&maps.computed_obs, io.computed_obs, io.nf, st * M, M)) {
+      const size_t wsmem = sizeof(double) * (kThreads / 32) * kWStages * ROWS * 32 + (kThreads / 32) * kWStages * sizeof(uint64_t);
+      auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
-      }
-      kern<<<grid, kThreads, smem, s>>>(md, io);
+        kern<<<grid, kThreads, wsmem, s>>>(md, io, maps);
+      };
+      if (srif) launch(nl_run_wtma_kernel<N, M, true>);
+      else launch(nl_run_wtma_kernel<N, M, false>);
       return 0;
     }
-    hybrid_run_kernel<N, M><<<grid, kThreads, 0, s>>>(md, io);
-    return 0;
   }
-  if (hm.kind == GKB_SRIF) {
+  if (srif) {
     srif_run_kernel<N, M><<<grid, kThreads, 0, s>>>(md, io);
     return 0;
   }
-  return GKB_ERR_UNSUPPORTED;
+  if (fast && want_bulk) {
+    auto kern = hybrid_run_tma_kernel<N, M>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<grid, kThreads, smem, s>>>(md, io);
+    return 0;
+  }
+  hybrid_run_kernel<N, M><<<grid, kThreads, 0, s>>>(md, io);
+  return 0;
 }
 
 int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s) {

@@ -130,40 +130,70 @@ GKB_DEV int inverse_lu(double (&a)[N * N]) {
       for (int j = 0; j < N; ++j) s += fabs(a[i * N + j]);
       anorm = fmax(anorm, s);
     }
+    // Two warp-uniform shortcuts for N >= 3 (the votes are over the lanes that are converged here):
+    //  * the input is upper triangular in every lane (the SRIF's R after a measurement update, srif.go:223-235):
+    //    dgetf2 would find no pivot to swap and only zero multipliers, so the factorisation and the
+    //    dgetri back-multiplication are skipped -- the result is the same dtrti2 inverse, bit for bit;
+    //  * no lane needs a row / column interchange: the predicated register swaps (N^2 selects per column)
+    //    are skipped.
+    constexpr bool kVote = N >= 3;
+    bool tri = false;
+    if constexpr (kVote) {
+      bool lower_zero = true;
+#pragma unroll
+      for (int i = 1; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) lower_zero = lower_zero && (a[i * N + j] == 0.0);
+      tri = __all_sync(__activemask(), lower_zero);
+    }
     int piv[N];
     bool singular = false;
+    bool any_swap = false;
+    if (tri) {
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      int p = j;
-      double pmax = fabs(a[j * N + j]);
-#pragma unroll
-      for (int i = j + 1; i < N; ++i) {
-        double v = fabs(a[i * N + j]);
-        if (v > pmax) { pmax = v; p = i; }
+      for (int j = 0; j < N; ++j) {
+        piv[j] = j;
+        singular = singular || (a[j * N + j] == 0.0);
       }
-      piv[j] = p;
-      if (pmax != 0.0) {
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        int p = j;
+        double pmax = fabs(a[j * N + j]);
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
-          bool sw = (p == i);
-#pragma unroll
-          for (int l = 0; l < N; ++l) {
-            double t0 = a[j * N + l], t1 = a[i * N + l];
-            a[j * N + l] = sw ? t1 : t0;
-            a[i * N + l] = sw ? t0 : t1;
-          }
+          double v = fabs(a[i * N + j]);
+          if (v > pmax) { pmax = v; p = i; }
         }
-        double rinv = rcp_nr(a[j * N + j]);
+        piv[j] = p;
+        if (pmax != 0.0) {
+          bool do_swaps = true;
+          if constexpr (kVote) do_swaps = __any_sync(__activemask(), p != j);
+          any_swap = any_swap || (p != j);
+          if (do_swaps) {
 #pragma unroll
-        for (int i = j + 1; i < N; ++i) a[i * N + j] *= rinv;
-      } else {
-        singular = true;
-      }
+            for (int i = j + 1; i < N; ++i) {
+              bool sw = (p == i);
 #pragma unroll
-      for (int i = j + 1; i < N; ++i) {
-        double lij = a[i * N + j];
+              for (int l = 0; l < N; ++l) {
+                double t0 = a[j * N + l], t1 = a[i * N + l];
+                a[j * N + l] = sw ? t1 : t0;
+                a[i * N + l] = sw ? t0 : t1;
+              }
+            }
+          }
+          double rinv = rcp_nr(a[j * N + j]);
 #pragma unroll
-        for (int l = j + 1; l < N; ++l) a[i * N + l] = fma(-lij, a[j * N + l], a[i * N + l]);
+          for (int i = j + 1; i < N; ++i) a[i * N + j] *= rinv;
+        } else {
+          singular = true;
+        }
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+          double lij = a[i * N + j];
+#pragma unroll
+          for (int l = j + 1; l < N; ++l) a[i * N + l] = fma(-lij, a[j * N + l], a[i * N + l]);
+        }
       }
     }
     if (singular) return 1;
@@ -182,33 +212,39 @@ GKB_DEV int inverse_lu(double (&a)[N * N]) {
 #pragma unroll
       for (int i = 0; i < j; ++i) a[i * N + j] *= ajj;
     }
-    // inv(A) L = inv(U)  (dgetri, unblocked)
+    if (!tri) {
+      // inv(A) L = inv(U)  (dgetri, unblocked)
 #pragma unroll
-    for (int j = N - 2; j >= 0; --j) {
-      double work[N];
+      for (int j = N - 2; j >= 0; --j) {
+        double work[N];
 #pragma unroll
-      for (int i = j + 1; i < N; ++i) {
-        work[i] = a[i * N + j];
-        a[i * N + j] = 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double t = a[i * N + j + 1] * work[j + 1];
-#pragma unroll
-        for (int l = j + 2; l < N; ++l) t = fma(a[i * N + l], work[l], t);
-        a[i * N + j] -= t;
-      }
-    }
-#pragma unroll
-    for (int j = N - 2; j >= 0; --j) {
-#pragma unroll
-      for (int jp = j + 1; jp < N; ++jp) {
-        bool sw = (piv[j] == jp);
+        for (int i = j + 1; i < N; ++i) {
+          work[i] = a[i * N + j];
+          a[i * N + j] = 0.0;
+        }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          double t0 = a[i * N + j], t1 = a[i * N + jp];
-          a[i * N + j] = sw ? t1 : t0;
-          a[i * N + jp] = sw ? t0 : t1;
+          double t = a[i * N + j + 1] * work[j + 1];
+#pragma unroll
+          for (int l = j + 2; l < N; ++l) t = fma(a[i * N + l], work[l], t);
+          a[i * N + j] -= t;
+        }
+      }
+      bool do_swaps = true;
+      if constexpr (kVote) do_swaps = __any_sync(__activemask(), any_swap);
+      if (do_swaps) {
+#pragma unroll
+        for (int j = N - 2; j >= 0; --j) {
+#pragma unroll
+          for (int jp = j + 1; jp < N; ++jp) {
+            bool sw = (piv[j] == jp);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              double t0 = a[i * N + j], t1 = a[i * N + jp];
+              a[i * N + j] = sw ? t1 : t0;
+              a[i * N + jp] = sw ? t0 : t1;
+            }
+          }
         }
       }
     }

@@ -143,6 +143,49 @@ def test_hybrid_tma_staged_path_matches_oracle(oracle, n, m, nf):
         assert fx.scaled_err(vec[:, f], ref.State()) <= TOL and fx.scaled_err(mat[:, :, f], ref.Covariance()) <= TOL
 
 
+@pytest.mark.parametrize("n,m,nf", [(6, 2, 130), (4, 2, 34), (6, 3, 64)])
+def test_srif_tma_staged_path_matches_oracle(oracle, n, m, nf):
+    """SRIF on the production path (final read-outs only, per-filter streams): the warp-private TMA
+    kernel, with Predict epochs (dense R afterwards: the general LU inverse) and Update epochs
+    (upper-triangular R: the triangular shortcut of inverse_lu).  Equal to the plain-load kernel bit
+    for bit and to the oracle to 1e-10: State(), Covariance(), raw b and R."""
+    import os
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS, F_EKF, F_SNC
+    rng = np.random.default_rng(1900 + n + nf)
+    steps = 33
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    P0 = np.diag(np.concatenate([np.full(n - n // 2, 50.0), np.full(n // 2, 1.0)]))
+    R = np.diag(np.full(m, 1e-2))
+    flags = np.array([F_MEAS if (k % 5 != 3) else 0 for k in range(steps)], dtype=np.uint8)
+
+    def run(path):
+        if path:
+            os.environ["GKB_NL_PATH"] = path
+        try:
+            kf, _ = gk.NewSRIF(0.2 * np.ones(n), P0, m, False, gk.NewNoiseless(np.zeros((n, n)), R), n_filters=nf)
+            est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=False, want=("state", "covar"))
+            vec, mat = kf.GetState()
+        finally:
+            os.environ.pop("GKB_NL_PATH", None)
+        return est, vec, mat
+    est, vec, mat = run(None)
+    assert np.all(est.status == 0)
+    est2, vec2, mat2 = run("plain")
+    assert np.array_equal(vec, vec2) and np.array_equal(mat, mat2)
+    assert np.array_equal(np.asarray(est.State()), np.asarray(est2.State()))
+    assert np.array_equal(np.asarray(est.Covariance()), np.asarray(est2.Covariance()))
+    for f in sorted(set([0, 1, nf // 2, nf - 2, nf - 1])):
+        o = oracle.NewSRIF(0.2 * np.ones(n), P0, m, False, R)
+        ref = _oracle_run(o, flags, Phi, Ht, real, comp, None, f, F_MEAS, F_EKF, F_SNC)[-1]
+        xs = np.asarray(est.State()).reshape(n, nf)[:, f]
+        Pc = np.asarray(est.Covariance()).reshape(n, n, nf)[:, :, f]
+        assert fx.scaled_err(xs, ref.State()) <= TOL, (f, fx.scaled_err(xs, ref.State()))
+        assert fx.scaled_err(Pc, ref.Covariance()) <= TOL, (f, fx.scaled_err(Pc, ref.Covariance()))
+        rv, rm, _ = ref.raw()
+        assert fx.scaled_err(vec[:, f], rv) <= TOL and fx.scaled_err(mat[:, :, f], np.asarray(rm).reshape(n, n)) <= TOL
+
+
 @pytest.mark.parametrize("n,m", [(6, 2), (4, 2), (3, 1)])
 def test_srif_matches_oracle(oracle, n, m):
     """srif.go:101-160 with per-filter Phi / Htilde; State(), Covariance(), PredCovariance() read-outs."""
