@@ -124,6 +124,18 @@ def fp64_peak():
         return 34.2, "fallback constant (profiles/r01_peak_fp64.json)"
 
 
+def measured_traffic(workload, is_default_config):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu
+    capture of this same bench configuration (tools/measure_traffic.sh -> profiles/r01_traffic.json); None when
+    the run uses another size."""
+    if not is_default_config:
+        return None
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[workload]["traffic"]
+    except Exception:
+        return None
+
+
 def hbm_peak():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json (of measured)"
@@ -277,7 +289,8 @@ def run_ours_mc(args, rank, world, local):
                    "sharding": "trials split by rank, one NCCL all-reduce of 2 x %d doubles per step" % steps,
                    "l2": "flushed between timed iterations (256 MiB memset)", "nis_mean": nis_mean, "nees_mean": nees_mean},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None,
+                     "frac": achieved_tf / peak_tf,
+                     "traffic": measured_traffic(wl, trials == 1000000 and steps == 1000),
                      "kernel": spec["kernel"], "kernel_ms": main_ms,
                      "flops_per_unit": spec["flops"], "peak_source": peak_src,
                      "note": "%g algorithmic flop per (trial, step) per SURVEY App. B; RNG/Box-Muller work not counted" % spec["flops"]},

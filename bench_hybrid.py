@@ -44,7 +44,7 @@ def run_ours_hybrid(args, rank, world, local):
     import torch.distributed as dist
     import gokalman_b200 as gk
     from gokalman_b200 import _lib as L
-    from bench import ClockSampler, fp64_peak, hbm_peak
+    from bench import ClockSampler, fp64_peak, hbm_peak, measured_traffic
 
     lib = gk.load()
     torch.cuda.set_device(local)
@@ -158,7 +158,9 @@ def run_ours_hybrid(args, rank, world, local):
                    "l2": "inputs (%.1f GB) exceed L2; flushed anyway" % (nf * steps * BYTES_IN / 1e9)},
         "roofline": {"bound": "hbm" if bound_hbm else "fp64", "achieved": gbs if bound_hbm else tf,
                      "peak": hbm if bound_hbm else peak_tf, "unit": "GB/s" if bound_hbm else "TFLOP/s",
-                     "frac": (gbs / hbm) if bound_hbm else (tf / peak_tf), "traffic": None,
+                     "frac": (gbs / hbm) if bound_hbm else (tf / peak_tf),
+                     "traffic": measured_traffic(args.workload, nf == 100000 and steps == 200),
+                     "algorithmic_bytes": float(nf) * steps * BYTES_IN,
                      "kernel": "srif_run_kernel<6,2>" if srif else "hybrid_run_wtma_kernel<6,2> (warp-private TMA tensor-map pipelines)", "kernel_ms": main_ms,
                      "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm, "bytes_per_unit": BYTES_IN, "source": hbm_src},
                      "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf, "frac": tf / peak_tf, "flops_per_unit": flops,

@@ -17,7 +17,7 @@ def run_ours_tile(args, rank, world, local):
     import torch.distributed as dist
     import gokalman_b200 as gk
     from gokalman_b200 import _lib as L
-    from bench import ClockSampler, fp64_peak
+    from bench import ClockSampler, fp64_peak, measured_traffic
     import fixtures as fx
 
     lib = gk.load()
@@ -106,7 +106,8 @@ def run_ours_tile(args, rank, world, local):
         "config": {"workload": "vanilla32: synthetic 32-state vanilla KF, m = 8, warp-per-filter FP64 DMMA (BASELINE configs[4])",
                    "filters_per_gpu": nf, "epochs": steps, "n": n, "m": m, "failed_filters": bad,
                    "l2": "flushed between timed iterations (256 MiB memset)"},
-        "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+        "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                     "traffic": measured_traffic("vanilla32", nf == 100000 and steps == 200),
                      "kernel": "vanilla_tile_kernel<32>", "kernel_ms": main_ms, "flops_per_unit": FLOPS_ALG,
                      "machine_tflops": ups * FLOPS_MACHINE / 1e12, "machine_flops_per_unit": FLOPS_MACHINE,
                      "peak_source": peak_src,
