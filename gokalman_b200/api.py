@@ -856,3 +856,111 @@ def NewChiSquare(kf, runs, controls, withNEES, withNIS, sums=False):
     if res["first_error"][0] != 0:  # the reference panics (chisquare.go:40-42)
         raise GkbError(int(res["first_error"][0]), "a trial failed during Update")
     return res["NIS"], res["NEES"]
+
+
+# --------------------------------------------------------------------------------------------------
+# BatchKF (batch.go) and BatchGroundTruth (truth.go)
+# --------------------------------------------------------------------------------------------------
+class BatchKF:
+    """batch.go:12-79.  SetNextMeasurement stores the measurements on the host; Solve() sends them to the
+    device in one call (`gkb_batch_solve`: Lambda / N accumulation + inverse in one kernel).  SolveBatch is
+    the batched entry point: N independent batch filters, each with its own measurement streams."""
+
+    def __init__(self, numMeasurements, noise, device=0):
+        self._cap, self.noise, self._device = int(numMeasurements), noise, device
+        self.Measurements = []
+        self.step = 0
+
+    def SetNextMeasurement(self, realObs, computedObs, Phi, H):
+        if self.step >= self._cap:
+            raise IndexError("index out of range: BatchKF was created for %d measurements" % self._cap)  # Go slice panic
+        real, comp, H = _arr(realObs), _arr(computedObs), _mat(H)
+        self.Measurements.append(dict(RealObs=real, ComputedObs=comp, ObservationDev=real - comp, Phi=Phi, H=H))
+        self.step += 1
+
+    def Solve(self):
+        """batch.go:64-79 -> (xHat0, P0); raises where the reference returns an error."""
+        if not self.Measurements:
+            raise GkbError(-10, "no measurement was set")
+        H = np.stack([mm["H"] for mm in self.Measurements])
+        real = np.stack([mm["RealObs"] for mm in self.Measurements])
+        comp = np.stack([mm["ComputedObs"] for mm in self.Measurements])
+        x, P, status = self.SolveBatch(H, real, comp, n_filters=1)
+        if status[0] != 0:
+            raise GkbError(int(status[0]), "could not invert the information matrix")
+        return x[:, 0], P[:, :, 0]
+
+    def SolveBatch(self, H, real_obs, computed_obs, n_filters):
+        """H: [steps, m, n] (shared) or [steps, m, n, N]; observations [steps, m] or [steps, m, N].
+        Returns xHat0 [n, N], P0 [n, n, N], status [N]."""
+        lib = _lib.load()
+        H = _arr(H)
+        steps, m, n = H.shape[0], H.shape[1], H.shape[2]
+        nf = int(n_filters)
+        h_shared = 1 if H.ndim == 3 else 0
+        H = np.ascontiguousarray(H.reshape(steps, m * n) if h_shared else H.reshape(steps, m * n, nf))
+
+        def obs(a):
+            a = _arr(a)
+            if a.ndim == 2:
+                a = np.repeat(a[:, :, None], nf, axis=2)
+            return np.ascontiguousarray(a.reshape(steps, m, nf))
+        real_obs, computed_obs = obs(real_obs), obs(computed_obs)
+        R = _mat(self.noise.MeasurementMatrix())
+        if R.shape[0] != m:
+            raise GkbError(-1, "H(%dx...) R(%dx...)" % (m, R.shape[0]))
+        x, P, status = np.zeros((n, nf)), np.zeros((n * n, nf)), np.zeros(nf, dtype=np.int32)
+        _lib.check(lib.gkb_batch_solve(n, m, steps, nf, self._device, _ptr(R), _ptr(H), h_shared, _ptr(real_obs),
+                                       _ptr(computed_obs), _lib.HOST, _ptr(x), _ptr(P), status.ctypes.data))
+        return x, P.reshape(n, n, nf), status
+
+
+def NewBatchKF(numMeasurements, noise, device=0):
+    return BatchKF(numMeasurements, noise, device)
+
+
+class ErrorEstimate(Estimate):
+    """truth.go:68-70: a VanillaEstimate holding (estimate - truth)."""
+
+
+class BatchGroundTruth:
+    """truth.go:10-66 (host side, like exporter.go: it only subtracts stored vectors)."""
+
+    def __init__(self, states, measurements):
+        self.states, self.measurements = states, measurements
+
+    def Error(self, k, est):
+        return self.ErrorWithOffset(k, est, None)
+
+    def ErrorWithOffset(self, k, est, offset):
+        x = np.asarray(est.State(), dtype=np.float64)
+        y = np.asarray(est.Measurement(), dtype=np.float64)
+        es, em = np.zeros_like(x), np.zeros_like(y)
+        if k >= 0:
+            es = x.copy()
+            if offset is not None:
+                es = es + _arr(offset)
+            if self.states is not None:
+                t = self.states[k]
+                if t is not None:
+                    t = _arr(t)
+                    if t.shape[0] != es.shape[0]:
+                        raise ValueError("ground truth state size different from estimated state size (k=%d: %d != %d)"
+                                         % (k, es.shape[0], t.shape[0]))
+                    es = es - t
+            em = y.copy()
+            if self.states is not None:  # truth.go:52 tests t.states here too
+                t = self.measurements[k]
+                if t is not None:
+                    t = _arr(t)
+                    if t.shape[0] != em.shape[0]:
+                        raise ValueError("ground truth measurement size different from estimated measurement size (k=%d)" % k)
+                    em = em - t
+        n, m = es.shape[0], em.shape[0]
+        f = {"state": es.reshape(1, n, 1), "meas": em.reshape(1, m, 1),
+             "covar": np.asarray(est.Covariance(), dtype=np.float64).reshape(1, n * n, 1)}
+        return ErrorEstimate(n, m, f)
+
+
+def NewBatchGroundTruth(states, measurements):
+    return BatchGroundTruth(states, measurements)

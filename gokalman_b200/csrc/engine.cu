@@ -815,6 +815,48 @@ int gkb_smooth_all(int n, int steps, int64_t n_filters, int device, const double
   return 0;
 }
 
+// ---- BatchKF -------------------------------------------------------------------------------------------
+int gkb_batch_solve(int n, int m, int steps, int64_t n_filters, int device, const double* R, const double* H, int h_shared,
+                    const double* real_obs, const double* computed_obs, int mem, double* xhat0, double* P0,
+                    int32_t* status) {
+  if (!R || !H || !real_obs || !computed_obs || !xhat0 || !P0) return fail(GKB_ERR_ARG, "NULL argument");
+  if (!gkb_shape_supported(GKB_HYBRID, n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", n, m);
+  if (steps < 1 || n_filters < 1) return fail(GKB_ERR_ARG, "steps and n_filters must be >= 1");
+  int rc = check_device(device);
+  if (rc) return rc;
+  cudaStream_t s = cudaStreamLegacy;
+  double Rs[GKB_MAX_M * GKB_MAX_M];
+  sym_from_upper(Rs, R, m);
+  const size_t hb = sizeof(double) * (size_t)steps * m * n * (h_shared ? 1 : n_filters);
+  const size_t ob = sizeof(double) * (size_t)steps * m * n_filters;
+  const size_t xb = sizeof(double) * (size_t)n * n_filters, pb = xb * n, sb = sizeof(int32_t) * n_filters;
+  Timer tm(s);
+  if (mem == GKB_DEVICE) {
+    rc = launch_batch_solve(n, m, Rs, n_filters, steps, H, h_shared, real_obs, computed_obs, xhat0, P0, status, s);
+    tm.stop(1, false);
+    GKB_CUDA(cudaGetLastError());
+    return rc ? fail(rc, "no BatchKF kernel for n=%d m=%d", n, m) : 0;
+  }
+  DevBuf dh, dr, dc, dx, dP, dst;
+  auto cleanup = [&]() { dh.release(); dr.release(); dc.release(); dx.release(); dP.release(); dst.release(); };
+  if ((rc = dh.ensure(hb)) || (rc = dr.ensure(ob)) || (rc = dc.ensure(ob)) || (rc = dx.ensure(xb)) || (rc = dP.ensure(pb)) ||
+      (rc = dst.ensure(sb))) { cleanup(); return rc; }
+  cudaMemcpyAsync(dh.p, H, hb, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dr.p, real_obs, ob, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dc.p, computed_obs, ob, cudaMemcpyHostToDevice, s);
+  rc = launch_batch_solve(n, m, Rs, n_filters, steps, dh.as<double>(), h_shared, dr.as<double>(), dc.as<double>(),
+                          dx.as<double>(), dP.as<double>(), dst.as<int32_t>(), s);
+  tm.stop(1, true);
+  cudaMemcpyAsync(xhat0, dx.p, xb, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(P0, dP.p, pb, cudaMemcpyDeviceToHost, s);
+  if (status) cudaMemcpyAsync(status, dst.p, sb, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cleanup();
+  if (rc) return fail(rc, "no BatchKF kernel for n=%d m=%d", n, m);
+  if (e != cudaSuccess) return fail(GKB_ERR_CUDA, "BatchKF solve failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---- Monte Carlo + chi-square ------------------------------------------------------------------------
 
 namespace {

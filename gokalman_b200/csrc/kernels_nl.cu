@@ -240,6 +240,96 @@ int launch_smooth_all(int n, int64_t nf, int steps, const double* Phi, int phi_s
   }
 }
 
+// ---- BatchKF (batch.go:34-79) ------------------------------------------------------------------------------
+// One thread per batch filter: `steps` SetNextMeasurement accumulations Lambda += (H^T R) H, N += (H^T R) y
+// (R, not its inverse: the reference's formula, batch.go:50) over the filter's measurement streams, then
+// Solve(): P0 = inv(Lambda) by LU (upper triangle kept, AsSymDense), xHat0 = P0 N.  The full dense Lambda is
+// accumulated in the reference's operation order.  Streams H [steps][m*n][N], observations [steps][m][N].
+template <int N, int M>
+__global__ void __launch_bounds__(kThreads)
+batch_solve_kernel(const __grid_constant__ NlModel<N, M> md, int64_t nf, int steps, const double* __restrict__ H,
+                   int h_shared, const double* __restrict__ real_obs, const double* __restrict__ computed_obs,
+                   double* __restrict__ xhat0, double* __restrict__ P0, int32_t* __restrict__ status) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= nf) return;
+  double Lam[N * N], Nv[N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) Lam[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) Nv[i] = 0.0;
+  for (int k = 0; k < steps; ++k) {
+    double Hk[M * N], ro[M], co[M];
+    nl_load<M * N>(Hk, H, h_shared, k, nf, tid);
+    nl_load<M>(ro, real_obs, 0, k, nf, tid);
+    nl_load<M>(co, computed_obs, 0, k, nf, tid);
+    double HtR[N * M];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double s = Hk[i] * md.R[a];
+#pragma unroll
+        for (int b = 1; b < M; ++b) s = fma(Hk[b * N + i], md.R[b * M + a], s);
+        HtR[i * M + a] = s;
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = HtR[i * M] * Hk[j];
+#pragma unroll
+        for (int a = 1; a < M; ++a) s = fma(HtR[i * M + a], Hk[a * N + j], s);
+        Lam[i * N + j] += s;
+      }
+      double s = HtR[i * M] * (ro[0] - co[0]);
+#pragma unroll
+      for (int a = 1; a < M; ++a) s = fma(HtR[i * M + a], ro[a] - co[a], s);
+      Nv[i] += s;
+    }
+  }
+  int st = 0;
+  if (inverse_lu<N>(Lam) != 0) st = GKB_ERR_SINGULAR_S;  // batch.go:66-68 returns the error
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) Lam[i * N + j] = Lam[j * N + i];
+  double x[N];
+  mulvec<N, N>(x, Lam, Nv);
+  if (st != 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) Lam[i] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) xhat0[(int64_t)i * nf + tid] = x[i];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) P0[(int64_t)i * nf + tid] = Lam[i];
+  if (status != nullptr) status[tid] = st;
+}
+
+template <int N, int M>
+static int launch_batch_shape(const double* R_host, int64_t nf, int steps, const double* H, int h_shared,
+                              const double* real_obs, const double* computed_obs, double* xhat0, double* P0,
+                              int32_t* status, cudaStream_t s) {
+  NlModel<N, M> md;
+  memset(&md, 0, sizeof md);
+  for (int i = 0; i < M * M; ++i) md.R[i] = R_host[i];
+  const unsigned grid = (unsigned)((nf + kThreads - 1) / kThreads);
+  batch_solve_kernel<N, M><<<grid, kThreads, 0, s>>>(md, nf, steps, H, h_shared, real_obs, computed_obs, xhat0, P0, status);
+  return 0;
+}
+
+int launch_batch_solve(int n, int m, const double* R_host, int64_t nf, int steps, const double* H, int h_shared,
+                       const double* real_obs, const double* computed_obs, double* xhat0, double* P0, int32_t* status,
+                       cudaStream_t s) {
+#define GKB_CASE(NN, MM) \
+  if (n == NN && m == MM) return launch_batch_shape<NN, MM>(R_host, nf, steps, H, h_shared, real_obs, computed_obs, xhat0, P0, status, s);
+  GKB_FOR_EACH_SHAPE(GKB_CASE)
+#undef GKB_CASE
+  return GKB_ERR_UNSUPPORTED;
+}
+
 // ---- TMA-staged hybrid kernel --------------------------------------------------------------------------
 // Production configuration of the hybrid filter (per-filter Phi / Htilde / observation streams, no
 // SNC, outputs after the last epoch only).  A CTA owns 128 consecutive filters; the 52 (n=6, m=2)

@@ -168,6 +168,18 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
 int gkb_smooth_all(int n, int steps, int64_t n_filters, int device, const double* Phi, int phi_shared,
                    double* state, double* covar, int mem, int32_t* status);
 
+/* ---- BatchKF (batch.go:34-79): `steps` SetNextMeasurement(realObs, computedObs, Phi, H) calls followed
+ *      by Solve(), for N independent batch filters.  Per filter: Lambda = sum (H^T R) H,
+ *      N = sum (H^T R)(real - computed) -- the reference multiplies by R, not inv(R) (batch.go:50), kept;
+ *      P0 = inv(Lambda) (upper triangle mirrored, AsSymDense), xHat0 = P0 N.  Phi is stored but never
+ *      used by the reference's accumulation, so it is not an argument.  R is m x m (host, upper triangle
+ *      read); H [steps][m*n][N] (or [steps][m*n] shared), observations [steps][m][N]; outputs xhat0 [n][N],
+ *      P0 [n*n][N]; `mem` says where H / observations / outputs live.  status [N] (optional):
+ *      GKB_ERR_SINGULAR_S where Lambda cannot be inverted (Solve returns that error; outputs are zero). */
+int gkb_batch_solve(int n, int m, int steps, int64_t n_filters, int device, const double* R, const double* H,
+                    int h_shared, const double* real_obs, const double* computed_obs, int mem, double* xhat0,
+                    double* P0, int32_t* status);
+
 /* Raw filter state: x-like vector [n][N] and matrix [n*n][N] (vanilla/hybrid: x, P; information:
  * i, I; sqrt: x, S; SRIF: b, R).  Host pointers. */
 int gkb_get_state(const gkb_filter* f, double* vec, double* mat);

@@ -959,6 +959,35 @@ int gko_smooth_all(int n, int steps, const double* Phi, double* x, double* P) {
   return rc;
 }
 
+/* ---- BatchKF (batch.go:34-79) -------------------------------------------------------------------- */
+int gko_batch_solve(int n, int m, int count, const double* R, const double* H, const double* real_obs,
+                    const double* computed_obs, double* xhat0, double* P0) {
+  /* SetNextMeasurement (batch.go:41-61), `count` times: Lambda += (H^T R) H, N += (H^T R) y with
+   * y = real - computed.  The reference multiplies by R, not inv(R) (batch.go:50): kept.
+   * Solve (batch.go:64-79): P0 = AsSymDense(inv(Lambda)), xHat0 = P0 N. */
+  double* Lam = dalloc((size_t)n * n);
+  double* Nv = dalloc(n);
+  double* HtR = dalloc((size_t)n * m);
+  double* HtRH = dalloc((size_t)n * n);
+  double* y = dalloc(m);
+  double* t = dalloc(n);
+  int rc = 0;
+  for (int k = 0; k < count; ++k) {
+    const double* Hk = H + (size_t)k * m * n;
+    gko_mul_tn(HtR, Hk, R, n, m, m);
+    gko_mul(HtRH, HtR, Hk, n, m, n);
+    for (int i = 0; i < n * n; ++i) Lam[i] = Lam[i] + HtRH[i];
+    for (int a = 0; a < m; ++a) y[a] = real_obs[(size_t)k * m + a] - computed_obs[(size_t)k * m + a];
+    gko_mulvec(t, HtR, y, n, m);
+    for (int i = 0; i < n; ++i) Nv[i] = Nv[i] + t[i];
+  }
+  if (gko_inverse(P0, Lam, n, NULL) != 0) rc = GKO_ERR_SINGULAR_S;
+  else if (gko_as_sym(P0, n) != 0) rc = GKO_ERR_ASYMMETRIC;
+  else gko_mulvec(xhat0, P0, Nv, n, n);
+  free(Lam); free(Nv); free(HtR); free(HtRH); free(y); free(t);
+  return rc;
+}
+
 /* ---- Philox4x32-10 + Box-Muller: the oracle's own noise stream --------------------------------- */
 
 void gko_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {

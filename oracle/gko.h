@@ -116,6 +116,12 @@ void gko_measurement_srif_update(int n, int m, const double* R, const double* H,
  * GKO_ERR_SINGULAR_PHI / GKO_ERR_ASYMMETRIC. */
 int gko_smooth_all(int n, int steps, const double* Phi, double* x, double* P);
 
+/* batch.go:34-79 BatchKF: `count` SetNextMeasurement calls followed by Solve().  R[m x m],
+ * H[count][m*n], real_obs / computed_obs [count][m] -> xhat0[n], P0[n*n].  Returns 0,
+ * GKO_ERR_SINGULAR_S when Lambda cannot be inverted, GKO_ERR_ASYMMETRIC from AsSymDense. */
+int gko_batch_solve(int n, int m, int count, const double* R, const double* H, const double* real_obs,
+                    const double* computed_obs, double* xhat0, double* P0);
+
 /* ---- Monte Carlo + chi-square (montecarlo.go:92-119 + chisquare.go:16-95) -------------------- */
 typedef struct gko_mc_config {
   int n, m, c;

@@ -128,6 +128,7 @@ def lib():
     L.gko_srif_set_non_tri_r.argtypes = [C.c_void_p, ip]
     L.gko_measurement_srif_update.argtypes = [ip, ip, dp, dp, dp, dp, dp, dp, dp]
     L.gko_smooth_all.argtypes = [ip, ip, dp, dp, dp]
+    L.gko_batch_solve.argtypes = [ip, ip, ip, dp, dp, dp, dp, dp, dp]
     L.gko_mc_chisquare.argtypes = [C.POINTER(McConfig), dp, dp, dp, dp, dp, dp]
     L.gko_philox4x32_10.argtypes = [dp, dp, dp]
     L.gko_philox_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, ip, dp]
@@ -332,6 +333,18 @@ def smooth_all(Phi, x, P):
     Phi, x, P = _a(Phi), _a(x).copy(), _a(P).copy()
     steps, n = x.shape
     rc = lib().gko_smooth_all(n, steps, _p(Phi), _p(x), _p(P))
+    if rc != 0:
+        raise OracleError(rc)
+    return x, P
+
+
+def batch_solve(R, H, real_obs, computed_obs):
+    """batch.go:34-79: H [count, m, n], observations [count, m] -> (xHat0 [n], P0 [n, n])."""
+    H, R = _a(H), np.atleast_2d(_a(R))
+    count, m, n = H.shape
+    real_obs, computed_obs = _a(real_obs).reshape(count, m), _a(computed_obs).reshape(count, m)
+    x, P = np.zeros(n), np.zeros((n, n))
+    rc = lib().gko_batch_solve(n, m, count, _p(R), _p(H), _p(real_obs), _p(computed_obs), _p(x), _p(P))
     if rc != 0:
         raise OracleError(rc)
     return x, P
