@@ -8,5 +8,5 @@ from ._lib import GkbError, load, LIB_PATH  # noqa: F401
 from .api import (  # noqa: F401
     AWGN, BatchGroundTruth, BatchKF, BatchNoise, ErrorEstimate, Estimate, HybridKF, NewBatchGroundTruth, NewBatchKF, Information, MonteCarloRuns, NewAWGN, NewChiSquare, NewHybridKF,
     NewInformation, NewInformationFromState, NewMonteCarloRuns, NewNoiseless, NewPurePredictorVanilla, NewSRIF,
-    NewSquareRoot, NewVanilla, Noiseless, ReplayNoise, SRIF, SquareRoot, Vanilla,
+    NewSquareRoot, NewVanilla, Noiseless, ReplayNoise, SRIF, SquareRoot, VanLoan, Vanilla,
 )

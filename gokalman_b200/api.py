@@ -964,3 +964,31 @@ class BatchGroundTruth:
 
 def NewBatchGroundTruth(states, measurements):
     return BatchGroundTruth(states, measurements)
+
+
+# --------------------------------------------------------------------------------------------------
+# c2d.go -- stays host-side (BASELINE.json north_star: "c2d.go and exporter.go stay host-side")
+# --------------------------------------------------------------------------------------------------
+def VanLoan(A, Gamma, W, dt):
+    """c2d.go:13-75: (F, Q) of the discretised system from the continuous-time (A, Gamma, W) by Van Loan's
+    matrix exponential.  Returns (F, Q, err) like the Go function: `err` is None or the Nyquist warning
+    string (the reference still returns F and Q with it).  Quirk kept: the eigenvalue used for the test is
+    the LAST one of the spectrum (the loop never updates its running maximum, c2d.go:19-24)."""
+    from scipy.linalg import expm
+    A, Gamma, W = _mat(A), _mat(Gamma), _mat(W)
+    n = A.shape[0]
+    lam = np.linalg.eigvals(A)
+    err = None
+    if 2.0 * abs(lam[-1]) * dt >= np.pi:
+        err = "gokalman: Nyquist sampling criterion not fulfilled with Δt=%f" % dt
+    GWG = (Gamma @ W) @ Gamma.T * dt
+    Ap = A * dt
+    M = np.zeros((2 * n, 2 * n))
+    M[:n, :n] = -Ap
+    M[n:, n:] = Ap.T
+    M[:n, n:] = GWG
+    E = expm(M)
+    F = np.ascontiguousarray(E[n:, n:].T)
+    Q = F @ E[:n, n:]
+    Q = np.triu(Q) + np.triu(Q, 1).T  # AsSymDense: the upper triangle is kept
+    return F, Q, err
