@@ -332,9 +332,106 @@ def cpu_baseline(target_s=12.0, workload="mc_jerk3"):
                       "the Go/gonum reference cannot be built here (no Go toolchain)" % (trials, steps, workload, dt)}
 
 
+def np_od_streams(nf, steps, seed):
+    """numpy twin of bench_hybrid.make_streams (same construction, host side) for the CPU arm."""
+    rng = np.random.default_rng(seed)
+    n, m, dt = 6, 2, 10.0
+    Phi = np.zeros((steps, n, n, nf))
+    Phi += np.eye(n)[None, :, :, None]
+    for i in range(3):
+        Phi[:, i, 3 + i, :] += dt
+    A = 1e-6 * rng.standard_normal((steps, 3, 3, nf))
+    Gm = A + A.transpose(0, 2, 1, 3)
+    Phi[:, 3:, :3, :] += dt * Gm
+    Phi[:, :3, :3, :] += 0.5 * dt * dt * Gm
+    los = rng.standard_normal((steps, 3, nf))
+    los /= np.linalg.norm(los, axis=1, keepdims=True)
+    Ht = np.zeros((steps, m, n, nf))
+    Ht[:, 0, :3, :] = los
+    Ht[:, 1, 3:, :] = los
+    Ht[:, 1, :3, :] = 1e-3 * rng.standard_normal((steps, 3, nf))
+    real = rng.standard_normal((steps, m, nf))
+    comp = real + 1e-3 * rng.standard_normal((steps, m, nf))
+    return Phi.reshape(steps, n * n, nf), Ht.reshape(steps, m * n, nf), real, comp
+
+
+def oracle_filter_rate(workload, nf, steps, threads):
+    """CPU oracle over `nf` independent filters x `steps` (OpenMP over filters): hybrid6 / srif6 / vanilla32."""
+    from oracle import gko
+    gko.build()
+    if workload == "vanilla32":
+        f = fx.synth_lti(32, 8, seed=5)
+        y = np.random.default_rng(4321).standard_normal((steps, nf, 8))
+        t0 = time.perf_counter()
+        gko.run_vanilla_batch(f["x0"], f["P0"], f["F"], f["H"], f["Q"], f["R"], y, threads=threads, want_covar=False)
+        dt = time.perf_counter() - t0
+    else:
+        Phi, Ht, real, comp = np_od_streams(nf, steps, 1234)
+        srif = workload == "srif6"
+        P0 = np.diag([50, 50, 50, 1, 1, 1.0]) if srif else np.diag([10, 10, 10, 1, 1, 1.0])
+        flags = np.array([1 | (0 if srif else (2 if k >= 15 else 0)) for k in range(steps)], dtype=np.uint8)
+        t0 = time.perf_counter()
+        gko.run_nl_batch(gko.SRIF if srif else gko.HYBRID, np.zeros(6), P0, np.diag([1e-6, 1e-6]), flags, Phi, Ht, real, comp,
+                         threads=threads)
+        dt = time.perf_counter() - t0
+    return nf * steps / dt, dt
+
+
+FILTER_WORKLOADS = {
+    "hybrid6": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
+    "srif6": "srif6: 6-state SRIF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
+    "vanilla32": "vanilla32: synthetic 32-state vanilla KF, m = 8 (BASELINE configs[4])",
+}
+
+
+def filter_sample_size(workload, cores, target_s):
+    steps = 200
+    nf0 = cores * 8
+    rate, _ = oracle_filter_rate(workload, nf0, steps, cores)  # calibration
+    per_filter_bytes = steps * (64 if workload == "vanilla32" else 416)
+    nf = int(min(rate * target_s / steps, 2e9 / per_filter_bytes))
+    return max(cores, nf // cores * cores), steps
+
+
+def cpu_baseline_filters(workload, target_s=10.0):
+    cores = os.cpu_count() or 1
+    nf, steps = filter_sample_size(workload, cores, target_s)
+    rate, dt = oracle_filter_rate(workload, nf, steps, cores)
+    return {"value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port",
+            "sample": "%d filters x %d epochs of %s (%.1f s), C oracle restatement with OpenMP over filters; the Go/gonum "
+                      "reference cannot be built here (no Go toolchain)" % (nf, steps, workload, dt)}
+
+
+def run_reference_filters(args, rank, world):
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    wl = args.workload
+    nf, steps = filter_sample_size(wl, cores, 5.0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, dt = oracle_filter_rate(wl, nf, steps, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = nf * steps * args.steps / total
+    sample = "%d filters x %d epochs per step (bounded sample of the 10^5-filter workload), OpenMP x %d" % (nf, steps, cores)
+    return {
+        "impl": "reference", "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": FILTER_WORKLOADS[wl], "epochs": steps},
+        "cpu_baseline": {"value": value, "unit": "filter-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "filter-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle port (C, OpenMP); the reference is Go + un-vendored gonum and cannot be built in this image",
+    }
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return None
+    if args.workload in FILTER_WORKLOADS:
+        return run_reference_filters(args, rank, world)
     cores = os.cpu_count() or 1
     steps = args.filter_steps
     wl = args.workload if args.workload in MC_WORKLOADS else "mc_jerk3"
@@ -388,8 +485,9 @@ def main():
     else:
         line = run_ours_mc(args, rank, world, local)
     if line is not None:
-        if world == 1 and not args.no_cpu_baseline and args.workload in MC_WORKLOADS:
-            line["cpu_baseline"] = cpu_baseline(workload=args.workload)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = (cpu_baseline(workload=args.workload) if args.workload in MC_WORKLOADS
+                                    else cpu_baseline_filters(args.workload))
         elif "cpu_baseline" not in line:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

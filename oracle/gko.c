@@ -959,6 +959,71 @@ int gko_smooth_all(int n, int steps, const double* Phi, double* x, double* P) {
   return rc;
 }
 
+/* ---- batch runners: one independent filter object per filter, OpenMP over filters ----------------
+ * (the goroutine-per-filter structure a Go caller would use; bench.py's CPU baseline of the NLDKF and
+ * large-state workloads, and a batch-sized parity checker).  Streams use the engine's SoA layout
+ * [step][component][filter] for the NLDKF run and the filter-major layout for the LDKF run. */
+int gko_run_nl_batch(int kind, int n, int m, int64_t nf, int steps, const uint8_t* flags, const double* x0,
+                     const double* P0, const double* R, const double* Phi, const double* Htilde,
+                     const double* real_obs, const double* computed_obs, int threads, double* out_state,
+                     double* out_covar) {
+  int rc_all = 0;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+  for (int64_t f = 0; f < nf; ++f) {
+    gko_filter* kf = kind == GKO_SRIF ? gko_new_srif(n, m, x0, P0, R, 0) : gko_new_hybrid(n, m, 0, x0, P0, NULL, R);
+    gko_estimate* e = (gko_estimate*)malloc(sizeof(gko_estimate));
+    double Ph[GKO_MAXN * GKO_MAXN], Ht[GKO_MAXM * GKO_MAXN], ro[GKO_MAXM], co[GKO_MAXM];
+    int rc = 0;
+    for (int k = 0; k < steps && rc == 0; ++k) {
+      for (int i = 0; i < n * n; ++i) Ph[i] = Phi[((size_t)k * n * n + i) * nf + f];
+      for (int i = 0; i < m * n; ++i) Ht[i] = Htilde[((size_t)k * m * n + i) * nf + f];
+      for (int a = 0; a < m; ++a) {
+        ro[a] = real_obs[((size_t)k * m + a) * nf + f];
+        co[a] = computed_obs[((size_t)k * m + a) * nf + f];
+      }
+      const unsigned fl = flags ? flags[k] : 1u;
+      gko_prepare(kf, Ph, Ht);
+      gko_enable_ekf(kf, (fl & 2u) != 0);
+      rc = (fl & 1u) ? gko_nl_update(kf, ro, co, e) : gko_nl_predict(kf, e);
+    }
+    if (rc == 0) {
+      for (int i = 0; i < n; ++i) out_state[(size_t)i * nf + f] = e->state[i];
+      for (int i = 0; i < n * n; ++i) out_covar[(size_t)i * nf + f] = e->covar[i];
+    } else {
+#pragma omp critical
+      rc_all = rc;
+    }
+    free(e);
+    gko_free(kf);
+  }
+  return rc_all;
+}
+
+int gko_run_vanilla_batch(int n, int m, int64_t nf, int steps, const double* x0, const double* P0, const double* F,
+                          const double* H, const double* Q, const double* R, const double* y, int threads,
+                          double* out_state, double* out_covar) {
+  /* y [steps][nf][m], out_state [nf][n], out_covar [nf][n*n] (filter-major, like the large-state handles) */
+  int rc_all = 0;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+  for (int64_t f = 0; f < nf; ++f) {
+    gko_filter* kf = gko_new_vanilla(n, m, 0, x0, P0, F, NULL, H, Q, R, 0);
+    gko_estimate* e = (gko_estimate*)malloc(sizeof(gko_estimate));
+    int rc = 0;
+    for (int k = 0; k < steps && rc == 0; ++k) rc = gko_update(kf, y + ((size_t)k * nf + f) * m, NULL, e);
+    if (rc == 0) {
+      for (int i = 0; i < n; ++i) out_state[(size_t)f * n + i] = e->state[i];
+      if (out_covar)
+        for (int i = 0; i < n * n; ++i) out_covar[(size_t)f * n * n + i] = e->covar[i];
+    } else {
+#pragma omp critical
+      rc_all = rc;
+    }
+    free(e);
+    gko_free(kf);
+  }
+  return rc_all;
+}
+
 /* ---- BatchKF (batch.go:34-79) -------------------------------------------------------------------- */
 int gko_batch_solve(int n, int m, int count, const double* R, const double* H, const double* real_obs,
                     const double* computed_obs, double* xhat0, double* P0) {

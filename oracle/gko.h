@@ -116,6 +116,17 @@ void gko_measurement_srif_update(int n, int m, const double* R, const double* H,
  * GKO_ERR_SINGULAR_PHI / GKO_ERR_ASYMMETRIC. */
 int gko_smooth_all(int n, int steps, const double* Phi, double* x, double* P);
 
+/* Batch runners (bench.py CPU baseline; batch-sized parity checks): one filter object per filter, OpenMP
+ * over filters.  NLDKF: SoA streams [step][component][filter], flags bit 0 = Update (else Predict), bit 1 =
+ * EKF; outputs [component][filter] of the last estimate.  Vanilla: y [steps][nf][m], outputs filter-major. */
+int gko_run_nl_batch(int kind, int n, int m, int64_t nf, int steps, const uint8_t* flags, const double* x0,
+                     const double* P0, const double* R, const double* Phi, const double* Htilde,
+                     const double* real_obs, const double* computed_obs, int threads, double* out_state,
+                     double* out_covar);
+int gko_run_vanilla_batch(int n, int m, int64_t nf, int steps, const double* x0, const double* P0, const double* F,
+                          const double* H, const double* Q, const double* R, const double* y, int threads,
+                          double* out_state, double* out_covar);
+
 /* batch.go:34-79 BatchKF: `count` SetNextMeasurement calls followed by Solve().  R[m x m],
  * H[count][m*n], real_obs / computed_obs [count][m] -> xhat0[n], P0[n*n].  Returns 0,
  * GKO_ERR_SINGULAR_S when Lambda cannot be inverted, GKO_ERR_ASYMMETRIC from AsSymDense. */

@@ -128,6 +128,8 @@ def lib():
     L.gko_srif_set_non_tri_r.argtypes = [C.c_void_p, ip]
     L.gko_measurement_srif_update.argtypes = [ip, ip, dp, dp, dp, dp, dp, dp, dp]
     L.gko_smooth_all.argtypes = [ip, ip, dp, dp, dp]
+    L.gko_run_nl_batch.argtypes = [ip, ip, ip, C.c_int64, ip, C.c_void_p, dp, dp, dp, dp, dp, dp, dp, ip, dp, dp]
+    L.gko_run_vanilla_batch.argtypes = [ip, ip, C.c_int64, ip, dp, dp, dp, dp, dp, dp, dp, ip, dp, dp]
     L.gko_batch_solve.argtypes = [ip, ip, ip, dp, dp, dp, dp, dp, dp]
     L.gko_mc_chisquare.argtypes = [C.POINTER(McConfig), dp, dp, dp, dp, dp, dp]
     L.gko_philox4x32_10.argtypes = [dp, dp, dp]
@@ -336,6 +338,37 @@ def smooth_all(Phi, x, P):
     if rc != 0:
         raise OracleError(rc)
     return x, P
+
+
+def run_nl_batch(kind, x0, P0, R, flags, Phi, Htilde, real_obs, computed_obs, threads=1):
+    """Hybrid / SRIF over SoA streams Phi [steps, n*n, nf], Htilde [steps, m*n, nf], observations [steps, m, nf]:
+    last State() [n, nf] and Covariance() [n*n, nf] of every filter (OpenMP over filters)."""
+    Phi, Htilde, real_obs, computed_obs = _a(Phi), _a(Htilde), _a(real_obs), _a(computed_obs)
+    steps, nn, nf = Phi.shape
+    n = int(round(nn ** 0.5))
+    m = real_obs.shape[1]
+    flags = None if flags is None else np.ascontiguousarray(np.asarray(flags, dtype=np.uint8))
+    xs, Ps = np.zeros((n, nf)), np.zeros((n * n, nf))
+    rc = lib().gko_run_nl_batch(kind, n, m, nf, steps, None if flags is None else flags.ctypes.data, _p(_a(x0)), _p(_a(P0)),
+                                _p(np.atleast_2d(_a(R))), _p(Phi), _p(Htilde), _p(real_obs), _p(computed_obs), threads,
+                                _p(xs), _p(Ps))
+    if rc != 0:
+        raise OracleError(rc)
+    return xs, Ps
+
+
+def run_vanilla_batch(x0, P0, F, H, Q, R, y, threads=1, want_covar=True):
+    """Vanilla (Noiseless, no control) over y [steps, nf, m]: last State() [nf, n], Covariance() [nf, n*n]."""
+    F, H, y = _a(F), np.atleast_2d(_a(H)), _a(y)
+    n, m = F.shape[0], H.shape[0]
+    steps, nf = y.shape[0], y.shape[1]
+    xs = np.zeros((nf, n))
+    Ps = np.zeros((nf, n * n)) if want_covar else None
+    rc = lib().gko_run_vanilla_batch(n, m, nf, steps, _p(_a(x0)), _p(_a(P0)), _p(F), _p(H), _p(_a(Q)), _p(np.atleast_2d(_a(R))),
+                                     _p(y), threads, _p(xs), _p(Ps))
+    if rc != 0:
+        raise OracleError(rc)
+    return xs, Ps
 
 
 def batch_solve(R, H, real_obs, computed_obs):
