@@ -4,6 +4,10 @@
 
 namespace gkb {
 
+#ifndef GKB_MC_PART
+#error "compile with -DGKB_MC_PART=0..3 (see Makefile): 0 = dispatch + finish kernel, 1/2/3 = vanilla / information / sqrt kernels"
+#endif
+#if GKB_MC_PART == 0
 // out[col][k] = scale * sum_b partial[b][k][col], CTA rows added in CTA order.
 __global__ void mc_finish_kernel(const double* __restrict__ partial, int grid, int steps, int cols, double scale,
                                  double* __restrict__ out) {
@@ -14,6 +18,7 @@ __global__ void mc_finish_kernel(const double* __restrict__ partial, int grid, i
   const int k = idx / cols, col = idx % cols;
   out[(size_t)col * steps + k] = (col < kMcBaseCols) ? s * scale : s;  // only NIS / NEES become means
 }
+#endif  // GKB_MC_PART == 0
 
 template <int N, int M>
 static void fill_mc_model(const HostModel& hm, const McIo& io, McModel<N, M>& mm, const double* A0) {
@@ -52,8 +57,9 @@ static int pick_grid(Kern kern, size_t smem, int64_t trials, int device) {
   return (int)(g < 1 ? 1 : g);
 }
 
+#if GKB_MC_PART == 1
 template <int N, int M>
-static int launch_mc_shape(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+static int launch_mc_shape_vanilla(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
   const size_t smem = sizeof(double) * kWarps * kChunk * cols;
   int grid = 1;
@@ -61,15 +67,18 @@ static int launch_mc_shape(const HostModel& hm, const McIo& io, int device, int*
                     !io.noise_w && !io.noise_v && !io.status;
   McModel<N, M> mm;
   fill_mc_model<N, M>(hm, io, mm, io.P0);
-  switch (hm.kind) {
-    case GKB_VANILLA: {
+  {
       VanillaModel<N, M> md;
       for (int i = 0; i < N * N; ++i) { md.F[i] = hm.F[i]; md.Q[i] = hm.Q[i]; }
       for (int i = 0; i < M * M; ++i) md.R[i] = hm.R[i];
       for (int i = 0; i < N * GKB_MAX_C; ++i) md.G[i] = mm.G[i];
       for (int i = 0; i < M * N; ++i) md.H[i] = hm.H[i];
       md.c = hm.c; md.need_ctrl = hm.need_ctrl;
-      if (lean) {
+      if (lean && io.gu == nullptr) {
+        auto kern = mc_chisquare_kernel<N, M, VanillaTested<N, M>, true, true>;
+        *grid_out = grid = pick_grid(kern, smem, io.trials, device);
+        kern<<<grid, kThreads, smem, s>>>(mm, md, io);
+      } else if (lean) {
         auto kern = mc_chisquare_kernel<N, M, VanillaTested<N, M>, true>;
         *grid_out = grid = pick_grid(kern, smem, io.trials, device);
         kern<<<grid, kThreads, smem, s>>>(mm, md, io);
@@ -79,8 +88,29 @@ static int launch_mc_shape(const HostModel& hm, const McIo& io, int device, int*
         kern<<<grid, kThreads, smem, s>>>(mm, md, io);
       }
       return 0;
-    }
-    case GKB_INFORMATION: {
+      }
+}
+
+int launch_mc_vanilla(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+#define GKB_CASE(NN, MM) \
+  if (hm.n == NN && hm.m == MM) return launch_mc_shape_vanilla<NN, MM>(hm, io, device, grid_out, s);
+  GKB_FOR_EACH_SHAPE(GKB_CASE)
+#undef GKB_CASE
+  return GKB_ERR_UNSUPPORTED;
+}
+#endif
+
+#if GKB_MC_PART == 2
+template <int N, int M>
+static int launch_mc_shape_info(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+  const int cols = mc_cols(N, io.want_xstats);
+  const size_t smem = sizeof(double) * kWarps * kChunk * cols;
+  int grid = 1;
+  const bool lean = io.noise_mode == GKB_NOISE_PHILOX && !io.want_xstats && !io.truth_x && !io.truth_y &&
+                    !io.noise_w && !io.noise_v && !io.status;
+  McModel<N, M> mm;
+  fill_mc_model<N, M>(hm, io, mm, io.P0);
+  {
       InfoModel<N, M> md;
       for (int i = 0; i < N * N; ++i) { md.Finv[i] = hm.Finv[i]; md.Qinv[i] = hm.Qinv[i]; }
       for (int i = 0; i < M * M; ++i) md.Rinv[i] = hm.Rinv[i];
@@ -98,8 +128,29 @@ static int launch_mc_shape(const HostModel& hm, const McIo& io, int device, int*
         kern<<<grid, kThreads, smem, s>>>(mm, md, io);
       }
       return 0;
-    }
-    case GKB_SQRT: {
+      }
+}
+
+int launch_mc_info(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+#define GKB_CASE(NN, MM) \
+  if (hm.n == NN && hm.m == MM) return launch_mc_shape_info<NN, MM>(hm, io, device, grid_out, s);
+  GKB_FOR_EACH_SHAPE(GKB_CASE)
+#undef GKB_CASE
+  return GKB_ERR_UNSUPPORTED;
+}
+#endif
+
+#if GKB_MC_PART == 3
+template <int N, int M>
+static int launch_mc_shape_sqrt(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+  const int cols = mc_cols(N, io.want_xstats);
+  const size_t smem = sizeof(double) * kWarps * kChunk * cols;
+  int grid = 1;
+  const bool lean = io.noise_mode == GKB_NOISE_PHILOX && !io.want_xstats && !io.truth_x && !io.truth_y &&
+                    !io.noise_w && !io.noise_v && !io.status;
+  McModel<N, M> mm;
+  fill_mc_model<N, M>(hm, io, mm, io.P0);
+  {
       SqrtModel<N, M> md;
       for (int i = 0; i < N * N; ++i) { md.F[i] = hm.F[i]; md.sqrtQ[i] = hm.sqrtQ[i]; }
       for (int i = 0; i < M * M; ++i) md.sqrtR[i] = hm.sqrtR[i];
@@ -116,23 +167,36 @@ static int launch_mc_shape(const HostModel& hm, const McIo& io, int device, int*
         kern<<<grid, kThreads, smem, s>>>(mm, md, io);
       }
       return 0;
-    }
-    default: return GKB_ERR_UNSUPPORTED;
-  }
+      }
 }
 
+int launch_mc_sqrt(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+#define GKB_CASE(NN, MM) \
+  if (hm.n == NN && hm.m == MM) return launch_mc_shape_sqrt<NN, MM>(hm, io, device, grid_out, s);
+  GKB_FOR_EACH_SHAPE(GKB_CASE)
+#undef GKB_CASE
+  return GKB_ERR_UNSUPPORTED;
+}
+#endif
+
+#if GKB_MC_PART == 0
 int mc_max_grid(int device) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   return sms * kMcMaxCtasPerSm;
 }
 
+int launch_mc_vanilla(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_info(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_sqrt(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+
 int launch_mc(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
-#define GKB_CASE(NN, MM) \
-  if (hm.n == NN && hm.m == MM) return launch_mc_shape<NN, MM>(hm, io, device, grid_out, s);
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
-#undef GKB_CASE
-  return GKB_ERR_UNSUPPORTED;
+  switch (hm.kind) {
+    case GKB_VANILLA: return launch_mc_vanilla(hm, io, device, grid_out, s);
+    case GKB_INFORMATION: return launch_mc_info(hm, io, device, grid_out, s);
+    case GKB_SQRT: return launch_mc_sqrt(hm, io, device, grid_out, s);
+    default: return GKB_ERR_UNSUPPORTED;
+  }
 }
 
 int launch_mc_finish(const double* partial, int grid, int steps, int cols, double scale, double* out_cols,
@@ -141,5 +205,7 @@ int launch_mc_finish(const double* partial, int grid, int steps, int cols, doubl
   mc_finish_kernel<<<(total + 255) / 256, 256, 0, s>>>(partial, grid, steps, cols, scale, out_cols);
   return 0;
 }
+
+#endif  // GKB_MC_PART == 0
 
 }  // namespace gkb

@@ -242,7 +242,9 @@ struct SqrtTested {
 // LEAN = the production configuration (Philox noise, no dumps, no Mean/StdDev sums, no per-trial
 // status): the optional paths are compiled out so that the time loop stays small in the
 // instruction cache.  Results are identical to the general instantiation.
-template <int N, int M, class Tested, bool LEAN>
+// NOCTRL (LEAN only) = the run has no control term (io.gu == nullptr: no G, or all-zero controls as in
+// montecarlo.go:98-104): the per-step control loads and selects are compiled out.
+template <int N, int M, class Tested, bool LEAN, bool NOCTRL = false>
 __global__ void __launch_bounds__(kThreads, GKB_MC_MIN_CTAS(N, M, LEAN))
 mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_constant__ typename Tested::Model md_c,
                     const __grid_constant__ McIo io) {
@@ -282,6 +284,8 @@ mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_con
     Tested kf;
     kf.init(mm);
     int status = 0;
+    PhiloxTrial pt;
+    if (LEAN && N + M <= 4) pt.init(io.seed, gtrial);
     for (int k0 = 0; k0 < io.steps; k0 += kChunk) {
       const int kend = min(kChunk, io.steps - k0);
       for (int kk = 0; kk < kend; ++kk) {
@@ -290,7 +294,8 @@ mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_con
         double w[N], v[M];
         if (LEAN || io.noise_mode == GKB_NOISE_PHILOX) {
           double z[N + M];
-          philox_normals<N + M>(cf, io.seed, gtrial, (uint32_t)k, z);
+          if constexpr (LEAN && N + M <= 4) philox_normals_trial<N + M>(cf, pt, io.seed, (uint32_t)k, z);
+          else philox_normals<N + M>(cf, io.seed, gtrial, (uint32_t)k, z);
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             double s = 0.0;
@@ -316,7 +321,7 @@ mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_con
         double gu[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) gu[i] = 0.0;
-        const bool ctrl = mm.need_ctrl && io.gu != nullptr;  // uniform
+        const bool ctrl = !(LEAN && NOCTRL) && mm.need_ctrl && io.gu != nullptr;  // uniform
         if (ctrl) {
 #pragma unroll
           for (int i = 0; i < N; ++i) gu[i] = __ldg(io.gu + (int64_t)k * N + i);
