@@ -340,16 +340,35 @@ def smooth_all(Phi, x, P):
     return x, P
 
 
-def run_nl_batch(kind, x0, P0, R, flags, Phi, Htilde, real_obs, computed_obs, threads=1):
+_fma_lib = None
+
+
+def fma_lib():
+    """The FMA-contracted build of the same restatement (oracle/Makefile: libgko_fma.so) -- a rounding-sensitivity
+    probe, never the parity oracle."""
+    global _fma_lib
+    if _fma_lib is None:
+        path = os.path.join(_HERE, "_build", "libgko_fma.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+        L = C.CDLL(path)
+        dp, ip = C.c_void_p, C.c_int
+        L.gko_run_nl_batch.argtypes = [ip, ip, ip, C.c_int64, ip, C.c_void_p, dp, dp, dp, dp, dp, dp, dp, ip, dp, dp]
+        _fma_lib = L
+    return _fma_lib
+
+
+def run_nl_batch(kind, x0, P0, R, flags, Phi, Htilde, real_obs, computed_obs, threads=1, fma=False):
     """Hybrid / SRIF over SoA streams Phi [steps, n*n, nf], Htilde [steps, m*n, nf], observations [steps, m, nf]:
-    last State() [n, nf] and Covariance() [n*n, nf] of every filter (OpenMP over filters)."""
+    last State() [n, nf] and Covariance() [n*n, nf] of every filter (OpenMP over filters).  fma=True runs the
+    FMA-contracted build instead (rounding-sensitivity probe)."""
     Phi, Htilde, real_obs, computed_obs = _a(Phi), _a(Htilde), _a(real_obs), _a(computed_obs)
     steps, nn, nf = Phi.shape
     n = int(round(nn ** 0.5))
     m = real_obs.shape[1]
     flags = None if flags is None else np.ascontiguousarray(np.asarray(flags, dtype=np.uint8))
     xs, Ps = np.zeros((n, nf)), np.zeros((n * n, nf))
-    rc = lib().gko_run_nl_batch(kind, n, m, nf, steps, None if flags is None else flags.ctypes.data, _p(_a(x0)), _p(_a(P0)),
+    rc = (fma_lib() if fma else lib()).gko_run_nl_batch(kind, n, m, nf, steps, None if flags is None else flags.ctypes.data, _p(_a(x0)), _p(_a(P0)),
                                 _p(np.atleast_2d(_a(R))), _p(Phi), _p(Htilde), _p(real_obs), _p(computed_obs), threads,
                                 _p(xs), _p(Ps))
     if rc != 0:
