@@ -6,6 +6,7 @@ filter call needs libgokalman_b200.so and a B200.
 """
 from ._lib import GkbError, load, LIB_PATH  # noqa: F401
 from .api import (  # noqa: F401
+    AsSymDense, DenseIdentity, HouseholderTransf, Identity, IsNil, ScaledDenseIdentity, ScaledIdentity, Sign,
     AWGN, BatchGroundTruth, BatchKF, BatchNoise, ErrorEstimate, Estimate, HybridKF, NewBatchGroundTruth, NewBatchKF, Information, MonteCarloRuns, NewAWGN, NewChiSquare, NewHybridKF,
     NewInformation, NewInformationFromState, NewMonteCarloRuns, NewNoiseless, NewPurePredictorVanilla, NewSRIF,
     NewSquareRoot, NewVanilla, Noiseless, ReplayNoise, SRIF, SquareRoot, VanLoan, Vanilla,

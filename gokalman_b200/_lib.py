@@ -78,6 +78,7 @@ SYMBOLS = [
     ("gkb_get_state", _i, [_vp, _vp, _vp]),
     ("gkb_set_state", _i, [_vp, _vp, _vp]),
     ("gkb_smooth_all", _i, [_i, _i, _i64, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    ("gkb_householder_transf", _i, [_i, _i, _i64, _i, _vp, _i]),
     ("gkb_batch_solve", _i, [_i, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     ("gkb_mc_chisquare", _i, [C.POINTER(McConfig), C.POINTER(McOutputs)]),
     ("gkb_last_kernel_ms", C.c_float, []),

@@ -992,3 +992,65 @@ def VanLoan(A, Gamma, W, dt):
     Q = F @ E[:n, n:]
     Q = np.triu(Q) + np.triu(Q, 1).T  # AsSymDense: the upper triangle is kept
     return F, Q, err
+
+
+# --------------------------------------------------------------------------------------------------
+# helper.go: exported helpers
+# --------------------------------------------------------------------------------------------------
+def ScaledIdentity(n, s):
+    """helper.go:13-23"""
+    return s * np.eye(n)
+
+
+def DenseIdentity(n):
+    """helper.go:26-28"""
+    return np.eye(n)
+
+
+def ScaledDenseIdentity(n, s):
+    """helper.go:31-41"""
+    return s * np.eye(n)
+
+
+def Identity(n):
+    """helper.go:44-46"""
+    return np.eye(n)
+
+
+def IsNil(m):
+    """helper.go:49-63: nil or all zeros"""
+    return m is None or not np.any(np.asarray(m))
+
+
+def AsSymDense(m):
+    """helper.go:65-84: the upper triangle as a symmetric matrix; error when an off-diagonal pair differs by
+    more than 1e-6 absolute AND more than 1e-2 relative."""
+    m = _mat(m)
+    r, c = m.shape
+    if r != c:
+        raise GkbError(-3, "matrix is not square")
+    for i in range(r):
+        for j in range(i):
+            a, b = m[i, j], m[j, i]
+            if abs(a - b) > 1e-6 and abs(a - b) > 1e-2 * max(abs(a), abs(b)):
+                raise GkbError(-3, "matrix is not symmetric (%d, %d): %.30f != %.30f" % (i, j, a, b))
+    return np.triu(m) + np.triu(m, 1).T
+
+
+def Sign(v):
+    """helper.go:133-138"""
+    return 1.0 if abs(v) < 1e-12 or v > 0 else -1.0
+
+
+def HouseholderTransf(A, n, m, device=0):
+    """helper.go:142-172, in place like the Go function (and returns A).  A: [(n+m), (n+1)] or a batch
+    [(n+m), (n+1), count]; runs on the GPU (`gkb_householder_transf`)."""
+    lib = _lib.load()
+    A = np.asarray(A, dtype=np.float64)
+    if A.shape[0] != n + m or A.shape[1] != n + 1:
+        raise GkbError(-1, "A(%dx%d) is not (n+m)x(n+1) = %dx%d" % (A.shape[0], A.shape[1], n + m, n + 1))
+    count = 1 if A.ndim == 2 else A.shape[2]
+    buf = np.ascontiguousarray(A.reshape((n + m) * (n + 1), count))
+    _lib.check(lib.gkb_householder_transf(n, m, count, device, _ptr(buf), _lib.HOST))
+    A[...] = buf.reshape(A.shape)
+    return A

@@ -815,6 +815,33 @@ int gkb_smooth_all(int n, int steps, int64_t n_filters, int device, const double
   return 0;
 }
 
+// ---- HouseholderTransf ---------------------------------------------------------------------------------
+int gkb_householder_transf(int n, int m, int64_t count, int device, double* A, int mem) {
+  if (!A) return fail(GKB_ERR_ARG, "NULL argument");
+  if (!gkb_shape_supported(GKB_SRIF, n, m) && !(n == 2 && m == 3))
+    return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", n, m);
+  if (count < 1) return fail(GKB_ERR_ARG, "count must be >= 1");
+  int rc = check_device(device);
+  if (rc) return rc;
+  cudaStream_t s = cudaStreamLegacy;
+  const size_t bytes = sizeof(double) * (size_t)(n + m) * (n + 1) * count;
+  if (mem == GKB_DEVICE) {
+    rc = launch_householder(n, m, count, A, s);
+    GKB_CUDA(cudaGetLastError());
+    return rc ? fail(rc, "no Householder kernel for n=%d m=%d", n, m) : 0;
+  }
+  DevBuf d;
+  if ((rc = d.ensure(bytes))) return rc;
+  cudaMemcpyAsync(d.p, A, bytes, cudaMemcpyHostToDevice, s);
+  rc = launch_householder(n, m, count, d.as<double>(), s);
+  cudaMemcpyAsync(A, d.p, bytes, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  d.release();
+  if (rc) return fail(rc, "no Householder kernel for n=%d m=%d", n, m);
+  if (e != cudaSuccess) return fail(GKB_ERR_CUDA, "HouseholderTransf failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---- BatchKF -------------------------------------------------------------------------------------------
 int gkb_batch_solve(int n, int m, int steps, int64_t n_filters, int device, const double* R, const double* H, int h_shared,
                     const double* real_obs, const double* computed_obs, int mem, double* xhat0, double* P0,

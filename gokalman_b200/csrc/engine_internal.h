@@ -136,6 +136,8 @@ int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s);
 // SmoothAll (hybrid.go:209-238, srif.go:165-192) over stored [steps][C][nf] histories, in place.
 int launch_smooth_all(int n, int64_t nf, int steps, const double* Phi, int phi_shared, double* xs, double* Ps,
                       int32_t* status, cudaStream_t s);
+// HouseholderTransf (helper.go:142-172) on `count` matrices [(n+m)*(n+1)][count], in place.
+int launch_householder(int n, int m, int64_t count, double* A, cudaStream_t s);
 // BatchKF (batch.go:34-79): accumulation over the measurement streams + Solve(), one thread per batch filter.
 int launch_batch_solve(int n, int m, const double* R_host, int64_t nf, int steps, const double* H, int h_shared,
                        const double* real_obs, const double* computed_obs, double* xhat0, double* P0, int32_t* status,

@@ -240,6 +240,32 @@ int launch_smooth_all(int n, int64_t nf, int steps, const double* Phi, int phi_s
   }
 }
 
+// ---- HouseholderTransf (helper.go:142-172), the reference's exported helper, on a batch of matrices --------
+// A [(n+m)*(n+1)][count] (row-major components, matrix index fastest), transformed in place: one matrix per
+// thread, the same register routine the SRIF measurement update (srif.go:298-340) uses.
+template <int N, int M>
+__global__ void __launch_bounds__(kThreads) householder_kernel(int64_t count, double* __restrict__ A) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= count) return;
+  constexpr int LEN = (N + M) * (N + 1);
+  double a[LEN];
+#pragma unroll
+  for (int i = 0; i < LEN; ++i) a[i] = A[(int64_t)i * count + tid];
+  householder_transf<N, M>(a);
+#pragma unroll
+  for (int i = 0; i < LEN; ++i) A[(int64_t)i * count + tid] = a[i];
+}
+
+int launch_householder(int n, int m, int64_t count, double* A, cudaStream_t s) {
+  const unsigned grid = (unsigned)((count + kThreads - 1) / kThreads);
+#define GKB_CASE(NN, MM) \
+  if (n == NN && m == MM) { householder_kernel<NN, MM><<<grid, kThreads, 0, s>>>(count, A); return 0; }
+  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_CASE(2, 3)  // srif_test.go:31-56 (the reference's measurementSRIFUpdate known-answer test)
+#undef GKB_CASE
+  return GKB_ERR_UNSUPPORTED;
+}
+
 // ---- BatchKF (batch.go:34-79) ------------------------------------------------------------------------------
 // One thread per batch filter: `steps` SetNextMeasurement accumulations Lambda += (H^T R) H, N += (H^T R) y
 // (R, not its inverse: the reference's formula, batch.go:50) over the filter's measurement streams, then

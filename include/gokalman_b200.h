@@ -168,6 +168,12 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
 int gkb_smooth_all(int n, int steps, int64_t n_filters, int device, const double* Phi, int phi_shared,
                    double* state, double* covar, int mem, int32_t* status);
 
+/* ---- HouseholderTransf(A, n, m) (helper.go:142-172), the reference's exported helper and the core of the
+ *      SRIF measurement update (srif.go:298-340), on `count` independent (n+m) x (n+1) matrices in place.
+ *      A is [(n+m)*(n+1)][count] (row-major components, matrix index fastest; count = 1 is the plain
+ *      row-major matrix).  Sign(|v| < 1e-12) = +1 as in helper.go:133-138. */
+int gkb_householder_transf(int n, int m, int64_t count, int device, double* A, int mem);
+
 /* ---- BatchKF (batch.go:34-79): `steps` SetNextMeasurement(realObs, computedObs, Phi, H) calls followed
  *      by Solve(), for N independent batch filters.  Per filter: Lambda = sum (H^T R) H,
  *      N = sum (H^T R)(real - computed) -- the reference multiplies by R, not inv(R) (batch.go:50), kept;

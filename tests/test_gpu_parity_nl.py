@@ -293,3 +293,28 @@ def test_smooth_all_matches_oracle(oracle, kind, n, m, nf, shared):
         for k in range(steps):
             assert fx.scaled_err(xs[k, :, f], xr[k]) <= TOL, (f, k)
             assert fx.scaled_err(Ps[k, :, :, f], Pr[k]) <= TOL, (f, k)
+
+
+def test_householder_and_srif_update_kats_on_device(oracle):
+    """The reference's own known-answer tests run on the GPU routine: helper_test.go:108-117
+    (HouseholderTransf, 1e-15) and srif_test.go:31-56 (measurementSRIFUpdate: A = [[R b],[H y]], 1e-4 on the
+    four printed digits), plus a random batch against the oracle."""
+    gk = _gpu()
+    A = np.array([[1, -2, -1], [2, -1, 1], [1, 1, 2.0]])
+    want = np.array([[-2.449489742783178, 1.224744871391589, -1.2247448713915892],
+                     [0, -2.121320343559643, -2.121320343559643], [0, 0, 0]])
+    got = gk.HouseholderTransf(A.copy(), 2, 1)
+    assert np.max(np.abs(got - want)) <= 1e-15
+    R, H = 0.1 * np.eye(2) * 0 + np.array([[0.1, 0], [0, 0.1]]), np.array([[1, -2.0], [2, -1], [1, 1]])
+    b, y = np.array([0.2, 0.2]), np.array([-1.1, 1.2, 1.8])
+    A2 = np.zeros((5, 3))
+    A2[:2, :2], A2[:2, 2], A2[2:, :2], A2[2:, 2] = R, b, H, y
+    got2 = gk.HouseholderTransf(A2.copy(), 2, 3)
+    assert np.max(np.abs(got2[:2, :2] - np.array([[-2.4515, 1.2237], [0, -2.1243]]))) <= 1e-4
+    assert np.max(np.abs(got2[:2, 2] - np.array([-1.2727, -2.0607]))) <= 1e-4
+    assert np.max(np.abs(got2[2:, 2] - np.array([-0.1319, 0.0871, -0.2810]))) <= 1e-4
+    rng = np.random.default_rng(8)
+    batch = rng.standard_normal((8, 7, 50))
+    ref = np.stack([oracle.householder_transf(batch[:, :, j].copy(), 6, 2) for j in range(50)], axis=2)
+    got3 = gk.HouseholderTransf(batch.copy(), 6, 2)
+    assert fx.scaled_err(got3, ref) <= 1e-13

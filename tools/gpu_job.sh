@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -s 2>&1 | tail -15
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
