@@ -3,6 +3,7 @@ shared LTI model, per-filter measurement stream [epoch][filter][m]) advanced by 
 FP64 tensor-core kernel (kernels_tile.cu).  Covariances stay in shared memory for all epochs of a
 launch; HBM traffic is 64 B of measurement per update, so the FP64 pipe binds."""
 import ctypes as C
+import os
 import statistics
 import time
 
@@ -26,7 +27,7 @@ def run_ours_tile(args, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nf = args.trials if args.trials != 1000000 else 100000
     steps = args.filter_steps if args.filter_steps != 1000 else 200
-    n, m = 32, 8
+    n, m = int(os.environ.get('GKB_BENCH_TILE_N', '32')), 8
     dev = torch.device("cuda", local)
     f = fx.synth_lti(n, m, seed=5)
     g = torch.Generator(device=dev)

@@ -94,11 +94,43 @@ struct Frag {
     if (kt > ct) return a(ct, ks);
     return ((ks & 1) ? up_b1 : up_b0) ? b(ks, ct) : a(ct, ks);
   }
+  // symmetric n x n matrix stored as its upper 8 x 8 TILES only, packed (tile (ti, tj), ti <= tj, at
+  // 64 * pt(ti, tj); inside a tile the n x 8 layout): A / B / C patterns, the lower triangle through the transpose
+  template <int TM>
+  static __device__ __forceinline__ constexpr int pt(int ti, int tj) { return ti * TM - ti * (ti - 1) / 2 + (tj - ti); }
+  template <int TM>
+  __device__ __forceinline__ int p_c(int rt, int ct) const { return pt<TM>(rt, ct) * 64 + g * 8 + ((2 * t) ^ sA8); }
+  template <int TM>
+  __device__ __forceinline__ int p_a(int rt, int ks) const {  // element (rt*8 + g, ks*4 + t)
+    const int kt = ks >> 1, kl = (ks & 1) * 4;
+    const int direct = pt<TM>(rt < kt ? rt : kt, rt < kt ? kt : rt) * 64 + g * 8 + (kl ^ sA8) + t;
+    const int transp = pt<TM>(rt < kt ? rt : kt, rt < kt ? kt : rt) * 64 + (kl + t) * 8 + (g ^ sB8);
+    if (rt < kt) return direct;
+    if (rt > kt) return transp;
+    return ((ks & 1) ? up_a1 : up_a0) ? direct : transp;
+  }
+  template <int TM>
+  __device__ __forceinline__ int p_b(int ks, int ct) const {  // element (ks*4 + t, ct*8 + g)
+    const int kt = ks >> 1, kl = (ks & 1) * 4;
+    const int direct = pt<TM>(kt < ct ? kt : ct, kt < ct ? ct : kt) * 64 + (kl + t) * 8 + (g ^ sB8);
+    const int transp = pt<TM>(kt < ct ? kt : ct, kt < ct ? ct : kt) * 64 + g * 8 + (kl ^ sA8) + t;
+    if (kt < ct) return direct;
+    if (kt > ct) return transp;
+    return ((ks & 1) ? up_b1 : up_b0) ? direct : transp;
+  }
   // n x 8 matrices
   __device__ __forceinline__ int a8(int rt, int ks) const { return (rt * 8 + g) * 8 + ((ks * 4) ^ sA8) + t; }
   __device__ __forceinline__ int b8(int ks) const { return (ks * 4 + t) * 8 + (g ^ sB8); }
   __device__ __forceinline__ int c8(int rt) const { return (rt * 8 + g) * 8 + ((2 * t) ^ sA8); }
 };
+
+// element (r, c) of a tile-packed symmetric matrix (any r, c)
+template <int TM>
+__device__ __forceinline__ int idx_packed(int r, int c) {
+  const int lo = r < c ? r : c, hi = r < c ? c : r;
+  const int ti = lo >> 3, tj = hi >> 3;
+  return (ti * TM - ti * (ti - 1) / 2 + (tj - ti)) * 64 + idx_small(lo & 7, hi & 7);
+}
 
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void sts2(double* p, const double (&v)[2]) {
@@ -108,32 +140,29 @@ __device__ __forceinline__ void sts2(double* p, const double (&v)[2]) {
 }  // namespace
 
 template <int N>
-__global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_constant__ TileIo io) {
+__global__ void __launch_bounds__(N <= 16 ? 512 : 384, 1) vanilla_tile_kernel(const __grid_constant__ TileIo io) {
   constexpr int TM = N / 8, KS = N / 4, LDB = (N + 15) / 16 * 16;
   static_assert(N % 8 == 0 && N <= 32, "tile kernel shapes");
   extern __shared__ __align__(16) double smem[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Frag<LDB> fr(lane);
   const int g = fr.g, t = fr.t;
-  // CTA-shared model
+  // CTA-shared model (Q is only ever a C-fragment initialiser: read straight from global / L2 once per step)
+  constexpr int kPacked = TM * (TM + 1) / 2 * 64;  // upper tiles of a symmetric n x n matrix
   double* sF = smem;                // [N][LDB]
-  double* sQ = sF + N * LDB;        // [N][LDB]
-  double* sH = sQ + N * LDB;        // [8][LDB]  rows >= m are zero
+  double* sH = sF + N * LDB;        // [8][LDB]  rows >= m are zero
   double* sR = sH + kMP * LDB;      // [8][8]    padded with a unit diagonal
   double* wbase = sR + kMP * 8;
-  constexpr int kPerWarp = 2 * N * LDB + 2 * N * 8 + 2 * N + 2 * kMP;
-  double* bufA = wbase + (size_t)warp * kPerWarp;  // P, then P-, then P+  (symmetric: upper triangle valid)
-  double* bufB = bufA + N * LDB;                   // T (full), then T2 (upper)
+  constexpr int kPerWarp = kPacked + N * LDB + 2 * N * 8 + 2 * N + 2 * kMP;
+  double* bufA = wbase + (size_t)warp * kPerWarp;  // P, then P-, then P+  (symmetric: packed upper tiles)
+  double* bufB = bufA + kPacked;                   // T (full), then T2 (upper)
   double* sPH = bufB + N * LDB;                    // P- H^T, later V
   double* sK = sPH + N * 8;                        // gain
   double* xs = sK + N * 8;                         // posterior state
   double* xms = xs + N;                            // predicted state
   double* sinn = xms + N;                          // innovation (8), y-hat (8)
 
-  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
-    sF[idx_big<LDB>(idx / N, idx % N)] = io.F[idx];
-    sQ[idx_big<LDB>(idx / N, idx % N)] = io.Q[idx];
-  }
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) sF[idx_big<LDB>(idx / N, idx % N)] = io.F[idx];
   for (int idx = threadIdx.x; idx < kMP * N; idx += blockDim.x) sH[idx_big<LDB>(idx / N, idx % N)] = io.H[idx];
   for (int idx = threadIdx.x; idx < kMP * kMP; idx += blockDim.x) sR[idx_small(idx / kMP, idx % kMP)] = io.R[idx];
   __syncthreads();
@@ -145,7 +174,8 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
     for (int idx = lane; idx < N; idx += 32) xs[idx] = io.x[f * N + idx];
     {
       const double* Pg = io.P + f * (int64_t)(N * N);
-      for (int idx = lane; idx < N * N; idx += 32) bufA[idx_big<LDB>(idx / N, idx % N)] = Pg[idx];
+      for (int idx = lane; idx < N * N; idx += 32)
+        if (idx / N <= idx % N) bufA[idx_packed<TM>(idx / N, idx % N)] = Pg[idx];
     }
     __syncwarp();
     int status = 0;
@@ -171,7 +201,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
 #pragma unroll
           for (int ti = 0; ti < TM; ++ti) a[ti] = sF[fr.a(ti, ks)];
 #pragma unroll
-          for (int tj = 0; tj < TM; ++tj) b[tj] = bufA[fr.sym_b(ks, tj)];
+          for (int tj = 0; tj < TM; ++tj) b[tj] = bufA[fr.template p_b<TM>(ks, tj)];
 #pragma unroll
           for (int ti = 0; ti < TM; ++ti) {
             xpart[ti] = fma(a[ti], xq[ks], xpart[ti]);
@@ -195,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
         for (int tj = ti; tj < TM; ++tj) {
-          const double2 q = lds2(sQ + fr.c(ti, tj));
+          const double2 q = __ldg(reinterpret_cast<const double2*>(io.Q + (ti * 8 + g) * N + tj * 8 + 2 * t));
           c[ti * TM + tj][0] = q.x;
           c[ti * TM + tj][1] = q.y;
         }
@@ -214,13 +244,13 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
-        for (int tj = ti; tj < TM; ++tj) sts2(bufA + fr.c(ti, tj), c[ti * TM + tj]);
+        for (int tj = ti; tj < TM; ++tj) sts2(bufA + fr.template p_c<TM>(ti, tj), c[ti * TM + tj]);
       __syncwarp();
       if (io.o_pred != nullptr && (io.every_step || k == io.steps - 1)) {
         double* dst = io.o_pred + ((io.every_step ? (int64_t)k * io.nf : 0) + f) * (N * N);
         for (int idx = lane; idx < N * N; idx += 32) {
           const int r = idx / N, cc = idx % N;
-          dst[idx] = bufA[r <= cc ? idx_big<LDB>(r, cc) : idx_big<LDB>(cc, r)];
+          dst[idx] = bufA[idx_packed<TM>(r, cc)];
         }
       }
       // ---- PHt = P- H^T (160-161), y-hat = H x (155-157), H x- for the innovation (182-184)
@@ -239,7 +269,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
           hx = fma(b, xq[ks], hx);
           hm = fma(b, xmq[ks], hm);
 #pragma unroll
-          for (int ti = 0; ti < TM; ++ti) dmma(ph[ti], bufA[fr.sym_a(ti, ks)], b);
+          for (int ti = 0; ti < TM; ++ti) dmma(ph[ti], bufA[fr.template p_a<TM>(ti, ks)], b);
         }
         yhat = quad_sum(hx);
         hxm = quad_sum(hm);
@@ -318,7 +348,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
         for (int tj = ti; tj < TM; ++tj) {
-          const double2 v = lds2(bufA + fr.c(ti, tj));
+          const double2 v = lds2(bufA + fr.template p_c<TM>(ti, tj));
           c[ti * TM + tj][0] = v.x;
           c[ti * TM + tj][1] = v.y;
         }
@@ -375,7 +405,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll
-        for (int tj = ti; tj < TM; ++tj) sts2(bufA + fr.c(ti, tj), c[ti * TM + tj]);
+        for (int tj = ti; tj < TM; ++tj) sts2(bufA + fr.template p_c<TM>(ti, tj), c[ti * TM + tj]);
       __syncwarp();
       // ---- Estimate fields of this step
       if (io.every_step || k == io.steps - 1) {
@@ -390,7 +420,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
           double* dst = io.o_covar + row * (int64_t)(N * N);
           for (int idx = lane; idx < N * N; idx += 32) {
             const int r = idx / N, cc = idx % N;
-            dst[idx] = bufA[r <= cc ? idx_big<LDB>(r, cc) : idx_big<LDB>(cc, r)];
+            dst[idx] = bufA[idx_packed<TM>(r, cc)];
           }
         }
       }
@@ -398,7 +428,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
     // ---- state out (a failed filter keeps the state it had when the call started)
     if (status == 0) {
       bool finite = true;
-      for (int idx = lane; idx < N; idx += 32) finite = finite && isfinite(xs[idx]) && isfinite(bufA[idx_big<LDB>(idx, idx)]);
+      for (int idx = lane; idx < N; idx += 32) finite = finite && isfinite(xs[idx]) && isfinite(bufA[idx_packed<TM>(idx, idx)]);
       finite = __all_sync(0xffffffffu, finite);
       if (!finite) status = GKB_ERR_NONFINITE;
     }
@@ -407,7 +437,7 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
       double* Pg = io.P + f * (int64_t)(N * N);
       for (int idx = lane; idx < N * N; idx += 32) {
         const int r = idx / N, cc = idx % N;
-        Pg[idx] = bufA[r <= cc ? idx_big<LDB>(r, cc) : idx_big<LDB>(cc, r)];
+        Pg[idx] = bufA[idx_packed<TM>(r, cc)];
       }
     } else if (lane == 0 && io.status != nullptr && io.status[f] == 0) {
       io.status[f] = status;
@@ -419,8 +449,9 @@ __global__ void __launch_bounds__(256, 1) vanilla_tile_kernel(const __grid_const
 template <int N>
 static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
   constexpr int LDB = (N + 15) / 16 * 16;
-  constexpr size_t kShared = sizeof(double) * (2 * N * LDB + kMP * LDB + kMP * 8);
-  constexpr size_t kPerWarp = sizeof(double) * (2 * N * LDB + 2 * N * 8 + 2 * N + 2 * kMP);
+  constexpr int TM = N / 8;
+  constexpr size_t kShared = sizeof(double) * (N * LDB + kMP * LDB + kMP * 8);
+  constexpr size_t kPerWarp = sizeof(double) * (TM * (TM + 1) / 2 * 64 + N * LDB + 2 * N * 8 + 2 * N + 2 * kMP);
   static thread_local int cached_device = -1, sms = 148, max_smem = 227 * 1024;
   if (cached_device != device) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -429,7 +460,8 @@ static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
     cached_device = device;
   }
   int warps = (int)(((size_t)max_smem - kShared) / kPerWarp);
-  if (warps > 8) warps = 8;
+  constexpr int kMaxWarps = N <= 16 ? 16 : 12;  // register budget: 64 K / (32 x registers per thread)
+  if (warps > kMaxWarps) warps = kMaxWarps;
   if (warps < 1) return GKB_ERR_UNSUPPORTED;
   int64_t ctas = (io.nf + warps - 1) / warps;
   if (ctas > sms) ctas = sms;  // persistent: one CTA per SM, warps stride over the filters
