@@ -161,7 +161,7 @@ def run_ours_hybrid(args, rank, world, local):
                      "frac": (gbs / hbm) if bound_hbm else (tf / peak_tf),
                      "traffic": measured_traffic(args.workload, nf == 100000 and steps == 200),
                      "algorithmic_bytes": float(nf) * steps * BYTES_IN,
-                     "kernel": "srif_run_kernel<6,2>" if srif else "hybrid_run_wtma_kernel<6,2> (warp-private TMA tensor-map pipelines)", "kernel_ms": main_ms,
+                     "kernel": "nl_run_wtma_sched_kernel<6,2,SRIF>" if srif else "nl_run_wtma_sched_kernel<6,2> (warp-private TMA tensor-map pipelines, persistent chunk scheduler)", "kernel_ms": main_ms,
                      "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm, "bytes_per_unit": BYTES_IN, "source": hbm_src},
                      "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf, "frac": tf / peak_tf, "flops_per_unit": flops,
                               "source": peak_src}},

@@ -159,6 +159,7 @@ struct gkb_filter {
   // large-state handles (kernels_tile.cu): filter-major arrays, model kept on the device
   bool tile = false;
   DevBuf tile_model;  // F [n*n], Q [n*n], H [8][n], R [8][8]
+  DevBuf sched;       // NLDKF production kernel: task counter + one flag per group of 32 filters
 };
 
 extern "C" {
@@ -226,7 +227,7 @@ static int finish_create(gkb_filter* f, const double* x0, int x0_per_filter, con
 static void destroy_filter(gkb_filter* f) {
   if (!f) return;
   cudaSetDevice(f->device);
-  DevBuf* bufs[] = {&f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
+  DevBuf* bufs[] = {&f->sched, &f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
                     &f->in_a, &f->in_b, &f->in_c, &f->in_d, &f->in_e, &f->in_f, &f->o_state, &f->o_meas, &f->o_innov,
                     &f->o_covar, &f->o_pred, &f->o_gain, &f->o_obsdev};
   for (DevBuf* b : bufs) b->release();
@@ -758,6 +759,8 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
   io.real_obs = static_cast<const double*>(dr);
   io.computed_obs = static_cast<const double*>(dc);
   io.Gamma = static_cast<const double*>(dg);
+  if ((rc = f->sched.ensure(sizeof(int) * (size_t)((f->nf + 31) / 32 + 1)))) return rc;
+  io.sched = f->sched.as<int>();
   const int innov_len = (hm.kind == GKB_SRIF) ? n : m;
   OutPlan pl;
   if ((rc = plan_outputs(f, out, steps, innov_len, pl))) return rc;

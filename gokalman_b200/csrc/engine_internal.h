@@ -64,6 +64,8 @@ struct NlIo {
   const double* real_obs;
   const double* computed_obs;
   const double* Gamma;  // [steps][n*q] shared or nullptr
+  int* sched;           // TMA production path: [1 + ceil(nf / 32)] ints of scheduler scratch (task counter + per-group flags)
+  int chunks, chunk_len;  // filled by the launcher: epochs are run in `chunks` chunks of `chunk_len`
   int every_step;
   double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain, *o_obsdev;
   int32_t* status;
@@ -133,6 +135,8 @@ int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStrea
 int launch_gu(const double* G_host, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s);
 int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s);
 int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s);
+// kernels_nl_tma.cu: the TMA production path of the NLDKF kinds.  0 = launched, 1 = not applicable to this call.
+int launch_nl_tma(const HostModel& hm, const NlIo& io, cudaStream_t s);
 // SmoothAll (hybrid.go:209-238, srif.go:165-192) over stored [steps][C][nf] histories, in place.
 int launch_smooth_all(int n, int64_t nf, int steps, const double* Phi, int phi_shared, double* xs, double* Ps,
                       int32_t* status, cudaStream_t s);

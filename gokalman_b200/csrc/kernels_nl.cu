@@ -356,353 +356,6 @@ int launch_batch_solve(int n, int m, const double* R_host, int64_t nf, int steps
   return GKB_ERR_UNSUPPORTED;
 }
 
-// ---- TMA-staged hybrid kernel --------------------------------------------------------------------------
-// Production configuration of the hybrid filter (per-filter Phi / Htilde / observation streams, no
-// SNC, outputs after the last epoch only).  A CTA owns 128 consecutive filters; the 52 (n=6, m=2)
-// input rows of an epoch are 1 KB contiguous segments of the SoA streams, copied into shared memory
-// by the TMA (cp.async.bulk, one 1 KB bulk copy per row, completion counted on an mbarrier) two
-// epochs ahead of the arithmetic, so HBM latency overlaps the FP64 work instead of stalling the two
-// resident warps per scheduler.  Each thread then reads its own column with conflict-free LDS.64.
-namespace tma {
-
-GKB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-GKB_DEV void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-GKB_DEV void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-GKB_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-GKB_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-GKB_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// 2-D tiled TMA load (cp.async.bulk.tensor): box {32 filters, rows} of a [rows_total][nf] stream.
-GKB_DEV void tensor_g2s_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-
-}  // namespace tma
-
-template <int N, int M>
-__global__ void __launch_bounds__(kThreads)
-hybrid_run_tma_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant__ NlIo io) {
-  constexpr int SN = N * (N + 1) / 2;
-  constexpr int ROWS_PHI = N * N, ROWS_H = M * N, ROWS = ROWS_PHI + ROWS_H + 2 * M;
-  constexpr int STAGES = 2;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* stage = reinterpret_cast<double*>(smem_raw);                       // [STAGES][ROWS][kThreads]
-  uint64_t* full = reinterpret_cast<uint64_t*>(stage + (size_t)STAGES * ROWS * kThreads);  // [STAGES]
-  const int64_t cta_base = (int64_t)blockIdx.x * kThreads;
-  const int64_t tid = cta_base + threadIdx.x;
-  const bool active = tid < io.nf;
-  const uint32_t cnt = (uint32_t)min((int64_t)kThreads, io.nf - cta_base);  // filters of this CTA (even)
-  const uint32_t row_bytes = cnt * 8u;
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) tma::mbar_init(&full[s], 1);
-    tma::fence_barrier_init();
-  }
-  __syncthreads();
-
-  // warp 0 issues the bulk copies of one epoch: lane r copies rows r, r + 32, ...
-  auto issue = [&](int k, int s) {
-    const bool has_meas = io.flags ? ((io.flags[k] & GKB_F_MEAS) != 0) : true;
-    const int rows = has_meas ? ROWS : ROWS_PHI;
-    double* dst = stage + (size_t)s * ROWS * kThreads;
-    if (threadIdx.x == 0) tma::mbar_expect_tx(&full[s], (uint32_t)rows * row_bytes);
-    __syncwarp();
-    for (int r = threadIdx.x; r < rows; r += 32) {
-      const double* src;
-      if (r < ROWS_PHI) src = io.Phi + ((int64_t)k * ROWS_PHI + r) * io.nf;
-      else if (r < ROWS_PHI + ROWS_H) src = io.Htilde + ((int64_t)k * ROWS_H + (r - ROWS_PHI)) * io.nf;
-      else if (r < ROWS_PHI + ROWS_H + M) src = io.real_obs + ((int64_t)k * M + (r - ROWS_PHI - ROWS_H)) * io.nf;
-      else src = io.computed_obs + ((int64_t)k * M + (r - ROWS_PHI - ROWS_H - M)) * io.nf;
-      tma::bulk_g2s(dst + (size_t)r * kThreads, src + cta_base, row_bytes, &full[s]);
-    }
-  };
-
-  double x[N], P[SN];
-  if (active) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = io.vec[(int64_t)i * io.nf + tid];
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = i; j < N; ++j) P[sym_idx<N>(i, j)] = io.mat[(int64_t)(i * N + j) * io.nf + tid];
-  }
-  if (threadIdx.x < 32) {
-    issue(0, 0);
-    if (io.steps > 1) issue(1, 1);
-  }
-  int status = 0;
-  for (int k = 0; k < io.steps; ++k) {
-    const int s = k & 1;
-    const unsigned fl = io.flags ? io.flags[k] : (unsigned)GKB_F_MEAS;
-    const bool has_meas = (fl & GKB_F_MEAS) != 0, ekf = (fl & GKB_F_EKF) != 0;
-    tma::mbar_wait(&full[s], (uint32_t)((k >> 1) & 1));
-    const double* col = stage + (size_t)s * ROWS * kThreads + threadIdx.x;
-    double Phi[N * N], Ht[M * N], ro[M], co[M];
-#pragma unroll
-    for (int i = 0; i < N * N; ++i) Phi[i] = col[(size_t)i * kThreads];
-    if (has_meas) {
-#pragma unroll
-      for (int i = 0; i < M * N; ++i) Ht[i] = col[(size_t)(ROWS_PHI + i) * kThreads];
-#pragma unroll
-      for (int a = 0; a < M; ++a) {
-        ro[a] = col[(size_t)(ROWS_PHI + ROWS_H + a) * kThreads];
-        co[a] = col[(size_t)(ROWS_PHI + ROWS_H + M + a) * kThreads];
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < M * N; ++i) Ht[i] = 0.0;
-#pragma unroll
-      for (int a = 0; a < M; ++a) { ro[a] = 0.0; co[a] = 0.0; }
-    }
-    __syncthreads();  // every thread holds its epoch-k inputs in registers: the stage can be refilled
-    if (threadIdx.x < 32 && k + STAGES < io.steps) issue(k + STAGES, s);
-    if (active) {
-      NlOut<N, M> o;
-      int err = hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, nullptr, has_meas, ekf, false, o);
-      if (err != 0 && status == 0) status = err;
-    }
-  }
-  if (active) {
-    if (io.o_state != nullptr) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) io.o_state[(int64_t)i * io.nf + tid] = x[i];
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) io.vec[(int64_t)i * io.nf + tid] = x[i];
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const double v = P[sym_idx<N>(i, j)];
-        io.mat[(int64_t)(i * N + j) * io.nf + tid] = v;
-        if (io.o_covar != nullptr) io.o_covar[(int64_t)(i * N + j) * io.nf + tid] = v;
-      }
-    if (io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
-  }
-}
-
-// ---- warp-private TMA pipelines (tensor maps) ------------------------------------------------------------
-// Same production configuration as above, but no CTA-wide synchronisation at all: every warp owns 32
-// consecutive filters and a private ring of kWStages shared-memory stages with one mbarrier each.  An epoch
-// of a warp is four tiled TMA loads (cp.async.bulk.tensor.2d): the {32 filters x N*N rows} box of the Phi
-// stream, {32 x M*N} of Htilde and {32 x M} of each observation stream.  As soon as a lane has moved its
-// column of a stage into registers the stage is re-armed for epoch k + kWStages, so every warp always has
-// one to two epochs (13 KB each at n = 6, m = 2) in flight while it does the FP64 work of the current one.
-// Out-of-range filters of a ragged last warp are zero-filled by the TMA and never written back.
-struct NlTensorMaps {
-  alignas(64) CUtensorMap phi;
-  alignas(64) CUtensorMap h;
-  alignas(64) CUtensorMap real_obs;
-  alignas(64) CUtensorMap computed_obs;
-};
-constexpr int kWStages = 2;
-
-template <int N, int M, bool SRIF>
-__global__ void __launch_bounds__(kThreads)
-nl_run_wtma_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant__ NlIo io,
-                   const __grid_constant__ NlTensorMaps maps) {
-  constexpr int SN = SRIF ? N * N : N * (N + 1) / 2;  // SRIF keeps the full sqrt-information matrix R
-  constexpr int ROWS_PHI = N * N, ROWS_H = M * N, ROWS = ROWS_PHI + ROWS_H + 2 * M;
-  constexpr int kWarpsPerCta = kThreads / 32;
-  constexpr uint32_t kBytesPhi = ROWS_PHI * 32 * 8, kBytesAll = ROWS * 32 * 8;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kWStages * ROWS * 32;  // [stage][row][lane]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kWarpsPerCta * kWStages * ROWS * 32) +
-                   warp * kWStages;
-  const int64_t warp_base = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32;
-  if (warp_base >= io.nf) return;  // whole warp out of range (no CTA-wide barrier anywhere below)
-  const int64_t tid = warp_base + lane;
-  const bool active = tid < io.nf;
-
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kWStages; ++s) tma::mbar_init(&full[s], 1);
-    tma::fence_barrier_init();
-  }
-  __syncwarp();
-
-  auto issue = [&](int k, int s) {  // lane 0 only
-    const bool has_meas = io.flags ? ((io.flags[k] & GKB_F_MEAS) != 0) : true;
-    double* dst = ring + (size_t)s * ROWS * 32;
-    tma::mbar_expect_tx(&full[s], has_meas ? kBytesAll : kBytesPhi);
-    tma::tensor_g2s_2d(dst, &maps.phi, (int)warp_base, k * ROWS_PHI, &full[s]);
-    if (has_meas) {
-      tma::tensor_g2s_2d(dst + ROWS_PHI * 32, &maps.h, (int)warp_base, k * ROWS_H, &full[s]);
-      tma::tensor_g2s_2d(dst + (ROWS_PHI + ROWS_H) * 32, &maps.real_obs, (int)warp_base, k * M, &full[s]);
-      tma::tensor_g2s_2d(dst + (ROWS_PHI + ROWS_H + M) * 32, &maps.computed_obs, (int)warp_base, k * M, &full[s]);
-    }
-  };
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kWStages; ++s)
-      if (s < io.steps) issue(s, s);
-  }
-
-  double x[N], P[SN];  // hybrid: x, P (packed upper);  SRIF: b, R
-  if (active) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = io.vec[(int64_t)i * io.nf + tid];
-    if constexpr (SRIF) {
-#pragma unroll
-      for (int i = 0; i < N * N; ++i) P[i] = io.mat[(int64_t)i * io.nf + tid];
-    } else {
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int j = i; j < N; ++j) P[sym_idx<N>(i, j)] = io.mat[(int64_t)(i * N + j) * io.nf + tid];
-    }
-  } else {  // lanes past the last filter run on an identity problem (the TMA zero-fills their columns)
-#pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < SN; ++i) P[i] = 0.0;
-    if constexpr (SRIF) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) P[i * N + i] = 1.0;
-    }
-  }
-  int status = 0;
-  int s = 0;
-  uint32_t phase = 0;
-  for (int k = 0; k < io.steps; ++k) {
-    const unsigned fl = io.flags ? io.flags[k] : (unsigned)GKB_F_MEAS;
-    const bool has_meas = (fl & GKB_F_MEAS) != 0, ekf = (fl & GKB_F_EKF) != 0;
-    tma::mbar_wait(&full[s], phase);
-    const double* col = ring + (size_t)s * ROWS * 32 + lane;
-    double Phi[N * N], Ht[M * N], ro[M], co[M];
-#pragma unroll
-    for (int i = 0; i < N * N; ++i) Phi[i] = col[i * 32];
-    if (has_meas) {
-#pragma unroll
-      for (int i = 0; i < M * N; ++i) Ht[i] = col[(ROWS_PHI + i) * 32];
-#pragma unroll
-      for (int a = 0; a < M; ++a) {
-        ro[a] = col[(ROWS_PHI + ROWS_H + a) * 32];
-        co[a] = col[(ROWS_PHI + ROWS_H + M + a) * 32];
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < M * N; ++i) Ht[i] = 0.0;
-#pragma unroll
-      for (int a = 0; a < M; ++a) { ro[a] = 0.0; co[a] = 0.0; }
-    }
-    __syncwarp();  // all 32 columns of the stage are in registers: re-arm it
-    if (lane == 0 && k + kWStages < io.steps) issue(k + kWStages, s);
-    if (++s == kWStages) { s = 0; phase ^= 1u; }
-    NlOut<N, M> o;
-    int err;
-    if constexpr (SRIF) {
-      if (!active) {  // keep the padding lanes' Phi invertible (zero-filled by the TMA)
-#pragma unroll
-        for (int i = 0; i < N; ++i) Phi[i * N + i] = 1.0;
-      }
-      err = srif_step<N, M>(md, x, P, Phi, Ht, ro, co, has_meas, o);
-    } else {
-      err = hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, nullptr, has_meas, ekf, false, o);
-    }
-    if (err != 0 && status == 0) status = err;
-  }
-  if constexpr (SRIF) {
-    // read-outs of the last estimate: State() = inv(R) b (srif.go:223-235), Covariance() = inv(R) inv(R)^T (253-265)
-    if (io.o_state != nullptr) {
-      double xs[N];
-      if (!srif_state<N>(xs, P, x)) {
-        if (status == 0) status = GKB_ERR_SINGULAR_R;
-#pragma unroll
-        for (int i = 0; i < N; ++i) xs[i] = 0.0;
-      }
-      if (active) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) io.o_state[(int64_t)i * io.nf + tid] = xs[i];
-      }
-    }
-    if (io.o_covar != nullptr) {
-      double Pc[N * N];
-      srif_covariance<N>(Pc, P);
-      if (active) {
-#pragma unroll
-        for (int i = 0; i < N * N; ++i) io.o_covar[(int64_t)i * io.nf + tid] = Pc[i];
-      }
-    }
-    if (active) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) io.vec[(int64_t)i * io.nf + tid] = x[i];
-#pragma unroll
-      for (int i = 0; i < N * N; ++i) io.mat[(int64_t)i * io.nf + tid] = P[i];
-    }
-  } else if (active) {
-    if (io.o_state != nullptr) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) io.o_state[(int64_t)i * io.nf + tid] = x[i];
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) io.vec[(int64_t)i * io.nf + tid] = x[i];
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const double v = P[sym_idx<N>(i, j)];
-        io.mat[(int64_t)(i * N + j) * io.nf + tid] = v;
-        if (io.o_covar != nullptr) io.o_covar[(int64_t)(i * N + j) * io.nf + tid] = v;
-      }
-  }
-  if (active && io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
-}
-
-// cuTensorMapEncodeTiled, fetched through the runtime so the library carries no link-time libcuda dependency.
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-// [rows_total][nf] FP64 stream, box = {32 filters, box_rows}; false when TMA cannot describe it.
-static bool make_stream_map(CUtensorMap* map, const double* base, int64_t nf, int64_t rows_total, int box_rows) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || rows_total < 1 || rows_total > 0x7fffffffLL || box_rows > 256) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)nf, (cuuint64_t)rows_total};
-  const cuuint64_t strides[1] = {(cuuint64_t)nf * sizeof(double)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1u, 1u};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int N, int M>
 static int launch_nl_shape(const HostModel& hm, const NlIo& io, cudaStream_t s) {
   const unsigned grid = (unsigned)((io.nf + kThreads - 1) / kThreads);
@@ -711,48 +364,12 @@ static int launch_nl_shape(const HostModel& hm, const NlIo& io, cudaStream_t s) 
   for (int i = 0; i < hm.q * hm.q; ++i) md.Q[i] = hm.Q[i];
   for (int i = 0; i < M * M; ++i) { md.R[i] = hm.R[i]; md.L[i] = hm.L[i]; }
   md.q = hm.q;
-  // TMA-staged fast path (the production configuration of both NLDKF kinds): per-filter streams, no SNC
-  // epochs, final-estimate outputs only, streams that satisfy the TMA's 16-byte rules (even filter count,
-  // 16-byte aligned bases).
-  constexpr int ROWS = N * N + M * N + 2 * M;
-  const size_t smem = sizeof(double) * 2 * ROWS * kThreads + 2 * sizeof(uint64_t);
-  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const bool fast = !io.phi_shared && !io.h_shared && io.Gamma == nullptr && !io.every_step && io.Htilde != nullptr &&
-                    io.real_obs != nullptr && io.computed_obs != nullptr && (io.nf % 2 == 0) && aligned(io.Phi) &&
-                    aligned(io.Htilde) && aligned(io.real_obs) && aligned(io.computed_obs) && io.o_meas == nullptr &&
-                    io.o_innov == nullptr && io.o_pred == nullptr && io.o_gain == nullptr && io.o_obsdev == nullptr &&
-                    smem <= 110 * 1024 && io.steps >= 2 && io.nf < 0x7fffffffLL;
-  const char* path = getenv("GKB_NL_PATH");  // A/B switch for tests and profiling: plain | bulk | tensor
-  const bool want_bulk = path && !strcmp(path, "bulk"), want_plain = path && !strcmp(path, "plain");
   const bool srif = hm.kind == GKB_SRIF;
   if (hm.kind != GKB_HYBRID && !srif) return GKB_ERR_UNSUPPORTED;
-  if (fast && !want_plain && !(want_bulk && !srif)) {
-    NlTensorMaps maps;
-    const int64_t st = io.steps;
-    if (make_stream_map(&maps.phi, io.Phi, io.nf, st * N * N, N * N) &&
-        make_stream_map(&maps.h, io.Htilde, io.nf, st * M * N, M * N) &&
-        make_stream_map(&maps.real_obs, io.real_obs, io.nf, st * M, M) &&
-        make_stream_map(&maps.computed_obs, io.computed_obs, io.nf, st * M, M)) {
-      const size_t wsmem = sizeof(double) * (kThreads / 32) * kWStages * ROWS * 32 + (kThreads / 32) * kWStages * sizeof(uint64_t);
-      auto launch = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        kern<<<grid, kThreads, wsmem, s>>>(md, io, maps);
-      };
-      if (srif) launch(nl_run_wtma_kernel<N, M, true>);
-      else launch(nl_run_wtma_kernel<N, M, false>);
-      return 0;
-    }
-  }
+  // production configuration (per-filter streams, final outputs only): the TMA kernels of kernels_nl_tma.cu
+  if (launch_nl_tma(hm, io, s) == 0) return 0;
   if (srif) {
     srif_run_kernel<N, M><<<grid, kThreads, 0, s>>>(md, io);
-    return 0;
-  }
-  if (fast && want_bulk) {
-    auto kern = hybrid_run_tma_kernel<N, M>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<grid, kThreads, smem, s>>>(md, io);
     return 0;
   }
   hybrid_run_kernel<N, M><<<grid, kThreads, 0, s>>>(md, io);

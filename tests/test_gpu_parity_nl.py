@@ -133,6 +133,17 @@ def test_hybrid_tma_staged_path_matches_oracle(oracle, n, m, nf):
         est2, vec2, mat2 = run(path)
         assert np.array_equal(vec, vec2) and np.array_equal(mat, mat2), path
         assert np.array_equal(np.asarray(est.State()), np.asarray(est2.State())), path
+    # the persistent scheduler's chunked mode (epochs of a group handed from warp to warp through the state
+    # arrays) is what a 10^5-filter run uses; forced here on a small batch: bit-identical again
+    for chunks in ("2", "5"):
+        os.environ["GKB_NL_CHUNKS"] = chunks
+        try:
+            est3, vec3, mat3 = run(None)
+        finally:
+            del os.environ["GKB_NL_CHUNKS"]
+        assert np.array_equal(vec, vec3) and np.array_equal(mat, mat3), chunks
+        assert np.array_equal(np.asarray(est.State()), np.asarray(est3.State())), chunks
+        assert np.array_equal(np.asarray(est.Covariance()), np.asarray(est3.Covariance())), chunks
     for f in sorted(set([0, 1, nf // 2, nf - 2, nf - 1])):
         o = oracle.NewHybridKF(np.zeros(n), P0, Q, R, m)
         ref = _oracle_run(o, flags, Phi, Ht, real, comp, None, f, F_MEAS, F_EKF, F_SNC)[-1]
@@ -175,6 +186,13 @@ def test_srif_tma_staged_path_matches_oracle(oracle, n, m, nf):
     assert np.array_equal(vec, vec2) and np.array_equal(mat, mat2)
     assert np.array_equal(np.asarray(est.State()), np.asarray(est2.State()))
     assert np.array_equal(np.asarray(est.Covariance()), np.asarray(est2.Covariance()))
+    os.environ["GKB_NL_CHUNKS"] = "4"  # chunked persistent scheduling, forced
+    try:
+        est3, vec3, mat3 = run(None)
+    finally:
+        del os.environ["GKB_NL_CHUNKS"]
+    assert np.array_equal(vec, vec3) and np.array_equal(mat, mat3)
+    assert np.array_equal(np.asarray(est.Covariance()), np.asarray(est3.Covariance()))
     for f in sorted(set([0, 1, nf // 2, nf - 2, nf - 1])):
         o = oracle.NewSRIF(0.2 * np.ones(n), P0, m, False, R)
         ref = _oracle_run(o, flags, Phi, Ht, real, comp, None, f, F_MEAS, F_EKF, F_SNC)[-1]
