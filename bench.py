@@ -296,7 +296,9 @@ def run_ours_mc(args, rank, world, local):
                      "note": "%g algorithmic flop per (trial, step) per SURVEY App. B; RNG/Box-Muller work not counted" % spec["flops"]},
         "e2e": {"value": e2e_value, "unit": "filter-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "NewMonteCarloRuns + NewChiSquare (host buffers)"},
-        "gpu_launches": 3 * args.steps,  # setup + fused MC kernel + finish per step (ours; torch memset/NCCL not counted)
+        # fused MC kernel + finish kernel per step, as counted by the library (the model-setup kernel runs once, before
+        # the timed region: its result is cached); torch's memset / division and NCCL are not ours and not counted
+        "gpu_launches": int(lib.gkb_last_kernel_launches()) * args.steps,
         "clocks": clocks,
         "wall_s": wall,
         "step_ms": [round(x, 3) for x in step_ms],

@@ -1,7 +1,8 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 120 python bench.py --workload hybrid6 --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/hyb_e.json
-python -c "import json;d=json.load(open('gpurun_out/hyb_e.json'));print('hyb',d['value'],d['roofline']['kernel_ms'],d['roofline']['hbm']['frac'],d['cpu_baseline'])"
-timeout 120 python bench.py --workload srif6 --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/srif_g.json
-python -c "import json;d=json.load(open('gpurun_out/srif_g.json'));print('srif',d['value'],d['roofline']['kernel_ms'],d['cpu_baseline'])"
-timeout 300 python bench.py --workload vanilla32 --steps 5 --warmup 3 2>&1 | tail -1 > gpurun_out/tile_d.json
-python -c "import json;d=json.load(open('gpurun_out/tile_d.json'));print('tile',d['value'],d['roofline']['kernel_ms'],d['cpu_baseline'])"
+# The round-end check, as one gpurun command:  gpurun --timeout 1500 -- 'bash tools/gpu_job.sh > gpurun_out/job.log 2>&1'
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_final_reference.json | cut -c1-300
+python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_final.json | cut -c1-300
+ncu --target-processes application-only --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+tail -8 gpurun_out/launches_final.csv | cut -c1-300
