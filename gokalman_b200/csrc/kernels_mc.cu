@@ -61,7 +61,7 @@ static int pick_grid(Kern kern, size_t smem, int64_t trials, int device) {
 template <int N, int M>
 static int launch_mc_shape_vanilla(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
-  const size_t smem = sizeof(double) * kWarps * kChunk * cols;
+  const size_t smem = sizeof(double) * (kIcdfSegments * kIcdfCoefs + kWarps * kChunk * cols);
   int grid = 1;
   const bool lean = io.noise_mode == GKB_NOISE_PHILOX && !io.want_xstats && !io.truth_x && !io.truth_y &&
                     !io.noise_w && !io.noise_v && !io.status;
@@ -104,7 +104,7 @@ int launch_mc_vanilla(const HostModel& hm, const McIo& io, int device, int* grid
 template <int N, int M>
 static int launch_mc_shape_info(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
-  const size_t smem = sizeof(double) * kWarps * kChunk * cols;
+  const size_t smem = sizeof(double) * (kIcdfSegments * kIcdfCoefs + kWarps * kChunk * cols);
   int grid = 1;
   const bool lean = io.noise_mode == GKB_NOISE_PHILOX && !io.want_xstats && !io.truth_x && !io.truth_y &&
                     !io.noise_w && !io.noise_v && !io.status;
@@ -144,7 +144,7 @@ int launch_mc_info(const HostModel& hm, const McIo& io, int device, int* grid_ou
 template <int N, int M>
 static int launch_mc_shape_sqrt(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
-  const size_t smem = sizeof(double) * kWarps * kChunk * cols;
+  const size_t smem = sizeof(double) * (kIcdfSegments * kIcdfCoefs + kWarps * kChunk * cols);
   int grid = 1;
   const bool lean = io.noise_mode == GKB_NOISE_PHILOX && !io.want_xstats && !io.truth_x && !io.truth_y &&
                     !io.noise_w && !io.noise_v && !io.status;

@@ -11,9 +11,6 @@
 // global memory, flushed every kChunk steps -> a second tiny kernel sums the CTA rows in CTA order.
 // No atomics: the result is bit-reproducible for a given (trials, grid).
 #pragma once
-#ifndef GKB_MC_HOIST_COEF
-#define GKB_MC_HOIST_COEF 0
-#endif
 #ifndef GKB_MC_MIN_CTAS
 // resident CTAs per SM the register allocator must leave room for (measured on B200 for n = 3:
 // 5 CTAs of 128 threads = 96 registers is the fastest point, see DESIGN.md "tuning log")
@@ -260,18 +257,15 @@ mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_con
   const typename Tested::Model& md = md_c;
 #endif
   const int cols = kMcBaseCols + ((!LEAN && io.want_xstats) ? 3 * N : 0);
-  extern __shared__ double acc[];  // [kWarps][kChunk][cols]
+  extern __shared__ __align__(16) double smem_mc[];  // [icdf table][kWarps][kChunk][cols]
+  double* icdf_tab = smem_mc;
+  double* acc = smem_mc + kIcdfSegments * kIcdfCoefs;
+  icdf_load(icdf_tab);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* wacc = acc + (size_t)warp * kChunk * cols;
   for (int i = threadIdx.x; i < kWarps * kChunk * cols; i += blockDim.x) acc[i] = 0.0;
   __syncthreads();
   double* prow = io.partial + (size_t)blockIdx.x * io.steps * cols;
-  BmCoef cf;
-#if GKB_MC_HOIST_COEF
-  cf.load_opaque();
-#else
-  cf.load();
-#endif
 
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < io.trials; base += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = base + threadIdx.x;
@@ -294,8 +288,8 @@ mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_con
         double w[N], v[M];
         if (LEAN || io.noise_mode == GKB_NOISE_PHILOX) {
           double z[N + M];
-          if constexpr (LEAN && N + M <= 4) philox_normals_trial<N + M>(cf, pt, io.seed, (uint32_t)k, z);
-          else philox_normals<N + M>(cf, io.seed, gtrial, (uint32_t)k, z);
+          if constexpr (LEAN && N + M <= 4) philox_normals_trial<N + M>(icdf_tab, pt, io.seed, (uint32_t)k, z);
+          else philox_normals<N + M>(icdf_tab, io.seed, gtrial, (uint32_t)k, z);
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             double s = 0.0;

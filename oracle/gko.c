@@ -1053,7 +1053,7 @@ int gko_batch_solve(int n, int m, int count, const double* R, const double* H, c
   return rc;
 }
 
-/* ---- Philox4x32-10 + Box-Muller: the oracle's own noise stream --------------------------------- */
+/* ---- Philox4x32-10 + inverse normal CDF: the oracle's own noise stream --------------------------------- */
 
 void gko_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
@@ -1072,23 +1072,38 @@ void gko_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* The engine's Gaussian transform (include/gokalman_b200_icdf.inc, tools/gen_icdf_table.py): one 32-bit word k
+ * -> u = (k + 0.5) 2^-32 -> z = Phi^-1(u) by a quintic in the low 27 bits of the normalised tail probability on one
+ * of 512 segments (16 per binary octave).  Same table, same fused Horner evaluation as the kernels: bit-identical. */
+static const double gko_icdf_table[512 * 6] = {
+#include "../include/gokalman_b200_icdf.inc"
+};
+
+double gko_icdf_normal(uint32_t k) {
+  const uint32_t upper = k >> 31;
+  const uint32_t j = upper ? ~k : k;
+  const uint32_t J = (j << 1) | 1u;
+  const int lz = __builtin_clz(J);
+  const uint32_t Jn = J << lz;
+  const uint32_t seg = ((31u - (uint32_t)lz) << 4) | ((Jn >> 27) & 15u);
+  const double v = (double)(Jn & 0x07ffffffu);
+  const double* c = gko_icdf_table + seg * 6;
+  double g = fma(c[5], v, c[4]);
+  g = fma(g, v, c[3]);
+  g = fma(g, v, c[2]);
+  g = fma(g, v, c[1]);
+  g = fma(g, v, c[0]);
+  return upper ? g : -g;
+}
+
 void gko_philox_normals(uint64_t seed, uint64_t trial, uint32_t step, int count, double* z) {
-  /* normals 4b..4b+3 come from block b: counter = (trial_lo, trial_hi, step, b), key = seed.
-   * u = (word + 0.5) * 2^-32 in (0,1); (z0,z1) = sqrt(-2 ln u0) (cos, sin)(2 pi u1), same for words 2,3. */
+  /* normal 4b + i is word i of block b: counter = (trial_lo, trial_hi, step, b), key = seed */
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   for (int b = 0; 4 * b < count; ++b) {
     uint32_t ctr[4] = {(uint32_t)trial, (uint32_t)(trial >> 32), step, (uint32_t)b};
     uint32_t o[4];
     gko_philox4x32_10(ctr, key, o);
-    for (int p = 0; p < 2; ++p) {
-      double u0 = ((double)o[2 * p] + 0.5) * 2.3283064365386963e-10;
-      double u1 = ((double)o[2 * p + 1] + 0.5) * 2.3283064365386963e-10;
-      double r = sqrt(-2.0 * log(u0));
-      double a = 6.283185307179586476925286766559 * u1;
-      int j = 4 * b + 2 * p;
-      if (j < count) z[j] = r * cos(a);
-      if (j + 1 < count) z[j + 1] = r * sin(a);
-    }
+    for (int i = 0; i < 4 && 4 * b + i < count; ++i) z[4 * b + i] = gko_icdf_normal(o[i]);
   }
 }
 

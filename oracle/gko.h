@@ -162,6 +162,8 @@ int gko_mc_chisquare(const gko_mc_config* cfg, double* nis_means, double* nees_m
 
 /* Philox4x32-10 (Salmon et al., SC'11; Random123 v1.09), one block: ctr[4], key[2] -> out[4]. */
 void gko_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* One standard normal from one 32-bit word: the engine's piecewise-quintic inverse CDF (same table as the kernels). */
+double gko_icdf_normal(uint32_t k);
 /* The oracle's standard-normal stream: normal #j (j = 0..n+m-1) of (seed, trial, step). */
 void gko_philox_normals(uint64_t seed, uint64_t trial, uint32_t step, int count, double* z);
 

@@ -80,7 +80,8 @@ class McConfig(C.Structure):
 
 def build(force=False):
     """Compile oracle/_build/libgko.so with the committed Makefile (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("gko.c", "gko_linalg.c", "gko.h", "gko_linalg.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("gko.c", "gko_linalg.c", "gko.h", "gko_linalg.h", "Makefile",
+                                               os.path.join("..", "include", "gokalman_b200_icdf.inc"))]
     if (not force and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
@@ -133,6 +134,8 @@ def lib():
     L.gko_batch_solve.argtypes = [ip, ip, ip, dp, dp, dp, dp, dp, dp]
     L.gko_mc_chisquare.argtypes = [C.POINTER(McConfig), dp, dp, dp, dp, dp, dp]
     L.gko_philox4x32_10.argtypes = [dp, dp, dp]
+    L.gko_icdf_normal.argtypes = [C.c_uint32]
+    L.gko_icdf_normal.restype = C.c_double
     L.gko_philox_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, ip, dp]
     for name in ("gko_inverse",):
         getattr(L, name).argtypes = [dp, dp, ip, dp]
@@ -400,6 +403,11 @@ def batch_solve(R, H, real_obs, computed_obs):
     if rc != 0:
         raise OracleError(rc)
     return x, P
+
+
+def icdf_normal(k):
+    """The engine's Gaussian transform of one 32-bit word (piecewise-quintic inverse normal CDF)."""
+    return lib().gko_icdf_normal(int(k) & 0xFFFFFFFF)
 
 
 def philox4x32_10(ctr, key):
