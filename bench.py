@@ -285,7 +285,7 @@ def run_ours_mc(args, rank, world, local):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": spec["label"],
-                   "trials_per_gpu": trials, "filter_steps": steps, "n": nn, "m": mm, "c": 1, "noise": "philox4x32-10 in-kernel",
+                   "trials_per_gpu": trials, "filter_steps": steps, "n": nn, "m": mm, "c": 1, "noise": "philox4x32-10 + table inverse normal CDF, in-kernel",
                    "sharding": "trials split by rank, one NCCL all-reduce of 2 x %d doubles per step" % steps,
                    "l2": "flushed between timed iterations (256 MiB memset)", "nis_mean": nis_mean, "nees_mean": nees_mean},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
@@ -293,7 +293,7 @@ def run_ours_mc(args, rank, world, local):
                      "traffic": measured_traffic(wl, trials == 1000000 and steps == 1000),
                      "kernel": spec["kernel"], "kernel_ms": main_ms,
                      "flops_per_unit": spec["flops"], "peak_source": peak_src,
-                     "note": "%g algorithmic flop per (trial, step) per SURVEY App. B; RNG/Box-Muller work not counted" % spec["flops"]},
+                     "note": "%g algorithmic flop per (trial, step) per SURVEY App. B; RNG / inverse-CDF work not counted" % spec["flops"]},
         "e2e": {"value": e2e_value, "unit": "filter-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "NewMonteCarloRuns + NewChiSquare (host buffers)"},
         # fused MC kernel + finish kernel per step, as counted by the library (the model-setup kernel runs once, before

@@ -197,7 +197,7 @@ int gkb_set_state(gkb_filter* f, const double* vec, const double* mat);
  *      measurements; NEES and NIS are reduced over trials per step.  Nothing is stored unless an
  *      optional dump pointer is given. */
 typedef enum gkb_noise_mode {
-  GKB_NOISE_PHILOX = 0, /* Philox4x32-10, key = seed, counter = (trial, step, block); Box-Muller */
+  GKB_NOISE_PHILOX = 0, /* Philox4x32-10, key = seed, counter = (trial, step, block); inverse normal CDF */
   GKB_NOISE_REPLAY = 1  /* uploaded, already coloured w [steps][n][trials], v [steps][m][trials]  */
 } gkb_noise_mode;
 

@@ -144,7 +144,7 @@ typedef struct gko_mc_config {
   int trials, steps;
   const double* controls;     /* [steps][c], or NULL => zero controls (montecarlo.go:98-104)   */
   /* noise source for the truth generator: replay arrays if non-NULL, else Philox4x32-10 keyed by
-   * `seed` with counter (trial_offset+trial, step) -> Box-Muller, coloured by chol(Q), chol(R). */
+   * `seed` with counter (trial_offset+trial, step) -> inverse normal CDF (gko_icdf_normal), coloured by chol(Q), chol(R). */
   const double* w;            /* [trials][steps][n], already coloured                          */
   const double* v;            /* [trials][steps][m]                                            */
   uint64_t seed;
