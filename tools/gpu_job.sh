@@ -1,2 +1,9 @@
-ncu --set full --clock-control none --import-source on -k regex:mc_chisquare -s 3 -c 1 -o gpurun_out/prof_mc_r01_icdf python bench.py --filter-steps 300 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_mc.log 2>&1
-tail -2 gpurun_out/ncu_mc.log | cut -c1-200
+# The round-end check, as one gpurun command:  gpurun --timeout 1500 -- 'bash tools/gpu_job.sh > gpurun_out/job.log 2>&1'
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_final_reference.json | cut -c1-300
+python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_final.json | cut -c1-300
+ncu --target-processes application-only --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+tail -4 gpurun_out/launches_final.csv | cut -c1-300
+bash tools/measure_traffic.sh > gpurun_out/traffic.log 2>&1
