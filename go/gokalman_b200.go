@@ -164,3 +164,59 @@ func sqrt(x float64) float64 { // avoid importing math for one call in this sket
 	}
 	return z
 }
+
+// ---- entry points added after the first sketch (same caveat: source only) -------------------------------
+
+// SmoothAll mirrors HybridKF.SmoothAll / SRIF.SmoothAll (hybrid.go:209-238, srif.go:165-192) on the stored
+// histories of a batch: Phi [steps][n*n][N] (or [steps][n*n] when phiShared), state [steps][n][N],
+// covar [steps][n*n][N], all overwritten in place for k < steps-1.
+func SmoothAll(n, steps int, nFilters int64, device int, Phi []float64, phiShared bool, state, covar []float64) error {
+	shared := C.int(0)
+	if phiShared {
+		shared = 1
+	}
+	status := make([]C.int32_t, nFilters)
+	rc := C.gkb_smooth_all(C.int(n), C.int(steps), C.int64_t(nFilters), C.int(device), ptr(Phi), shared,
+		ptr(state), ptr(covar), C.GKB_HOST, &status[0])
+	if err := lastErr(rc); err != nil {
+		return err
+	}
+	for _, s := range status {
+		if s != 0 {
+			return errors.New("provided STM Φ is not invertible") // hybrid.go:222
+		}
+	}
+	return nil
+}
+
+// BatchSolve mirrors NewBatchKF + SetNextMeasurement x steps + Solve (batch.go:34-79) for N batch filters.
+func BatchSolve(n, m, steps int, nFilters int64, device int, R, H []float64, hShared bool, realObs, computedObs []float64) (xHat0, P0 []float64, err error) {
+	shared := C.int(0)
+	if hShared {
+		shared = 1
+	}
+	xHat0 = make([]float64, int64(n)*nFilters)
+	P0 = make([]float64, int64(n*n)*nFilters)
+	rc := C.gkb_batch_solve(C.int(n), C.int(m), C.int(steps), C.int64_t(nFilters), C.int(device), ptr(R), ptr(H), shared,
+		ptr(realObs), ptr(computedObs), C.GKB_HOST, ptr(xHat0), ptr(P0), nil)
+	return xHat0, P0, lastErr(rc)
+}
+
+// HouseholderTransf mirrors gokalman.HouseholderTransf (helper.go:142-172), in place on A ((n+m) x (n+1)).
+func HouseholderTransf(A *mat64.Dense, n, m int) error {
+	data := raw(A)
+	if err := lastErr(C.gkb_householder_transf(C.int(n), C.int(m), 1, 0, ptr(data), C.GKB_HOST)); err != nil {
+		return err
+	}
+	r, c := A.Dims()
+	for i := 0; i < r; i++ {
+		for j := 0; j < c; j++ {
+			A.Set(i, j, data[i*c+j])
+		}
+	}
+	return nil
+}
+
+// FilterMajor reports the array layout of a handle: large-state Vanilla handles (n = 16 / 24 / 32) take and
+// return filter-major arrays [N][C] instead of [C][N] (see gkb_filter_major in the header).
+func (kf *Vanilla) FilterMajor() bool { return C.gkb_filter_major(kf.h) != 0 }
