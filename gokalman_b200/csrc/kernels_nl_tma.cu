@@ -225,11 +225,17 @@ __device__ __forceinline__ void nl_wtma_task(const NlModel<N, M>& md, const NlIo
   };
   // the input streams do not depend on the previous chunk: start them before waiting for the state
   if (lane == 0) {
-    int st = s;
+    if constexpr (SCHED) {
+      int st = s;
 #pragma unroll
-    for (int j = 0; j < kWStages; ++j) {
-      if (k0 + j < k1) issue(k0 + j, st);
-      if (++st == kWStages) st = 0;
+      for (int j = 0; j < kWStages; ++j) {
+        if (k0 + j < k1) issue(k0 + j, st);
+        if (++st == kWStages) st = 0;
+      }
+    } else {  // one task per warp: the ring starts at stage 0
+#pragma unroll
+      for (int j = 0; j < kWStages; ++j)
+        if (j < k1) issue(j, j);
     }
   }
   if (SCHED && wait_for != nullptr) acquire_group_state(wait_for, wait_value, lane);
