@@ -323,13 +323,25 @@ def oracle_mc_rate(trials, steps, threads, workload="mc_jerk3"):
     return trials * steps / dt, dt, float(r["NEES"].mean())
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(target_s=12.0, workload="mc_jerk3"):
     cores = os.cpu_count() or 1
     steps = 1000
     rate, _, _ = oracle_mc_rate(cores * 4, steps, cores, workload)  # calibration
     trials = max(cores, int(rate * target_s / steps / cores) * cores)
+    single, _, _ = oracle_mc_rate(max(8, trials // (cores * 8)), steps, 1, workload)  # ~1.5 s on one thread
     rate, dt, _ = oracle_mc_rate(trials, steps, cores, workload)
-    return {"value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port",
+    return {"value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port", "single_thread_value": single,
+            "cpu_model": cpu_model(), "omp_num_threads": cores,
             "sample": "%d trials x %d steps of %s (%.1f s), C oracle restatement with OpenMP over trials; "
                       "the Go/gonum reference cannot be built here (no Go toolchain)" % (trials, steps, workload, dt)}
 
@@ -399,7 +411,8 @@ def cpu_baseline_filters(workload, target_s=10.0):
     cores = os.cpu_count() or 1
     nf, steps = filter_sample_size(workload, cores, target_s)
     rate, dt = oracle_filter_rate(workload, nf, steps, cores)
-    return {"value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port",
+    return {"value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+            "omp_num_threads": cores,
             "sample": "%d filters x %d epochs of %s (%.1f s), C oracle restatement with OpenMP over filters; the Go/gonum "
                       "reference cannot be built here (no Go toolchain)" % (nf, steps, workload, dt)}
 
