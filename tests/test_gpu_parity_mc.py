@@ -82,6 +82,30 @@ def test_mc_chisquare_jerk3_matches_oracle(oracle):
         assert fx.scaled_err(r["runs"].StdDev(k), ref["std"][k]) <= 1e-7  # one-pass vs two-pass variance
 
 
+@pytest.mark.parametrize("kind", ["vanilla", "sqrt"])
+def test_mc_chisquare_multid4_two_philox_blocks(oracle, kind):
+    """vanilla_test.go:97-115's 4-state / 2-measurement system: n + m = 6 normals per step, i.e. two Philox blocks
+    per (trial, step) and the general (non-hoisted) generator; m = 2 exercises the 2 x 2 NIS inverse."""
+    gk = _gpu()
+    f = fx.multid4()
+    # a positive definite Q for the AWGN colouring (the fixture's 3 x 3 block is numerically singular)
+    f["Q"] = f["Q"] + 1e-9 * np.eye(4)
+    f["x0_truth"] = f["x0"]
+    steps, trials = 70, 200
+    controls = [np.array([0.1 * np.sin(0.05 * k)]) for k in range(steps)]
+    r = _mc_pair(gk, oracle, f, kind, trials, steps, controls)
+    ref = r["ref"]
+    assert fx.scaled_err(r["nees"], ref["NEES"]) <= TOL
+    assert fx.scaled_err(r["nis"], ref["NIS"]) <= TOL
+    # and the noise the kernel drew is the oracle's own stream for the same (seed, trial, step)
+    LQ, _ = oracle.chol_lower(f["Q"])
+    LR, _ = oracle.chol_lower(f["R"])
+    for t in (0, 199):
+        z = oracle.philox_normals(0x5EED, t, 5, 6)
+        assert np.max(np.abs(r["w"][5, :, t] - LQ @ z[:4])) <= 1e-14 * np.max(np.abs(LQ))
+        assert np.max(np.abs(r["v"][5, :, t] - LR @ z[4:])) <= 1e-14
+
+
 def test_philox_stream_matches_oracle(oracle):
     """The device Philox4x32-10 + inverse-CDF stream is the one the oracle restates: same integers, the same
     table and fused Horner form, so the normals are bit-identical (the colouring L z may differ by an FMA
