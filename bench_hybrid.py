@@ -5,6 +5,7 @@ the end).  Synthetic orbit-determination-like inputs are generated ON THE DEVICE
 synthesis, not the measured path): Phi = I + dt*[[0, I],[G_k, 0]] with a random symmetric
 gravity-gradient block, Htilde from random line-of-sight unit vectors."""
 import ctypes as C
+import os
 import statistics
 import time
 
@@ -72,8 +73,12 @@ def run_ours_hybrid(args, rank, world, local):
     out_state = torch.zeros(n, nf, dtype=torch.float64, device=dev)
     out_cov = torch.zeros(n * n, nf, dtype=torch.float64, device=dev)
     status = torch.zeros(nf, dtype=torch.int32, device=dev)
+    every = bool(int(os.environ.get("GKB_BENCH_EVERY_STEP", "0"))) and not srif
+    if every:  # Estimate of every epoch streamed out (+336 B per update): what a smoothing pass consumes
+        out_state = torch.zeros(steps, n, nf, dtype=torch.float64, device=dev)
+        out_cov = torch.zeros(steps, n * n, nf, dtype=torch.float64, device=dev)
     out = L.Outputs()
-    out.mem, out.every_step = L.DEVICE, 0
+    out.mem, out.every_step = L.DEVICE, int(every)
     out.state, out.covar, out.status = out_state.data_ptr(), out_cov.data_ptr(), status.data_ptr()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -143,7 +148,8 @@ def run_ours_hybrid(args, rank, world, local):
         return None
     main_ms = statistics.mean(kern_ms)
     ups = float(nf) * steps / (main_ms * 1e-3)
-    gbs = ups * BYTES_IN / 1e9
+    bytes_unit = BYTES_IN + (336.0 if every else 0.0)
+    gbs = ups * bytes_unit / 1e9
     flops = 2168.0 if srif else FLOPS_EKF
     tf = ups * flops / 1e12
     bound_hbm = (gbs / hbm) >= (tf / peak_tf)
@@ -154,7 +160,7 @@ def run_ours_hybrid(args, rank, world, local):
         "config": {"workload": ("srif6: 6-state SRIF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])" if srif else
                                 "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams "
                                 "(BASELINE configs[3])"), "filters_per_gpu": nf, "epochs": steps, "n": 6, "m": 2,
-                   "ekf_after": 15, "outputs": "final state + covariance only", "failed_filters": bad,
+                   "ekf_after": 15, "outputs": "state + covariance of every epoch" if every else "final state + covariance only", "failed_filters": bad,
                    "l2": "inputs (%.1f GB) exceed L2; flushed anyway" % (nf * steps * BYTES_IN / 1e9)},
         "roofline": {"bound": "hbm" if bound_hbm else "fp64", "achieved": gbs if bound_hbm else tf,
                      "peak": hbm if bound_hbm else peak_tf, "unit": "GB/s" if bound_hbm else "TFLOP/s",
@@ -162,7 +168,7 @@ def run_ours_hybrid(args, rank, world, local):
                      "traffic": measured_traffic(args.workload, nf == 100000 and steps == 200),
                      "algorithmic_bytes": float(nf) * steps * BYTES_IN,
                      "kernel": "nl_run_wtma_sched_kernel<6,2,SRIF>" if srif else "nl_run_wtma_sched_kernel<6,2> (warp-private TMA tensor-map pipelines, persistent chunk scheduler)", "kernel_ms": main_ms,
-                     "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm, "bytes_per_unit": BYTES_IN, "source": hbm_src},
+                     "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm, "bytes_per_unit": bytes_unit, "source": hbm_src},
                      "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf, "frac": tf / peak_tf, "flops_per_unit": flops,
                               "source": peak_src}},
         "e2e": {"value": e2e_value, "unit": "filter-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

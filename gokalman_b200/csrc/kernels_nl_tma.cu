@@ -301,6 +301,20 @@ __device__ __forceinline__ void nl_wtma_task(const NlModel<N, M>& md, const NlIo
       err = srif_step<N, M>(md, x, P, Phi, Ht, ro, co, has_meas, o);
     } else {
       err = hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, nullptr, has_meas, ekf, false, o);
+      if (io.every_step && active && err == 0) {  // Estimate k: streamed out once, never read back here
+        if (io.o_state != nullptr) {
+          double* dst = io.o_state + (int64_t)k * N * io.nf + tid;
+#pragma unroll
+          for (int i = 0; i < N; ++i) __stcs(dst + (int64_t)i * io.nf, x[i]);
+        }
+        if (io.o_covar != nullptr) {
+          double* dst = io.o_covar + (int64_t)k * N * N * io.nf + tid;
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) __stcs(dst + (int64_t)(i * N + j) * io.nf, P[sym_idx<N>(i, j)]);
+        }
+      }
     }
     if (err != 0 && status == 0) status = err;
   }
@@ -333,7 +347,7 @@ __device__ __forceinline__ void nl_wtma_task(const NlModel<N, M>& md, const NlIo
       for (int i = 0; i < N * N; ++i) io.mat[(int64_t)i * io.nf + tid] = P[i];
     }
   } else if (active) {
-    if (last && io.o_state != nullptr) {
+    if (last && !io.every_step && io.o_state != nullptr) {
 #pragma unroll
       for (int i = 0; i < N; ++i) io.o_state[(int64_t)i * io.nf + tid] = x[i];
     }
@@ -345,7 +359,7 @@ __device__ __forceinline__ void nl_wtma_task(const NlModel<N, M>& md, const NlIo
       for (int j = 0; j < N; ++j) {
         const double v = P[sym_idx<N>(i, j)];
         io.mat[(int64_t)(i * N + j) * io.nf + tid] = v;
-        if (last && io.o_covar != nullptr) io.o_covar[(int64_t)(i * N + j) * io.nf + tid] = v;
+        if (last && !io.every_step && io.o_covar != nullptr) io.o_covar[(int64_t)(i * N + j) * io.nf + tid] = v;
       }
   }
   if (active && io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
@@ -466,7 +480,10 @@ static int launch_nl_tma_shape(const HostModel& hm, const NlIo& io, cudaStream_t
   constexpr int ROWS = N * N + M * N + 2 * M;
   const size_t smem = sizeof(double) * 2 * ROWS * kThreads + 2 * sizeof(uint64_t);
   auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const bool fast = !io.phi_shared && !io.h_shared && io.Gamma == nullptr && !io.every_step && io.Htilde != nullptr &&
+  // every-step outputs (state / covariance of each epoch, the input of SmoothAll) are streamed by the hybrid kernel;
+  // the SRIF's per-epoch read-outs need inv(R) each time and stay on the general kernel
+  const bool fast = !io.phi_shared && !io.h_shared && io.Gamma == nullptr && (!io.every_step || hm.kind == GKB_HYBRID) &&
+                    io.Htilde != nullptr &&
                     io.real_obs != nullptr && io.computed_obs != nullptr && (io.nf % 2 == 0) && aligned(io.Phi) &&
                     aligned(io.Htilde) && aligned(io.real_obs) && aligned(io.computed_obs) && io.o_meas == nullptr &&
                     io.o_innov == nullptr && io.o_pred == nullptr && io.o_gain == nullptr && io.o_obsdev == nullptr &&

@@ -144,6 +144,25 @@ def test_hybrid_tma_staged_path_matches_oracle(oracle, n, m, nf):
         assert np.array_equal(vec, vec3) and np.array_equal(mat, mat3), chunks
         assert np.array_equal(np.asarray(est.State()), np.asarray(est3.State())), chunks
         assert np.array_equal(np.asarray(est.Covariance()), np.asarray(est3.Covariance())), chunks
+    # every-step state / covariance outputs (what SmoothAll consumes) are streamed by the same TMA kernels
+    def run_all(path, chunks=None):
+        if path:
+            os.environ["GKB_NL_PATH"] = path
+        if chunks:
+            os.environ["GKB_NL_CHUNKS"] = chunks
+        try:
+            kf, _ = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R), m, n_filters=nf)
+            e = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=True, want=("state", "covar"))
+        finally:
+            os.environ.pop("GKB_NL_PATH", None)
+            os.environ.pop("GKB_NL_CHUNKS", None)
+        return np.asarray(e.State()).copy(), np.asarray(e.Covariance()).copy()
+    xs_a, Ps_a = run_all(None)
+    xs_p, Ps_p = run_all("plain")
+    xs_c, Ps_c = run_all(None, "3")
+    assert np.array_equal(xs_a, xs_p) and np.array_equal(Ps_a, Ps_p)
+    assert np.array_equal(xs_a, xs_c) and np.array_equal(Ps_a, Ps_c)
+    assert np.array_equal(xs_a.reshape(steps, n, nf)[-1], np.asarray(est.State()).reshape(n, nf))
     for f in sorted(set([0, 1, nf // 2, nf - 2, nf - 1])):
         o = oracle.NewHybridKF(np.zeros(n), P0, Q, R, m)
         ref = _oracle_run(o, flags, Phi, Ht, real, comp, None, f, F_MEAS, F_EKF, F_SNC)[-1]
