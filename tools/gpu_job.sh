@@ -1,1 +1,1 @@
-python tools/bench_smooth.py 2>&1 | tail -2
+python tools/bench_lti.py 2>&1 | tail -4
