@@ -8,13 +8,22 @@ namespace gkb {
 #error "compile with -DGKB_MC_PART=0..3 (see Makefile): 0 = dispatch + finish kernel, 1/2/3 = vanilla / information / sqrt kernels"
 #endif
 #if GKB_MC_PART == 0
-// out[col][k] = scale * sum_b partial[b][k][col], CTA rows added in CTA order.
-__global__ void mc_finish_kernel(const double* __restrict__ partial, int grid, int steps, int cols, double scale,
-                                 double* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= steps * cols) return;
+// out[col][k] = scale * sum_b partial[b][k][col].  A CTA is 32 result slots x 8 row groups: thread (x, y) adds the CTA
+// rows y, y + 8, ... of slot x in order, then the 8 group sums are added in group order -- a fixed order, so the
+// result is bit-reproducible for a given grid, with 8x the memory parallelism of one thread per slot.
+__global__ void __launch_bounds__(256) mc_finish_kernel(const double* __restrict__ partial, int grid, int steps, int cols,
+                                                        double scale, double* __restrict__ out) {
+  __shared__ double part[8][33];
+  const int idx = blockIdx.x * 32 + threadIdx.x;
+  const int total = steps * cols;
   double s = 0.0;
-  for (int b = 0; b < grid; ++b) s += partial[(size_t)b * steps * cols + idx];
+  if (idx < total)
+    for (int b = threadIdx.y; b < grid; b += 8) s += partial[(size_t)b * total + idx];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || idx >= total) return;
+#pragma unroll
+  for (int g = 1; g < 8; ++g) s += part[g][threadIdx.x];
   const int k = idx / cols, col = idx % cols;
   out[(size_t)col * steps + k] = (col < kMcBaseCols) ? s * scale : s;  // only NIS / NEES become means
 }
@@ -202,7 +211,7 @@ int launch_mc(const HostModel& hm, const McIo& io, int device, int* grid_out, cu
 int launch_mc_finish(const double* partial, int grid, int steps, int cols, double scale, double* out_cols,
                      cudaStream_t s) {
   const int total = steps * cols;
-  mc_finish_kernel<<<(total + 255) / 256, 256, 0, s>>>(partial, grid, steps, cols, scale, out_cols);
+  mc_finish_kernel<<<(total + 31) / 32, dim3(32, 8), 0, s>>>(partial, grid, steps, cols, scale, out_cols);
   return 0;
 }
 
