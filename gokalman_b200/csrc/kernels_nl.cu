@@ -5,9 +5,6 @@
 // observation, streamed from HBM in SoA [step][component][filter]: a warp reads one coalesced
 // 256-byte row per component.  Per-epoch flags (Predict vs Update, EKF on/off, SNC on/off) are
 // shared by all filters, so the control flow is warp-uniform.
-#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through the runtime, no libcuda link)
-
-#include <cstdlib>
 #include <cstring>
 
 #include "engine_internal.h"

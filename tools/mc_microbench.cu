@@ -1,6 +1,6 @@
 // Standalone timing of the LEAN <3,1,Vanilla> Monte Carlo kernel for kernel-tuning experiments:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr \
-//        [-DGKB_MC_HOIST_COEF=1 ...] -o /tmp/mcb tools/mc_microbench.cu
+//        -o /tmp/mcb tools/mc_microbench.cu
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -26,7 +26,7 @@ int main(int argc, char** argv) {
   md.R[0] = 0.5; mm.LR[0] = sqrt(0.5); mm.c = md.c = 1; mm.need_ctrl = md.need_ctrl = 1;
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   auto kern = mc_chisquare_kernel<N, M, VanillaTested<N, M>, true>;
-  const int cols = 2; const size_t smem = sizeof(double) * kWarps * kChunk * cols;
+  const int cols = 2; const size_t smem = sizeof(double) * (kIcdfSegments * kIcdfCoefs + kWarps * kChunk * cols);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
   if (MB_CTAS_PER_SM > 0 && per_sm > MB_CTAS_PER_SM) per_sm = MB_CTAS_PER_SM;
