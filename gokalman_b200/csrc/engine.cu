@@ -248,8 +248,7 @@ __global__ void fill_state_tile_kernel(double* vec, double* mat, const double* x
 static int create_tile(int n, int m, int c, int64_t n_filters, int device, const double* x0, int x0_per_filter,
                        const double* P0, const double* F, const double* G, const double* H, const double* Q,
                        const double* R, gkb_filter** out) {
-  if (!(G == nullptr || c == 0 || is_nil(G, n * c)))
-    return fail(GKB_ERR_UNSUPPORTED, "large-state filters (n=%d) do not take an input control yet", n);
+  if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
   int rc = check_device(device);
   if (rc) return rc;
   gkb_filter* f = new gkb_filter();
@@ -258,11 +257,15 @@ static int create_tile(int n, int m, int c, int64_t n_filters, int device, const
   f->tile = true;
   memset(&f->hm, 0, sizeof f->hm);
   f->hm.kind = GKB_VANILLA; f->hm.n = n; f->hm.m = m; f->hm.m_r = m;  // dimensions only: the arrays of hm are too small
-  std::vector<double> model((size_t)2 * n * n + 8 * n + 64, 0.0), A0((size_t)n * n);
+  f->hm.c = c;
+  f->hm.need_ctrl = !(G == nullptr || c == 0 || is_nil(G, n * c));  // vanilla.go:39
+  std::vector<double> model((size_t)2 * n * n + 8 * n + 64 + (size_t)n * GKB_MAX_C, 0.0), A0((size_t)n * n);
   double* mF = model.data();
   double* mQ = mF + n * n;
   double* mH = mQ + n * n;
   double* mR = mH + 8 * n;
+  double* mG = mR + 64;
+  if (G && c > 0) memcpy(mG, G, sizeof(double) * n * c);
   memcpy(mF, F, sizeof(double) * n * n);
   sym_from_upper(mQ, Q, n);
   memcpy(mH, H, sizeof(double) * m * n);
@@ -648,6 +651,13 @@ int gkb_update(gkb_filter* f, int steps, const double* y, int y_shared, const do
     tio.Q = tio.F + n * n;
     tio.H = tio.Q + n * n;
     tio.R = tio.H + 8 * n;
+    if (hm.need_ctrl && hm.c > 0) {  // u is required (checked above); G u once per step for the whole batch
+      const void* du = nullptr;
+      if ((rc = stage_in(f, f->in_u, u, sizeof(double) * (size_t)steps * hm.c, in_mem, &du))) return rc;
+      if ((rc = f->in_gu.ensure(sizeof(double) * (size_t)steps * n))) return rc;
+      launch_tile_gu(tio.R + 64, n, hm.c, static_cast<const double*>(du), steps, f->in_gu.as<double>(), f->stream);
+      tio.gu = f->in_gu.as<double>();
+    }
     OutPlan pl;
     if ((rc = plan_outputs(f, out, steps, m, pl))) return rc;
     tio.every_step = out ? out->every_step : 0;

@@ -84,6 +84,7 @@ struct TileIo {
   const double* Q;  // [n*n]
   const double* H;  // [8][n], rows >= m zero
   const double* R;  // [8][8], unit diagonal beyond m
+  const double* gu; // [steps][n]: G u per step (tile_gu_kernel), nullptr = no control term
   int every_step;
   int stagger_ns;
   double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain;  // [rows][nf][C]
@@ -149,6 +150,8 @@ int launch_batch_solve(int n, int m, const double* R_host, int64_t nf, int steps
 // Large-state Vanilla (kernels_tile.cu): n in {16, 24, 32}, m <= 8.
 int tile_shape_supported(int n, int m);
 int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s);
+// gu[k][i] = sum_j G[i][j] u[k][j] for a large-state handle (G [n][c] and u [steps][c] on the device).
+int launch_tile_gu(const double* G_dev, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s);
 // Upper bound on the CTAs launch_mc will use (rows of McIo::partial to allocate, zero-filled).
 int mc_max_grid(int device);
 // Picks a persistent grid (SM count x resident CTAs per SM, capped by the work) and launches.

@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : 384, 1) vanilla_tile_kernel(co
         }
 #pragma unroll
         for (int ti = 0; ti < TM; ++ti) {
-          const double s = quad_sum(xpart[ti]);
-          if (t == 0) xms[ti * 8 + g] = s;
+          const double s = quad_sum(xpart[ti]);  // + G u (vanilla.go:140-143), the same vector for every filter
+          if (t == 0) xms[ti * 8 + g] = io.gu != nullptr ? s + __ldg(io.gu + (int64_t)k * N + ti * 8 + g) : s;
         }
 #pragma unroll
         for (int ti = 0; ti < TM; ++ti)
@@ -470,6 +470,22 @@ static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
   if (const char* e = getenv("GKB_TILE_STAGGER_NS")) io2.stagger_ns = atoi(e);
   if (const char* e = getenv("GKB_TILE_WARPS")) { int w = atoi(e); if (w >= 1 && w <= warps) warps = w; }
   vanilla_tile_kernel<N><<<(unsigned)ctas, warps * 32, kShared + kPerWarp * warps, s>>>(io2);
+  return 0;
+}
+
+__global__ void tile_gu_kernel(const double* __restrict__ G, int n, int c, const double* __restrict__ u, int steps,
+                               double* __restrict__ gu) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= steps * n) return;
+  const int k = idx / n, i = idx % n;
+  double s = 0.0;
+  for (int j = 0; j < c; ++j) s = fma(G[i * c + j], u[(size_t)k * c + j], s);
+  gu[idx] = s;
+}
+
+int launch_tile_gu(const double* G_dev, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s) {
+  const int total = steps * n;
+  tile_gu_kernel<<<(total + 127) / 128, 128, 0, s>>>(G_dev, n, c, u_dev, steps, gu_dev);
   return 0;
 }
 

@@ -84,3 +84,27 @@ def test_tile_vanilla_shared_measurement_and_singular_s(oracle):
                            n_filters=nf)
     est2 = kf2.UpdateBatch(y, None, every_step=False, want=("state",))
     assert np.all(est2.status == -2)
+
+
+def test_tile_vanilla_with_input_control(oracle):
+    """x- = F x + G u (vanilla.go:138-143) on a large-state handle: the control term G u is formed once per step
+    for the whole batch; a missing control is the reference's dimension error."""
+    gk = _gpu()
+    n, m, c, nf, steps = 32, 8, 2, 12, 15
+    f = fx.synth_lti(n, m, seed=21)
+    rng = np.random.default_rng(210)
+    G = rng.standard_normal((n, c))
+    y = rng.standard_normal((steps, m, nf))
+    u = rng.standard_normal((steps, c))
+    kf, _ = gk.NewVanilla(f["x0"], f["P0"], f["F"], G, f["H"], gk.NewNoiseless(f["Q"], f["R"]), n_filters=nf)
+    assert kf._fm
+    est = kf.UpdateBatch(y, u, every_step=True, want=("state", "covar", "innov"))
+    for fi in (0, nf - 1):
+        o = oracle.NewVanilla(f["x0"], f["P0"], f["F"], G, f["H"], f["Q"], f["R"])
+        refs = [o.Update(y[k, :, fi], u[k]) for k in range(steps)]
+        for k in (0, steps - 1):
+            assert fx.scaled_err(np.asarray(est.State())[k][:, fi], refs[k].State()) <= TOL
+            assert fx.scaled_err(np.asarray(est.Innovation())[k][:, fi], refs[k].Innovation()) <= TOL
+            assert fx.scaled_err(np.asarray(est.Covariance())[k][:, :, fi], refs[k].Covariance()) <= TOL
+    with pytest.raises(gk.GkbError):
+        kf.UpdateBatch(y, None, every_step=False)
