@@ -436,7 +436,11 @@ int gkb_set_stream(gkb_filter* f, void* stream) {
 
 int gkb_set_state_transition(gkb_filter* f, const double* F) {
   if (!f || !F) return fail(GKB_ERR_ARG, "NULL argument");
-  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
+  if (f->tile) {  // the model of a large-state handle lives on the device: F [n*n] first
+    cudaSetDevice(f->device);
+    GKB_CUDA(cudaMemcpy(f->tile_model.p, F, sizeof(double) * f->hm.n * f->hm.n, cudaMemcpyHostToDevice));
+    return 0;
+  }
   cudaSetDevice(f->device);
   memcpy(f->hm.F, F, sizeof(double) * f->hm.n * f->hm.n);
   if (f->hm.kind == GKB_INFORMATION) {  // information.go:117-123
@@ -448,7 +452,15 @@ int gkb_set_state_transition(gkb_filter* f, const double* F) {
 
 int gkb_set_input_control(gkb_filter* f, int c, const double* G) {
   if (!f) return fail(GKB_ERR_ARG, "NULL handle");
-  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
+  if (f->tile) {
+    if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
+    cudaSetDevice(f->device);
+    const int n = f->hm.n;
+    f->hm.c = c;  // needCtrl is not re-evaluated (vanilla.go:99-101)
+    if (G && c > 0)
+      GKB_CUDA(cudaMemcpy(f->tile_model.as<double>() + 2 * n * n + 8 * n + 64, G, sizeof(double) * n * c, cudaMemcpyHostToDevice));
+    return 0;
+  }
   if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
   f->hm.c = c;  // needCtrl is not re-evaluated (vanilla.go:99-101)
   if (G && c > 0) memcpy(f->hm.G, G, sizeof(double) * f->hm.n * c);
@@ -457,7 +469,16 @@ int gkb_set_input_control(gkb_filter* f, int c, const double* G) {
 
 int gkb_set_measurement_matrix(gkb_filter* f, int m, const double* H) {
   if (!f || !H) return fail(GKB_ERR_ARG, "NULL argument");
-  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
+  if (f->tile) {
+    if (!tile_shape_supported(f->hm.n, m)) return fail(GKB_ERR_UNSUPPORTED, "no large-state kernel for n=%d m=%d", f->hm.n, m);
+    cudaSetDevice(f->device);
+    const int n = f->hm.n;
+    std::vector<double> Hp((size_t)8 * n, 0.0);  // rows >= m stay zero
+    memcpy(Hp.data(), H, sizeof(double) * m * n);
+    GKB_CUDA(cudaMemcpy(f->tile_model.as<double>() + 2 * n * n, Hp.data(), sizeof(double) * 8 * n, cudaMemcpyHostToDevice));
+    f->hm.m = m;
+    return 0;
+  }
   if (!gkb_shape_supported(f->hm.kind, f->hm.n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", f->hm.n, m);
   f->hm.m = m;
   memcpy(f->hm.H, H, sizeof(double) * m * f->hm.n);
@@ -466,7 +487,23 @@ int gkb_set_measurement_matrix(gkb_filter* f, int m, const double* H) {
 
 int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R) {
   if (!f || !R) return fail(GKB_ERR_ARG, "NULL argument");
-  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
+  if (f->tile) {
+    if (m_r < 1 || m_r > 8) return fail(GKB_ERR_UNSUPPORTED, "R dimension %d outside 1..8", m_r);
+    cudaSetDevice(f->device);
+    const int n = f->hm.n;
+    if (Q) {
+      std::vector<double> Qs((size_t)n * n);
+      sym_from_upper(Qs.data(), Q, n);
+      GKB_CUDA(cudaMemcpy(f->tile_model.as<double>() + n * n, Qs.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    }
+    double Rp[64];
+    for (int a = 0; a < 8; ++a)
+      for (int b = 0; b < 8; ++b)
+        Rp[a * 8 + b] = (a < m_r && b < m_r) ? (b >= a ? R[a * m_r + b] : R[b * m_r + a]) : (a == b ? 1.0 : 0.0);
+    GKB_CUDA(cudaMemcpy(f->tile_model.as<double>() + 2 * n * n + 8 * n, Rp, sizeof Rp, cudaMemcpyHostToDevice));
+    f->hm.m_r = m_r;
+    return 0;
+  }
   if (m_r < 1 || m_r > GKB_MAX_M) return fail(GKB_ERR_UNSUPPORTED, "R dimension %d outside 1..%d", m_r, GKB_MAX_M);
   if (f->hm.kind == GKB_SRIF) return fail(GKB_ERR_UNSUPPORTED, "noise not yet supported for SRIF (srif.go:77-79 panics)");
   cudaSetDevice(f->device);
@@ -487,7 +524,7 @@ int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R) {
 
 int gkb_set_replay_noise(gkb_filter* f, int steps, const double* w, const double* v, int mem) {
   if (!f) return fail(GKB_ERR_ARG, "NULL handle");
-  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) have a fixed model and Noiseless noise", f->hm.n);
+  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) carry Noiseless noise only (no replay samples)", f->hm.n);
   if (steps < 1) return fail(GKB_ERR_ARG, "steps must be >= 1");
   cudaSetDevice(f->device);
   const cudaMemcpyKind kind = mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;

@@ -108,3 +108,32 @@ def test_tile_vanilla_with_input_control(oracle):
             assert fx.scaled_err(np.asarray(est.Covariance())[k][:, :, fi], refs[k].Covariance()) <= TOL
     with pytest.raises(gk.GkbError):
         kf.UpdateBatch(y, None, every_step=False)
+
+
+def test_tile_vanilla_setters_between_calls(oracle):
+    """SetStateTransition / SetMeasurementMatrix / SetNoise on a large-state handle between two batched calls
+    (the jerkcar example's pattern, examples/jerkcar/main.go:141-159, at n = 16): m switches 8 -> 3 -> 8."""
+    gk = _gpu()
+    n, nf = 16, 10
+    fa, fb = fx.synth_lti(n, 8, seed=31), fx.synth_lti(n, 3, seed=32)
+    rng = np.random.default_rng(33)
+    ya, yb = rng.standard_normal((6, 8, nf)), rng.standard_normal((5, 3, nf))
+    kf, _ = gk.NewVanilla(fa["x0"], fa["P0"], fa["F"], None, fa["H"], gk.NewNoiseless(fa["Q"], fa["R"]), n_filters=nf)
+    o = oracle.NewVanilla(fa["x0"], fa["P0"], fa["F"], None, fa["H"], fa["Q"], fa["R"])
+    kf.UpdateBatch(ya, None, every_step=False, want=("state",))
+    for k in range(6):
+        ref = o.Update(ya[k, :, 4], None)
+    kf.SetStateTransition(fb["F"]); kf.SetMeasurementMatrix(fb["H"]); kf.SetNoise(gk.NewNoiseless(fb["Q"], fb["R"]))
+    o.SetStateTransition(fb["F"]); o.SetMeasurementMatrix(fb["H"]); o.SetNoise(fb["Q"], fb["R"])
+    est = kf.UpdateBatch(yb, None, every_step=False, want=("state", "covar", "gain"))
+    for k in range(5):
+        ref = o.Update(yb[k, :, 4], None)
+    assert fx.scaled_err(np.asarray(est.State())[:, 4], ref.State()) <= TOL
+    assert fx.scaled_err(np.asarray(est.Covariance())[:, :, 4], ref.Covariance()) <= TOL
+    assert fx.scaled_err(np.asarray(est.Gain())[:, :, 4], ref.Gain()) <= TOL
+    kf.SetMeasurementMatrix(fa["H"]); kf.SetNoise(gk.NewNoiseless(fa["Q"], fa["R"]))
+    o.SetMeasurementMatrix(fa["H"]); o.SetNoise(fa["Q"], fa["R"])
+    est = kf.UpdateBatch(ya[:2], None, every_step=False, want=("state",))
+    for k in range(2):
+        ref = o.Update(ya[k, :, 4], None)
+    assert fx.scaled_err(np.asarray(est.State())[:, 4], ref.State()) <= TOL
