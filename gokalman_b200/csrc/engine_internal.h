@@ -86,7 +86,6 @@ struct TileIo {
   const double* R;  // [8][8], unit diagonal beyond m
   const double* gu; // [steps][n]: G u per step (tile_gu_kernel), nullptr = no control term
   int every_step;
-  int stagger_ns;
   double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain;  // [rows][nf][C]
   int32_t* status;
 };

@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : 384, 1) vanilla_tile_kernel(co
   __syncthreads();
 
   const int m = io.m;
-  if (io.stagger_ns > 0 && warp >= 4) __nanosleep(io.stagger_ns);  // experiment: de-phase the two warps of an SMSP
   for (int64_t f = (int64_t)blockIdx.x * warps + warp; f < io.nf; f += (int64_t)gridDim.x * warps) {
     // ---- state in: x -> xs, P -> bufA (coalesced: a filter's matrix is contiguous)
     for (int idx = lane; idx < N; idx += 32) xs[idx] = io.x[f * N + idx];
@@ -465,11 +464,11 @@ static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
   if (warps < 1) return GKB_ERR_UNSUPPORTED;
   int64_t ctas = (io.nf + warps - 1) / warps;
   if (ctas > sms) ctas = sms;  // persistent: one CTA per SM, warps stride over the filters
-  const size_t smem = kShared + kPerWarp * warps;
-  TileIo io2 = io;
-  if (const char* e = getenv("GKB_TILE_STAGGER_NS")) io2.stagger_ns = atoi(e);
-  if (const char* e = getenv("GKB_TILE_WARPS")) { int w = atoi(e); if (w >= 1 && w <= warps) warps = w; }
-  vanilla_tile_kernel<N><<<(unsigned)ctas, warps * 32, kShared + kPerWarp * warps, s>>>(io2);
+  if (const char* e = getenv("GKB_TILE_WARPS")) {  // profiling knob: fewer warps per CTA (occupancy sweeps in DESIGN.md)
+    const int w = atoi(e);
+    if (w >= 1 && w <= warps) warps = w;
+  }
+  vanilla_tile_kernel<N><<<(unsigned)ctas, warps * 32, kShared + kPerWarp * warps, s>>>(io);
   return 0;
 }
 
