@@ -191,7 +191,7 @@ struct SqrtTested {
         double s = xt[i] - x[i];
 #pragma unroll
         for (int l = 0; l < i; ++l) s = fma(-S[i * N + l], z[l], s);
-        z[i] = s / S[i * N + i];
+        z[i] = s * rcp_nr(S[i * N + i]);
         q = fma(z[i], z[i], q);
       }
       nees = q;
