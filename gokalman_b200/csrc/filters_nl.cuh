@@ -194,7 +194,8 @@ GKB_DEV int hybrid_step(const NlModel<N, M>& md, double (&x)[N], double (&P)[N *
 // Inverse of an upper-triangular matrix held packed (row-major upper triangle): the same arithmetic as the
 // triangular shortcut of inverse_lu (dtrti2 + the ||A|| ||inv(A)|| <= 1e16 test), on 21 instead of 36 registers
 // at n = 6.  Returns 0 ok, 1 singular (a zero on the diagonal), 2 ill-conditioned.
-template <int N>
+// STRAIGHT: no early return on a zero diagonal (the arithmetic then runs on inf / NaN and only the return code counts).
+template <int N, bool STRAIGHT = false>
 GKB_DEV int inverse_upper_packed(double (&u)[N * (N + 1) / 2]) {
   double anorm = 0.0;
   bool singular = false;
@@ -206,7 +207,9 @@ GKB_DEV int inverse_upper_packed(double (&u)[N * (N + 1) / 2]) {
     anorm = fmax(anorm, s);
     singular = singular || (u[sym_idx<N>(i, i)] == 0.0);
   }
-  if (singular) return 1;
+  if constexpr (!STRAIGHT) {
+    if (singular) return 1;
+  }
 #pragma unroll
   for (int j = 0; j < N; ++j) {
     u[sym_idx<N>(j, j)] = rcp_nr(u[sym_idx<N>(j, j)]);
@@ -229,6 +232,7 @@ GKB_DEV int inverse_upper_packed(double (&u)[N * (N + 1) / 2]) {
     for (int j = i; j < N; ++j) s += fabs(u[sym_idx<N>(i, j)]);
     inorm = fmax(inorm, s);
   }
+  if (STRAIGHT && singular) return 1;
   return (anorm * inorm <= 1e16) ? 0 : 2;
 }
 
@@ -394,6 +398,168 @@ GKB_DEV int srif_step(const NlModel<N, M>& md, double (&b)[N], double (&R)[N * N
     finite = finite && isfinite(b[i]);
   }
   return finite ? 0 : GKB_ERR_NONFINITE;
+}
+
+// ---- the SRIF epoch for the usual case, as straight-line code ----------------------------------------------
+// Preconditions the caller has voted on: a measurement epoch, and R upper triangular in every lane of the warp
+// (HouseholderTransf leaves exact zeros below the diagonal), held packed in U.  The epoch runs the same arithmetic
+// as srif_step in the same order -- the triangular State(), the dgetf2 / dtrti2 / dgetri inverse of Phi, R-bar,
+// b-bar, the whitened Householder update -- but SPECULATES that no lane needs a row interchange in the LU of Phi
+// and that no lane hits an error; every branch and vote of the general routine collapses into one flag and one
+// vote at the end.  When the vote fails nothing has been committed: the caller runs srif_step on the same inputs,
+// which are still in the shared-memory stage.  `col` is this lane's column of the stage (Phi, Htilde, real,
+// computed rows, STRIDE doubles apart); Htilde and the observations are read only when they are needed, which
+// keeps them out of the registers during the two inverses.
+template <int N, int M, int STRIDE>
+GKB_DEV bool srif_step_tri(const NlModel<N, M>& md, double (&b)[N], double (&U)[N * (N + 1) / 2], const double* col,
+                           bool pad_lane) {
+  constexpr int SN = N * (N + 1) / 2, ROWS_PHI = N * N, ROWS_H = M * N;
+  bool ok = true;
+  // 117-118, 223-235: x-bar = Phi inv(R) b
+  double xbar[N];
+  double a[N * N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) a[i] = col[i * STRIDE];
+  if (pad_lane) {  // the TMA zero-fills the columns past the last filter: keep their Phi invertible
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i * N + i] = 1.0;
+  }
+  {
+    double Ui[SN], xs[N];
+#pragma unroll
+    for (int i = 0; i < SN; ++i) Ui[i] = U[i];
+    ok = ok && (inverse_upper_packed<N, true>(Ui) == 0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = Ui[sym_idx<N>(i, i)] * b[i];
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) s = fma(Ui[sym_idx<N>(i, j)], b[j], s);
+      xs[i] = s;
+    }
+    mulvec<N, N>(xbar, a, xs);
+  }
+  // 110-115: inv(Phi) as inverse_lu computes it when no interchange is needed (the pivot test only sets `ok`)
+  {
+    double anorm = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += fabs(a[i * N + j]);
+      anorm = fmax(anorm, s);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const double pmax = fabs(a[j * N + j]);
+      ok = ok && (pmax != 0.0);
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) ok = ok && !(fabs(a[i * N + j]) > pmax);
+      const double rinv = rcp_nr(a[j * N + j]);
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) a[i * N + j] *= rinv;
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) {
+        const double lij = a[i * N + j];
+#pragma unroll
+        for (int l = j + 1; l < N; ++l) a[i * N + l] = fma(-lij, a[j * N + l], a[i * N + l]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {  // dtrti2
+      a[j * N + j] = rcp_nr(a[j * N + j]);
+      const double ajj = -a[j * N + j];
+#pragma unroll
+      for (int i = 0; i < j; ++i) {
+        double t = a[i * N + i] * a[i * N + j];
+#pragma unroll
+        for (int l = i + 1; l < j; ++l) t = fma(a[i * N + l], a[l * N + j], t);
+        a[i * N + j] = t;
+      }
+#pragma unroll
+      for (int i = 0; i < j; ++i) a[i * N + j] *= ajj;
+    }
+#pragma unroll
+    for (int j = N - 2; j >= 0; --j) {  // dgetri
+      double work[N];
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) {
+        work[i] = a[i * N + j];
+        a[i * N + j] = 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double t = a[i * N + j + 1] * work[j + 1];
+#pragma unroll
+        for (int l = j + 2; l < N; ++l) t = fma(a[i * N + l], work[l], t);
+        a[i * N + j] -= t;
+      }
+    }
+    double inorm = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += fabs(a[i * N + j]);
+      inorm = fmax(inorm, s);
+    }
+    ok = ok && (anorm * inorm <= 1e16);
+  }
+  // R-bar = R inv(Phi) (R triangular), b-bar = R-bar x-bar, straight into the Householder work matrix
+  constexpr int COLS = N + 1;
+  double A[(N + M) * COLS];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = U[sym_idx<N>(i, i)] * a[i * N + j];
+#pragma unroll
+      for (int l = i + 1; l < N; ++l) s = fma(U[sym_idx<N>(i, l)], a[l * N + j], s);
+      A[i * COLS + j] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = A[i * COLS] * xbar[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) s = fma(A[i * COLS + j], xbar[j], s);
+    A[i * COLS + N] = s;
+  }
+  // 143-150: whitened observation rows (L = chol(R_meas), not its inverse: reference quirk)
+  {
+    double y[M];
+#pragma unroll
+    for (int c2 = 0; c2 < M; ++c2)
+      y[c2] = col[(ROWS_PHI + ROWS_H + c2) * STRIDE] - col[(ROWS_PHI + ROWS_H + M + c2) * STRIDE];
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+      double s = md.L[r * M] * y[0];
+#pragma unroll
+      for (int c2 = 1; c2 < M; ++c2) s = fma(md.L[r * M + c2], y[c2], s);
+      A[(N + r) * COLS + N] = s;
+    }
+    double Ht[M * N];
+#pragma unroll
+    for (int i = 0; i < M * N; ++i) Ht[i] = col[(ROWS_PHI + i) * STRIDE];
+#pragma unroll
+    for (int r = 0; r < M; ++r)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = md.L[r * M] * Ht[j];
+#pragma unroll
+        for (int c2 = 1; c2 < M; ++c2) s = fma(md.L[r * M + c2], Ht[c2 * N + j], s);
+        A[(N + r) * COLS + j] = s;
+      }
+  }
+  householder_transf<N, M>(A);
+#pragma unroll
+  for (int i = 0; i < N; ++i) ok = ok && isfinite(A[i * COLS + N]);
+  if (!__all_sync(0xffffffffu, ok)) return false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = i; j < N; ++j) U[sym_idx<N>(i, j)] = A[i * COLS + j];
+    b[i] = A[i * COLS + N];
+  }
+  return true;
 }
 
 }  // namespace gkb

@@ -266,7 +266,43 @@ __device__ __forceinline__ void nl_wtma_task(const NlModel<N, M>& md, const NlIo
     }
   }
   int status = 0;
+  bool try_fast = SRIF && N >= 3;  // the speculative SRIF epoch (srif_step_tri); given up for the task once it fails
   for (int k = k0; k < k1; ++k) {
+    if constexpr (SRIF && N >= 3) {
+      // Runs of measurement epochs with R upper triangular in every lane (all of them, once the first Householder
+      // update has happened) go through the straight-line epoch with R packed; anything else -- a Predict() epoch,
+      // a full R, a lane that needs a pivot interchange or hits an error -- falls through to the general epoch
+      // below with the stage untouched.
+      bool lower_zero = true;
+#pragma unroll
+      for (int i = 1; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) lower_zero = lower_zero && (P[i * N + j] == 0.0);
+      if (try_fast && __all_sync(0xffffffffu, lower_zero)) {
+        double U[N * (N + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = i; j < N; ++j) U[sym_idx<N>(i, j)] = P[i * N + j];
+        while (k < k1) {
+          if (io.flags && (io.flags[k] & GKB_F_MEAS) == 0) break;
+          tma::mbar_wait(&full[s], phase);
+          if (!srif_step_tri<N, M, 32>(md, x, U, ring + (size_t)s * ROWS * 32 + lane, !active)) {
+            try_fast = false;
+            break;
+          }
+          __syncwarp();  // every lane is done with the stage: re-arm it
+          if (lane == 0 && k + kWStages < k1) issue(k + kWStages, s);
+          if (++s == kWStages) { s = 0; phase ^= 1u; }
+          ++k;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = i; j < N; ++j) P[i * N + j] = U[sym_idx<N>(i, j)];
+        if (k >= k1) break;
+      }
+    }
     const unsigned fl = io.flags ? io.flags[k] : (unsigned)GKB_F_MEAS;
     const bool has_meas = (fl & GKB_F_MEAS) != 0, ekf = (fl & GKB_F_EKF) != 0;
     tma::mbar_wait(&full[s], phase);
