@@ -428,7 +428,8 @@ GKB_DEV bool srif_step_tri(const NlModel<N, M>& md, double (&b)[N], double (&U)[
     double Ui[SN], xs[N];
 #pragma unroll
     for (int i = 0; i < SN; ++i) Ui[i] = U[i];
-    ok = ok && (inverse_upper_packed<N, true>(Ui) == 0);
+    const int rc = inverse_upper_packed<N, true>(Ui);  // (no `ok && f()`: short-circuit evaluation would be a branch)
+    ok = ok && (rc == 0);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       double s = Ui[sym_idx<N>(i, i)] * b[i];
@@ -438,72 +439,9 @@ GKB_DEV bool srif_step_tri(const NlModel<N, M>& md, double (&b)[N], double (&U)[
     }
     mulvec<N, N>(xbar, a, xs);
   }
-  // 110-115: inv(Phi) as inverse_lu computes it when no interchange is needed (the pivot test only sets `ok`)
-  {
-    double anorm = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < N; ++j) s += fabs(a[i * N + j]);
-      anorm = fmax(anorm, s);
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const double pmax = fabs(a[j * N + j]);
-      ok = ok && (pmax != 0.0);
-#pragma unroll
-      for (int i = j + 1; i < N; ++i) ok = ok && !(fabs(a[i * N + j]) > pmax);
-      const double rinv = rcp_nr(a[j * N + j]);
-#pragma unroll
-      for (int i = j + 1; i < N; ++i) a[i * N + j] *= rinv;
-#pragma unroll
-      for (int i = j + 1; i < N; ++i) {
-        const double lij = a[i * N + j];
-#pragma unroll
-        for (int l = j + 1; l < N; ++l) a[i * N + l] = fma(-lij, a[j * N + l], a[i * N + l]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) {  // dtrti2
-      a[j * N + j] = rcp_nr(a[j * N + j]);
-      const double ajj = -a[j * N + j];
-#pragma unroll
-      for (int i = 0; i < j; ++i) {
-        double t = a[i * N + i] * a[i * N + j];
-#pragma unroll
-        for (int l = i + 1; l < j; ++l) t = fma(a[i * N + l], a[l * N + j], t);
-        a[i * N + j] = t;
-      }
-#pragma unroll
-      for (int i = 0; i < j; ++i) a[i * N + j] *= ajj;
-    }
-#pragma unroll
-    for (int j = N - 2; j >= 0; --j) {  // dgetri
-      double work[N];
-#pragma unroll
-      for (int i = j + 1; i < N; ++i) {
-        work[i] = a[i * N + j];
-        a[i * N + j] = 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double t = a[i * N + j + 1] * work[j + 1];
-#pragma unroll
-        for (int l = j + 2; l < N; ++l) t = fma(a[i * N + l], work[l], t);
-        a[i * N + j] -= t;
-      }
-    }
-    double inorm = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < N; ++j) s += fabs(a[i * N + j]);
-      inorm = fmax(inorm, s);
-    }
-    ok = ok && (anorm * inorm <= 1e16);
-  }
+  // 110-115: inv(Phi) as inverse_lu computes it when no interchange is needed
+  const bool inv_ok = inverse_lu_nopivot<N>(a);
+  ok = ok && inv_ok;
   // R-bar = R inv(Phi) (R triangular), b-bar = R-bar x-bar, straight into the Householder work matrix
   constexpr int COLS = N + 1;
   double A[(N + M) * COLS];

@@ -165,6 +165,14 @@ srif_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant_
 // iteration wrote, so every estimate is the final one mapped back through the STMs -- exactly what the
 // reference's in-place loop does.  One filter per thread; per (filter, step) the kernel reads one Phi and
 // writes one state + covariance: HBM-bound streaming, no reuse.
+// the rare path of smooth_all_kernel, kept out of line so that its predicated swaps do not cost the loop registers
+template <int N>
+__device__ __noinline__ int smooth_inverse_slow(double (&S)[N * N], const double* __restrict__ Phi, int phi_shared, int64_t k,
+                                                int64_t nf, int64_t tid) {
+  nl_load<N * N>(S, Phi, phi_shared, k, nf, tid);
+  return inverse_lu<N>(S);
+}
+
 template <int N>
 __global__ void __launch_bounds__(kThreads)
 smooth_all_kernel(int64_t nf, int steps, const double* __restrict__ Phi, int phi_shared, double* __restrict__ xs,
@@ -183,10 +191,25 @@ smooth_all_kernel(int64_t nf, int steps, const double* __restrict__ Phi, int phi
 #pragma unroll
       for (int j = i; j < N; ++j) P[sym_idx<N>(i, j)] = Pl[(int64_t)(i * N + j) * nf];
   }
+  // Phi of the next iteration is requested before the arithmetic of this one (the loads are the only long-latency
+  // operations of the loop), and the inverse first runs as straight-line code that speculates on "no row
+  // interchange" (inverse_lu_nopivot); a warp with a lane for which that fails redoes the epoch's inverse with
+  // the general routine on a re-read of Phi (an L2 hit).
+  double Snext[N * N];
+  if (steps >= 2) nl_load<N * N>(Snext, Phi, phi_shared, steps - 1, nf, tid);
   for (int k = steps - 2; k >= 0; --k) {
     double S[N * N];
-    nl_load<N * N>(S, Phi, phi_shared, k + 1, nf, tid);
-    if (inverse_lu<N>(S) != 0) {  // "provided STM is not invertible": the reference stops here
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) S[i] = Snext[i];
+    if (k >= 1) nl_load<N * N>(Snext, Phi, phi_shared, k, nf, tid);
+    bool ok = inverse_lu_nopivot<N>(S);
+    if (!__all_sync(__activemask(), ok)) {
+      double T[N * N];  // its address escapes to the out-of-line routine: a stack array, on this path only
+      ok = smooth_inverse_slow<N>(T, Phi, phi_shared, k + 1, nf, tid) == 0;
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) S[i] = T[i];
+    }
+    if (!ok) {  // "provided STM is not invertible": the reference stops here
       if (status != nullptr && status[tid] == 0) status[tid] = GKB_ERR_SINGULAR_PHI;
       return;
     }

@@ -261,6 +261,78 @@ GKB_DEV int inverse_lu(double (&a)[N * N]) {
   }
 }
 
+// ---- the same inverse, speculating that dgetf2 needs no row interchange ---------------------------------------
+// Straight-line code (no votes, no predicated swaps): the arithmetic of inverse_lu when every pivot is already on
+// the diagonal.  Returns false -- and a meaningless matrix -- when that does not hold for this thread (a larger
+// entry below a pivot, a zero pivot, cond_inf > 1e16): the caller then reruns inverse_lu on the original matrix.
+template <int N>
+GKB_DEV bool inverse_lu_nopivot(double (&a)[N * N]) {
+  bool ok = true;
+  double anorm = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s += fabs(a[i * N + j]);
+    anorm = fmax(anorm, s);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double pmax = fabs(a[j * N + j]);
+    ok = ok && (pmax != 0.0);
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) ok = ok && !(fabs(a[i * N + j]) > pmax);
+    const double rinv = rcp_nr(a[j * N + j]);
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) a[i * N + j] *= rinv;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      const double lij = a[i * N + j];
+#pragma unroll
+      for (int l = j + 1; l < N; ++l) a[i * N + l] = fma(-lij, a[j * N + l], a[i * N + l]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {  // dtrti2
+    a[j * N + j] = rcp_nr(a[j * N + j]);
+    const double ajj = -a[j * N + j];
+#pragma unroll
+    for (int i = 0; i < j; ++i) {
+      double t = a[i * N + i] * a[i * N + j];
+#pragma unroll
+      for (int l = i + 1; l < j; ++l) t = fma(a[i * N + l], a[l * N + j], t);
+      a[i * N + j] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < j; ++i) a[i * N + j] *= ajj;
+  }
+#pragma unroll
+  for (int j = N - 2; j >= 0; --j) {  // dgetri
+    double work[N];
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      work[i] = a[i * N + j];
+      a[i * N + j] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double t = a[i * N + j + 1] * work[j + 1];
+#pragma unroll
+      for (int l = j + 2; l < N; ++l) t = fma(a[i * N + l], work[l], t);
+      a[i * N + j] -= t;
+    }
+  }
+  double inorm = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s += fabs(a[i * N + j]);
+    inorm = fmax(inorm, s);
+  }
+  return ok && (anorm * inorm <= 1e16);
+}
+
 // ---- lower Cholesky factor from the upper triangle (dpotf2); returns false if not PD -------------
 template <int N>
 GKB_DEV bool chol_lower(double (&L)[N * N], const double (&A)[N * N]) {

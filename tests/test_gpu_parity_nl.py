@@ -223,6 +223,60 @@ def test_srif_tma_staged_path_matches_oracle(oracle, n, m, nf):
         assert fx.scaled_err(vec[:, f], rv) <= TOL and fx.scaled_err(mat[:, :, f], np.asarray(rm).reshape(n, n)) <= TOL
 
 
+@pytest.mark.parametrize("n,m,nf", [(6, 2, 70), (4, 1, 40)])
+def test_srif_tma_speculative_epoch_falls_back(oracle, n, m, nf):
+    """The production SRIF kernel runs measurement epochs speculatively without row interchanges in the LU of Phi
+    (srif_step_tri) and must hand the epoch to the general step, from the untouched shared-memory stage, when some
+    lane needs one.  Here a few filters get a Phi with two rows exchanged at some epochs (partial pivoting has to
+    swap), one filter gets a singular Phi (srif.go:112-114 error).  Bit-equal to the plain-load kernel, 1e-10 to the
+    oracle, and the singular filter reports the error without disturbing its neighbours."""
+    import os
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS, F_EKF, F_SNC
+    rng = np.random.default_rng(77 + n + nf)
+    steps = 29
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    swapped = {(3, 1), (3, 33), (11, 33), (12, 33), (20, nf - 1), (28, 0)}  # (epoch, filter)
+    for k, f in swapped:
+        Phi[k, [0, n - 1], :, f] = Phi[k, [n - 1, 0], :, f]
+    bad = 35
+    Phi[9, 1, :, bad] = Phi[9, 0, :, bad]  # two equal rows: exactly singular
+    P0 = np.diag(np.concatenate([np.full(n - n // 2, 50.0), np.full(n // 2, 1.0)]))
+    R = np.diag(np.full(m, 1e-2))
+    flags = np.array([F_MEAS if (k % 7 != 5) else 0 for k in range(steps)], dtype=np.uint8)
+
+    def run(path, chunks=None):
+        if path:
+            os.environ["GKB_NL_PATH"] = path
+        if chunks:
+            os.environ["GKB_NL_CHUNKS"] = chunks
+        try:
+            kf, _ = gk.NewSRIF(0.2 * np.ones(n), P0, m, False, gk.NewNoiseless(np.zeros((n, n)), R), n_filters=nf)
+            est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=False, want=("state", "covar"))
+            vec, mat = kf.GetState()
+        finally:
+            os.environ.pop("GKB_NL_PATH", None)
+            os.environ.pop("GKB_NL_CHUNKS", None)
+        return est, vec, mat
+    est, vec, mat = run(None)
+    good = np.array([f for f in range(nf) if f != bad])
+    assert np.all(est.status[good] == 0) and est.status[bad] != 0
+    for other in (run("plain"), run(None, "3")):
+        est2, vec2, mat2 = other
+        assert np.array_equal(est.status, est2.status)
+        assert np.array_equal(vec[:, good], vec2[:, good]) and np.array_equal(mat[:, :, good], mat2[:, :, good])
+        assert np.array_equal(np.asarray(est.Covariance())[..., good], np.asarray(est2.Covariance())[..., good])
+    for f in sorted(set([0, 1, 2, 32, 33, 34, 36, nf - 1])):
+        o = oracle.NewSRIF(0.2 * np.ones(n), P0, m, False, R)
+        ref = _oracle_run(o, flags, Phi, Ht, real, comp, None, f, F_MEAS, F_EKF, F_SNC)[-1]
+        xs = np.asarray(est.State()).reshape(n, nf)[:, f]
+        Pc = np.asarray(est.Covariance()).reshape(n, n, nf)[:, :, f]
+        assert fx.scaled_err(xs, ref.State()) <= TOL, (f, fx.scaled_err(xs, ref.State()))
+        assert fx.scaled_err(Pc, ref.Covariance()) <= TOL, (f, fx.scaled_err(Pc, ref.Covariance()))
+        rv, rm, _ = ref.raw()
+        assert fx.scaled_err(vec[:, f], rv) <= TOL and fx.scaled_err(mat[:, :, f], np.asarray(rm).reshape(n, n)) <= TOL
+
+
 @pytest.mark.parametrize("n,m", [(6, 2), (4, 2), (3, 1)])
 def test_srif_matches_oracle(oracle, n, m):
     """srif.go:101-160 with per-filter Phi / Htilde; State(), Covariance(), PredCovariance() read-outs."""
