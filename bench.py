@@ -373,8 +373,8 @@ def oracle_filter_rate(workload, nf, steps, threads):
     """CPU oracle over `nf` independent filters x `steps` (OpenMP over filters): hybrid6 / srif6 / vanilla32."""
     from oracle import gko
     gko.build()
-    if workload == "vanilla32":
-        f = fx.synth_lti(32, 8, seed=5)
+    if workload in ("vanilla32", "vanilla64"):
+        f = fx.synth_lti(int(workload[7:]), 8, seed=5)
         y = np.random.default_rng(4321).standard_normal((steps, nf, 8))
         t0 = time.perf_counter()
         gko.run_vanilla_batch(f["x0"], f["P0"], f["F"], f["H"], f["Q"], f["R"], y, threads=threads, want_covar=False)
@@ -395,6 +395,7 @@ FILTER_WORKLOADS = {
     "hybrid6": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
     "srif6": "srif6: 6-state SRIF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
     "vanilla32": "vanilla32: synthetic 32-state vanilla KF, m = 8 (BASELINE configs[4])",
+    "vanilla64": "vanilla64: synthetic 64-state vanilla KF, m = 8 (the n = 64 shape of BASELINE configs[4])",
 }
 
 
@@ -402,7 +403,7 @@ def filter_sample_size(workload, cores, target_s):
     steps = 200
     nf0 = cores * 8
     rate, _ = oracle_filter_rate(workload, nf0, steps, cores)  # calibration
-    per_filter_bytes = steps * (64 if workload == "vanilla32" else 416)
+    per_filter_bytes = steps * (64 if workload.startswith("vanilla") else 416)
     nf = int(min(rate * target_s / steps, 2e9 / per_filter_bytes))
     return max(cores, nf // cores * cores), steps
 
@@ -479,7 +480,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mc_jerk3", choices=["mc_jerk3", "mc_robot_info", "mc_robot_sqrt", "hybrid6", "srif6", "vanilla32"])
+    ap.add_argument("--workload", default="mc_jerk3", choices=["mc_jerk3", "mc_robot_info", "mc_robot_sqrt", "hybrid6", "srif6", "vanilla32", "vanilla64"])
     ap.add_argument("--trials", type=int, default=1000000, help="Monte Carlo trials (filters) per GPU")
     ap.add_argument("--filter-steps", type=int, default=1000, help="filter steps per trial")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -494,7 +495,7 @@ def main():
     if args.workload in ("hybrid6", "srif6"):
         from bench_hybrid import run_ours_hybrid
         line = run_ours_hybrid(args, rank, world, local)
-    elif args.workload == "vanilla32":
+    elif args.workload in ("vanilla32", "vanilla64"):
         from bench_tile import run_ours_tile
         line = run_ours_tile(args, rank, world, local)
     else:

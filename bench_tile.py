@@ -9,8 +9,16 @@ import time
 
 import numpy as np
 
-FLOPS_ALG = 331472.0          # vanilla(n=32, m=8), dense as executed by the reference
-FLOPS_MACHINE = 336 * 512.0   # 336 DMMA m8n8k4 per update (kernels_tile.cu header) + O(n m) vector work
+def flops_alg(n, m, c=0):
+    """vanilla(n, m, c), dense as executed by the reference (331 472 at n = 32, m = 8)."""
+    return float(8 * n**3 + 6 * n * n * m + 6 * n * m * m + 2 * m**3 + 5 * n * n + 6 * n * m + m * m + 2 * n * c + 4 * n + 2 * m)
+
+
+def dmma_per_update(n):
+    """DMMA m8n8k4 instructions per update (the stage table in the kernels_tile.cu header): 336 at n = 32, 2048 at n = 64."""
+    tm, ks = n // 8, n // 4
+    up = tm * (tm + 1) // 2
+    return tm * tm * ks + up * ks + tm * ks + ks + 2 * tm + 2 * up + tm * (ks + 2) + 2 * up
 
 
 def run_ours_tile(args, rank, world, local):
@@ -25,9 +33,11 @@ def run_ours_tile(args, rank, world, local):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nf = args.trials if args.trials != 1000000 else 100000
-    steps = args.filter_steps if args.filter_steps != 1000 else 200
-    n, m = int(os.environ.get('GKB_BENCH_TILE_N', '32')), 8
+    n, m = int(os.environ.get('GKB_BENCH_TILE_N', '64' if args.workload == "vanilla64" else '32')), 8
+    # n = 64: 3 warps (filters) per SM fit the shared memory -> 444 filters per wave; 26 640 = 60 waves
+    nf = args.trials if args.trials != 1000000 else (100000 if n <= 32 else 26640)
+    steps = args.filter_steps if args.filter_steps != 1000 else (200 if n <= 32 else 100)
+    FLOPS_ALG, FLOPS_MACHINE = flops_alg(n, m), dmma_per_update(n) * 512.0
     dev = torch.device("cuda", local)
     f = fx.synth_lti(n, m, seed=5)
     g = torch.Generator(device=dev)
@@ -104,16 +114,18 @@ def run_ours_tile(args, rank, world, local):
         "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "vanilla32: synthetic 32-state vanilla KF, m = 8, warp-per-filter FP64 DMMA (BASELINE configs[4])",
+        "config": {"workload": "vanilla%d: synthetic %d-state vanilla KF, m = 8, warp-per-filter FP64 DMMA (BASELINE configs[4]%s)"
+                               % (n, n, "" if n == 32 else "; the n = %d shape of the same kernel" % n),
                    "filters_per_gpu": nf, "epochs": steps, "n": n, "m": m, "failed_filters": bad,
                    "l2": "flushed between timed iterations (256 MiB memset)"},
         "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                     "traffic": measured_traffic("vanilla32", nf == 100000 and steps == 200),
-                     "kernel": "vanilla_tile_kernel<32>", "kernel_ms": main_ms, "flops_per_unit": FLOPS_ALG,
+                     "traffic": measured_traffic("vanilla32", n == 32 and nf == 100000 and steps == 200),
+                     "kernel": "vanilla_tile_kernel<%d>" % n, "kernel_ms": main_ms, "flops_per_unit": FLOPS_ALG,
                      "machine_tflops": ups * FLOPS_MACHINE / 1e12, "machine_flops_per_unit": FLOPS_MACHINE,
                      "peak_source": peak_src,
-                     "note": "achieved counts the reference's dense 331 k flop per update (SURVEY App. B); the kernel executes "
-                             "178 k (symmetry + restructured Joseph form), so frac can exceed 1; machine_tflops is the executed rate"},
+                     "note": "achieved counts the reference's dense %.0f flop per update (SURVEY App. B); the kernel executes "
+                             "%.0f (symmetry + restructured Joseph form), so frac can exceed 1; machine_tflops is the executed "
+                             "rate" % (FLOPS_ALG, FLOPS_MACHINE)},
         "e2e": {"value": e2e_value, "unit": "filter-updates/s", "h2d_bytes_per_step": 8 * steps * nf * m,
                 "d2h_bytes_per_step": 8 * nf * n + 4 * nf, "api": "Vanilla.UpdateBatch (host buffers)"},
         "gpu_launches": args.steps, "clocks": clocks, "wall_s": wall,

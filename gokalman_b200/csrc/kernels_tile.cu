@@ -1,4 +1,4 @@
-// kernels_tile.cu -- large-state Vanilla.Update (vanilla.go:128-220) for n = 16 / 24 / 32, m <= 8:
+// kernels_tile.cu -- large-state Vanilla.Update (vanilla.go:128-220) for n = 16 / 24 / 32 / 48 / 64, m <= 8:
 // one WARP per filter, covariance resident in shared memory for all the steps of a call, every dense
 // product on the FP64 tensor-core path (mma.sync m8n8k4 f64, "DMMA").
 //
@@ -140,9 +140,12 @@ __device__ __forceinline__ void sts2(double* p, const double (&v)[2]) {
 }  // namespace
 
 template <int N>
-__global__ void __launch_bounds__(N <= 16 ? 512 : 384, 1) vanilla_tile_kernel(const __grid_constant__ TileIo io) {
+__global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vanilla_tile_kernel(const __grid_constant__ TileIo io) {
   constexpr int TM = N / 8, KS = N / 4, LDB = (N + 15) / 16 * 16;
-  static_assert(N % 8 == 0 && N <= 32, "tile kernel shapes");
+  // The n x n products are accumulated TB row-tiles at a time: all of them for n <= 32 (the accumulators of the whole
+  // matrix fit the registers, and T2 stays there between the two Joseph stages), two for n = 48 / 64.
+  constexpr int TB = TM <= 4 ? TM : 2;
+  static_assert(N % 8 == 0 && N <= 64 && TM % TB == 0, "tile kernel shapes");
   extern __shared__ __align__(16) double smem[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Frag<LDB> fr(lane);
@@ -186,64 +189,68 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : 384, 1) vanilla_tile_kernel(co
       double xq[KS];
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) xq[ks] = xs[ks * 4 + t];
-      double c[TM * TM][2];
+      double c[TB * TM][2];
       // ---- T = F P (vanilla.go:149-150) and x- = F x (138-146; Noiseless, no control)
-      {
-        double xpart[TM];
 #pragma unroll
-        for (int i = 0; i < TM * TM; ++i) c[i][0] = c[i][1] = 0.0;
+      for (int t0 = 0; t0 < TM; t0 += TB) {
+        double xpart[TB];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) xpart[i] = 0.0;
+        for (int i = 0; i < TB * TM; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < TB; ++i) xpart[i] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          double a[TM], b[TM];
+          double a[TB], b[TM];
 #pragma unroll
-          for (int ti = 0; ti < TM; ++ti) a[ti] = sF[fr.a(ti, ks)];
+          for (int ti = 0; ti < TB; ++ti) a[ti] = sF[fr.a(t0 + ti, ks)];
 #pragma unroll
           for (int tj = 0; tj < TM; ++tj) b[tj] = bufA[fr.template p_b<TM>(ks, tj)];
 #pragma unroll
-          for (int ti = 0; ti < TM; ++ti) {
+          for (int ti = 0; ti < TB; ++ti) {
             xpart[ti] = fma(a[ti], xq[ks], xpart[ti]);
 #pragma unroll
             for (int tj = 0; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
           }
         }
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) {
+        for (int ti = 0; ti < TB; ++ti) {
           const double s = quad_sum(xpart[ti]);  // + G u (vanilla.go:140-143), the same vector for every filter
-          if (t == 0) xms[ti * 8 + g] = io.gu != nullptr ? s + __ldg(io.gu + (int64_t)k * N + ti * 8 + g) : s;
+          if (t == 0) xms[(t0 + ti) * 8 + g] = io.gu != nullptr ? s + __ldg(io.gu + (int64_t)k * N + (t0 + ti) * 8 + g) : s;
         }
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti)
+        for (int ti = 0; ti < TB; ++ti)
 #pragma unroll
-          for (int tj = 0; tj < TM; ++tj) sts2(bufB + fr.c(ti, tj), c[ti * TM + tj]);
+          for (int tj = 0; tj < TM; ++tj) sts2(bufB + fr.c(t0 + ti, tj), c[ti * TM + tj]);
       }
       __syncwarp();
       // ---- P- = T F^T + Q (150-152): upper tiles only (AsSymDense keeps the upper triangle, helper.go:65-84)
 #pragma unroll
-      for (int ti = 0; ti < TM; ++ti)
+      for (int t0 = 0; t0 < TM; t0 += TB) {
 #pragma unroll
-        for (int tj = ti; tj < TM; ++tj) {
-          const double2 q = __ldg(reinterpret_cast<const double2*>(io.Q + (ti * 8 + g) * N + tj * 8 + 2 * t));
-          c[ti * TM + tj][0] = q.x;
-          c[ti * TM + tj][1] = q.y;
+        for (int ti = 0; ti < TB; ++ti)
+#pragma unroll
+          for (int tj = t0 + ti; tj < TM; ++tj) {
+            const double2 q = __ldg(reinterpret_cast<const double2*>(io.Q + ((t0 + ti) * 8 + g) * N + tj * 8 + 2 * t));
+            c[ti * TM + tj][0] = q.x;
+            c[ti * TM + tj][1] = q.y;
+          }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          double a[TB], b[TM];
+#pragma unroll
+          for (int ti = 0; ti < TB; ++ti) a[ti] = bufB[fr.a(t0 + ti, ks)];
+#pragma unroll
+          for (int tj = t0; tj < TM; ++tj) b[tj] = sF[fr.a(tj, ks)];  // B[k][j] = F[j][k]
+#pragma unroll
+          for (int ti = 0; ti < TB; ++ti)
+#pragma unroll
+            for (int tj = t0 + ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
         }
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        double a[TM], b[TM];
+        for (int ti = 0; ti < TB; ++ti)
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) a[ti] = bufB[fr.a(ti, ks)];
-#pragma unroll
-        for (int tj = 0; tj < TM; ++tj) b[tj] = sF[fr.a(tj, ks)];  // B[k][j] = F[j][k]
-#pragma unroll
-        for (int ti = 0; ti < TM; ++ti)
-#pragma unroll
-          for (int tj = ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+          for (int tj = t0 + ti; tj < TM; ++tj) sts2(bufA + fr.template p_c<TM>(t0 + ti, tj), c[ti * TM + tj]);
       }
-#pragma unroll
-      for (int ti = 0; ti < TM; ++ti)
-#pragma unroll
-        for (int tj = ti; tj < TM; ++tj) sts2(bufA + fr.template p_c<TM>(ti, tj), c[ti * TM + tj]);
       __syncwarp();
       if (io.o_pred != nullptr && (io.every_step || k == io.steps - 1)) {
         double* dst = io.o_pred + ((io.every_step ? (int64_t)k * io.nf : 0) + f) * (N * N);
@@ -344,29 +351,32 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : 384, 1) vanilla_tile_kernel(co
       __syncwarp();
       // ---- Joseph form (197-205), restructured: T2 = P- - K PHt^T (symmetric: upper tiles)
 #pragma unroll
-      for (int ti = 0; ti < TM; ++ti)
+      for (int t0 = 0; t0 < TM; t0 += TB) {
 #pragma unroll
-        for (int tj = ti; tj < TM; ++tj) {
-          const double2 v = lds2(bufA + fr.template p_c<TM>(ti, tj));
-          c[ti * TM + tj][0] = v.x;
-          c[ti * TM + tj][1] = v.y;
+        for (int ti = 0; ti < TB; ++ti)
+#pragma unroll
+          for (int tj = t0 + ti; tj < TM; ++tj) {
+            const double2 v = lds2(bufA + fr.template p_c<TM>(t0 + ti, tj));
+            c[ti * TM + tj][0] = v.x;
+            c[ti * TM + tj][1] = v.y;
+          }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          double a[TB], b[TM];
+#pragma unroll
+          for (int ti = 0; ti < TB; ++ti) a[ti] = -sK[fr.a8(t0 + ti, ks)];
+#pragma unroll
+          for (int tj = t0; tj < TM; ++tj) b[tj] = sPH[fr.a8(tj, ks)];  // B[k][j] = PHt[j][k]
+#pragma unroll
+          for (int ti = 0; ti < TB; ++ti)
+#pragma unroll
+            for (int tj = t0 + ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
         }
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        double a[TM], b[TM];
+        for (int ti = 0; ti < TB; ++ti)
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) a[ti] = -sK[fr.a8(ti, ks)];
-#pragma unroll
-        for (int tj = 0; tj < TM; ++tj) b[tj] = sPH[fr.a8(tj, ks)];  // B[k][j] = PHt[j][k]
-#pragma unroll
-        for (int ti = 0; ti < TM; ++ti)
-#pragma unroll
-          for (int tj = ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+          for (int tj = t0 + ti; tj < TM; ++tj) sts2(bufB + fr.c(t0 + ti, tj), c[ti * TM + tj]);
       }
-#pragma unroll
-      for (int ti = 0; ti < TM; ++ti)
-#pragma unroll
-        for (int tj = ti; tj < TM; ++tj) sts2(bufB + fr.c(ti, tj), c[ti * TM + tj]);
       __syncwarp();
       // ---- V = T2 H^T - K R
       double vc[TM][2];
@@ -388,23 +398,36 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : 384, 1) vanilla_tile_kernel(co
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti) sts2(sPH + fr.c8(ti), vc[ti]);
       __syncwarp();
-      // ---- P+ = T2 - V K^T, upper tiles (c still holds T2)
+      // ---- P+ = T2 - V K^T, upper tiles (n <= 32: c still holds T2; larger n: T2 comes back from bufB)
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        double a[TM], b[TM];
+      for (int t0 = 0; t0 < TM; t0 += TB) {
+        if constexpr (TB < TM) {
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) a[ti] = -sPH[fr.a8(ti, ks)];
+          for (int ti = 0; ti < TB; ++ti)
 #pragma unroll
-        for (int tj = 0; tj < TM; ++tj) b[tj] = sK[fr.a8(tj, ks)];  // B[k][j] = K[j][k]
+            for (int tj = t0 + ti; tj < TM; ++tj) {
+              const double2 v = lds2(bufB + fr.c(t0 + ti, tj));
+              c[ti * TM + tj][0] = v.x;
+              c[ti * TM + tj][1] = v.y;
+            }
+        }
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti)
+        for (int ks = 0; ks < 2; ++ks) {
+          double a[TB], b[TM];
 #pragma unroll
-          for (int tj = ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+          for (int ti = 0; ti < TB; ++ti) a[ti] = -sPH[fr.a8(t0 + ti, ks)];
+#pragma unroll
+          for (int tj = t0; tj < TM; ++tj) b[tj] = sK[fr.a8(tj, ks)];  // B[k][j] = K[j][k]
+#pragma unroll
+          for (int ti = 0; ti < TB; ++ti)
+#pragma unroll
+            for (int tj = t0 + ti; tj < TM; ++tj) dmma(c[ti * TM + tj], a[ti], b[tj]);
+        }
+#pragma unroll
+        for (int ti = 0; ti < TB; ++ti)
+#pragma unroll
+          for (int tj = t0 + ti; tj < TM; ++tj) sts2(bufA + fr.template p_c<TM>(t0 + ti, tj), c[ti * TM + tj]);
       }
-#pragma unroll
-      for (int ti = 0; ti < TM; ++ti)
-#pragma unroll
-        for (int tj = ti; tj < TM; ++tj) sts2(bufA + fr.template p_c<TM>(ti, tj), c[ti * TM + tj]);
       __syncwarp();
       // ---- Estimate fields of this step
       if (io.every_step || k == io.steps - 1) {
@@ -459,7 +482,7 @@ static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
     cached_device = device;
   }
   int warps = (int)(((size_t)max_smem - kShared) / kPerWarp);
-  constexpr int kMaxWarps = N <= 16 ? 16 : 12;  // register budget: 64 K / (32 x registers per thread)
+  constexpr int kMaxWarps = N <= 16 ? 16 : (N <= 32 ? 12 : 4);  // register budget: 64 K / (32 x registers per thread)
   if (warps > kMaxWarps) warps = kMaxWarps;
   if (warps < 1) return GKB_ERR_UNSUPPORTED;
   int64_t ctas = (io.nf + warps - 1) / warps;
@@ -488,13 +511,15 @@ int launch_tile_gu(const double* G_dev, int n, int c, const double* u_dev, int s
   return 0;
 }
 
-int tile_shape_supported(int n, int m) { return (n == 16 || n == 24 || n == 32) && m >= 1 && m <= kMP; }
+int tile_shape_supported(int n, int m) { return (n == 16 || n == 24 || n == 32 || n == 48 || n == 64) && m >= 1 && m <= kMP; }
 
 int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s) {
   switch (n) {
     case 16: return launch_tile_shape<16>(io, device, s);
     case 24: return launch_tile_shape<24>(io, device, s);
     case 32: return launch_tile_shape<32>(io, device, s);
+    case 48: return launch_tile_shape<48>(io, device, s);
+    case 64: return launch_tile_shape<64>(io, device, s);
     default: return GKB_ERR_UNSUPPORTED;
   }
 }
