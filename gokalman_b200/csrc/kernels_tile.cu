@@ -139,47 +139,58 @@ __device__ __forceinline__ void sts2(double* p, const double (&v)[2]) {
 
 }  // namespace
 
+// Warps per filter: one up to n = 32; a PAIR for n = 48 / 64, where a filter's matrices take 40-60 KB of shared memory
+// and only three filters fit an SM -- one warp each would leave a scheduler idle.  The two warps of a pair split every
+// n x n product by row-tile blocks (tile_owner: balanced for the full and for the upper-triangular products), the
+// n x 8 products by row tiles, compute the 8 x 8 S and its inverse redundantly, and meet at a 64-thread named barrier
+// wherever the single-warp version has a __syncwarp.
 template <int N>
-__global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vanilla_tile_kernel(const __grid_constant__ TileIo io) {
-  constexpr int TM = N / 8, KS = N / 4, LDB = (N + 15) / 16 * 16;
+struct TileShape {
+  static constexpr int TM = N / 8, KS = N / 4, LDB = (N + 15) / 16 * 16;
+  static constexpr int PW = N <= 32 ? 1 : 2;
   // The n x n products are accumulated TB row-tiles at a time: all of them for n <= 32 (the accumulators of the whole
-  // matrix fit the registers, and T2 stays there between the two Joseph stages), two for n = 48 / 64.
-  constexpr int TB = TM <= 4 ? TM : 2;
+  // matrix fit the registers, and T2 stays there between the two Joseph stages), two (n = 64) or one (n = 48) otherwise.
+  static constexpr int TB = TM <= 4 ? TM : (TM % 4 == 0 ? 2 : 1);
+  static constexpr int kPacked = TM * (TM + 1) / 2 * 64;  // upper tiles of a symmetric n x n matrix
+  static constexpr int kPerFilter = kPacked + N * LDB + 2 * N * 8 + 2 * N + 2 * kMP;
   static_assert(N % 8 == 0 && N <= 64 && TM % TB == 0, "tile kernel shapes");
-  extern __shared__ __align__(16) double smem[];
-  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+};
+// owner of row-tile block b among the two warps of a pair: 0 1 1 0 0 1 1 0 ...
+__host__ __device__ constexpr int tile_owner(int b) { return ((b & 3) == 0 || (b & 3) == 3) ? 0 : 1; }
+
+template <int N, int HALF>
+__device__ __forceinline__ void tile_run(const TileIo& io, const double* sF, const double* sH, const double* sR,
+                                         double* fbase, int slot, int slots, int lane) {
+  using SH = TileShape<N>;
+  constexpr int TM = SH::TM, KS = SH::KS, LDB = SH::LDB, TB = SH::TB, PW = SH::PW, kPacked = SH::kPacked;
   const Frag<LDB> fr(lane);
   const int g = fr.g, t = fr.t;
-  // CTA-shared model (Q is only ever a C-fragment initialiser: read straight from global / L2 once per step)
-  constexpr int kPacked = TM * (TM + 1) / 2 * 64;  // upper tiles of a symmetric n x n matrix
-  double* sF = smem;                // [N][LDB]
-  double* sH = sF + N * LDB;        // [8][LDB]  rows >= m are zero
-  double* sR = sH + kMP * LDB;      // [8][8]    padded with a unit diagonal
-  double* wbase = sR + kMP * 8;
-  constexpr int kPerWarp = kPacked + N * LDB + 2 * N * 8 + 2 * N + 2 * kMP;
-  double* bufA = wbase + (size_t)warp * kPerWarp;  // P, then P-, then P+  (symmetric: packed upper tiles)
+  double* bufA = fbase;                            // P, then P-, then P+  (symmetric: packed upper tiles)
   double* bufB = bufA + kPacked;                   // T (full), then T2 (upper)
   double* sPH = bufB + N * LDB;                    // P- H^T, later V
   double* sK = sPH + N * 8;                        // gain
   double* xs = sK + N * 8;                         // posterior state
   double* xms = xs + N;                            // predicted state
   double* sinn = xms + N;                          // innovation (8), y-hat (8)
-
-  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) sF[idx_big<LDB>(idx / N, idx % N)] = io.F[idx];
-  for (int idx = threadIdx.x; idx < kMP * N; idx += blockDim.x) sH[idx_big<LDB>(idx / N, idx % N)] = io.H[idx];
-  for (int idx = threadIdx.x; idx < kMP * kMP; idx += blockDim.x) sR[idx_small(idx / kMP, idx % kMP)] = io.R[idx];
-  __syncthreads();
+  // the warps of this filter meet here (named barrier 1 + slot; barrier 0 is __syncthreads)
+  auto psync = [&]() {
+    if constexpr (PW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(32 * PW) : "memory");
+  };
+  auto mine = [](int row_tile) { return PW == 1 || tile_owner(row_tile / TB) == HALF; };
+  const int plane = lane + 32 * HALF;  // this thread among the filter's threads
+  constexpr int PT = 32 * PW;
 
   const int m = io.m;
-  for (int64_t f = (int64_t)blockIdx.x * warps + warp; f < io.nf; f += (int64_t)gridDim.x * warps) {
+  for (int64_t f = (int64_t)blockIdx.x * slots + slot; f < io.nf; f += (int64_t)gridDim.x * slots) {
     // ---- state in: x -> xs, P -> bufA (coalesced: a filter's matrix is contiguous)
-    for (int idx = lane; idx < N; idx += 32) xs[idx] = io.x[f * N + idx];
+    for (int idx = plane; idx < N; idx += PT) xs[idx] = io.x[f * N + idx];
     {
       const double* Pg = io.P + f * (int64_t)(N * N);
-      for (int idx = lane; idx < N * N; idx += 32)
+      for (int idx = plane; idx < N * N; idx += PT)
         if (idx / N <= idx % N) bufA[idx_packed<TM>(idx / N, idx % N)] = Pg[idx];
     }
-    __syncwarp();
+    psync();
     int status = 0;
     for (int k = 0; k < io.steps; ++k) {
       // this step's measurement: requested now, consumed after the gain (HBM latency hidden by the DMMA stages)
@@ -193,6 +204,7 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
       // ---- T = F P (vanilla.go:149-150) and x- = F x (138-146; Noiseless, no control)
 #pragma unroll
       for (int t0 = 0; t0 < TM; t0 += TB) {
+        if (!mine(t0)) continue;
         double xpart[TB];
 #pragma unroll
         for (int i = 0; i < TB * TM; ++i) c[i][0] = c[i][1] = 0.0;
@@ -222,10 +234,11 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
 #pragma unroll
           for (int tj = 0; tj < TM; ++tj) sts2(bufB + fr.c(t0 + ti, tj), c[ti * TM + tj]);
       }
-      __syncwarp();
+      psync();
       // ---- P- = T F^T + Q (150-152): upper tiles only (AsSymDense keeps the upper triangle, helper.go:65-84)
 #pragma unroll
       for (int t0 = 0; t0 < TM; t0 += TB) {
+        if (!mine(t0)) continue;
 #pragma unroll
         for (int ti = 0; ti < TB; ++ti)
 #pragma unroll
@@ -251,10 +264,10 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
 #pragma unroll
           for (int tj = t0 + ti; tj < TM; ++tj) sts2(bufA + fr.template p_c<TM>(t0 + ti, tj), c[ti * TM + tj]);
       }
-      __syncwarp();
+      psync();
       if (io.o_pred != nullptr && (io.every_step || k == io.steps - 1)) {
         double* dst = io.o_pred + ((io.every_step ? (int64_t)k * io.nf : 0) + f) * (N * N);
-        for (int idx = lane; idx < N * N; idx += 32) {
+        for (int idx = plane; idx < N * N; idx += PT) {
           const int r = idx / N, cc = idx % N;
           dst[idx] = bufA[idx_packed<TM>(r, cc)];
         }
@@ -275,14 +288,16 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
           hx = fma(b, xq[ks], hx);
           hm = fma(b, xmq[ks], hm);
 #pragma unroll
-          for (int ti = 0; ti < TM; ++ti) dmma(ph[ti], bufA[fr.template p_a<TM>(ti, ks)], b);
+          for (int ti = 0; ti < TM; ++ti)
+            if (mine(ti)) dmma(ph[ti], bufA[fr.template p_a<TM>(ti, ks)], b);
         }
         yhat = quad_sum(hx);
         hxm = quad_sum(hm);
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) sts2(sPH + fr.c8(ti), ph[ti]);
+        for (int ti = 0; ti < TM; ++ti)
+          if (mine(ti)) sts2(sPH + fr.c8(ti), ph[ti]);
       }
-      __syncwarp();
+      psync();
       // ---- S = H PHt + R (162-163), in the C-fragment layout: this lane holds S[g][2t], S[g][2t+1]
       double s[2];
       {
@@ -329,10 +344,12 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
         const double e1 = __shfl_sync(0xffffffffu, s[1], (lane & ~3) | (col >> 1));
         const double b = (col & 1) ? e1 : e0;
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) dmma(kc[ti], sPH[fr.a8(ti, ks)], b);
+        for (int ti = 0; ti < TM; ++ti)
+          if (mine(ti)) dmma(kc[ti], sPH[fr.a8(ti, ks)], b);
       }
 #pragma unroll
-      for (int ti = 0; ti < TM; ++ti) sts2(sK + fr.c8(ti), kc[ti]);
+      for (int ti = 0; ti < TM; ++ti)
+        if (mine(ti)) sts2(sK + fr.c8(ti), kc[ti]);
       // ---- innovation nu = y - H x- (182-184) and x+ = x- + K nu (186-195)
       const double innov = (g < m) ? (yv - hxm) : 0.0;  // valid in the t == 0 lane of quad g
       {
@@ -340,18 +357,20 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
         const double i1 = __shfl_sync(0xffffffffu, innov, (2 * t + 1) * 4);
 #pragma unroll
         for (int ti = 0; ti < TM; ++ti) {
+          if (!mine(ti)) continue;
           const double dx = quad_sum(fma(kc[ti][0], i0, kc[ti][1] * i1));
           if (t == 0) xs[ti * 8 + g] = xms[ti * 8 + g] + dx;
         }
       }
-      if (t == 0) {
+      if (HALF == 0 && t == 0) {
         sinn[g] = innov;
         sinn[kMP + g] = (g < m) ? yhat : 0.0;
       }
-      __syncwarp();
+      psync();
       // ---- Joseph form (197-205), restructured: T2 = P- - K PHt^T (symmetric: upper tiles)
 #pragma unroll
       for (int t0 = 0; t0 < TM; t0 += TB) {
+        if (!mine(t0)) continue;
 #pragma unroll
         for (int ti = 0; ti < TB; ++ti)
 #pragma unroll
@@ -377,7 +396,7 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
 #pragma unroll
           for (int tj = t0 + ti; tj < TM; ++tj) sts2(bufB + fr.c(t0 + ti, tj), c[ti * TM + tj]);
       }
-      __syncwarp();
+      psync();
       // ---- V = T2 H^T - K R
       double vc[TM][2];
 #pragma unroll
@@ -386,21 +405,25 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
       for (int ks = 0; ks < KS; ++ks) {
         const double b = sH[fr.a(0, ks)];
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) dmma(vc[ti], bufB[fr.sym_a(ti, ks)], b);
+        for (int ti = 0; ti < TM; ++ti)
+          if (mine(ti)) dmma(vc[ti], bufB[fr.sym_a(ti, ks)], b);
       }
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         const double b = sR[fr.b8(ks)];
 #pragma unroll
-        for (int ti = 0; ti < TM; ++ti) dmma(vc[ti], -sK[fr.a8(ti, ks)], b);
+        for (int ti = 0; ti < TM; ++ti)
+          if (mine(ti)) dmma(vc[ti], -sK[fr.a8(ti, ks)], b);
       }
-      // V takes the place of PHt (every lane is past its last read of sPH: the __syncwarp above)
+      // V takes the place of PHt (every thread of the filter is past its last read of sPH: the barrier above)
 #pragma unroll
-      for (int ti = 0; ti < TM; ++ti) sts2(sPH + fr.c8(ti), vc[ti]);
-      __syncwarp();
+      for (int ti = 0; ti < TM; ++ti)
+        if (mine(ti)) sts2(sPH + fr.c8(ti), vc[ti]);
+      psync();
       // ---- P+ = T2 - V K^T, upper tiles (n <= 32: c still holds T2; larger n: T2 comes back from bufB)
 #pragma unroll
       for (int t0 = 0; t0 < TM; t0 += TB) {
+        if (!mine(t0)) continue;
         if constexpr (TB < TM) {
 #pragma unroll
           for (int ti = 0; ti < TB; ++ti)
@@ -428,19 +451,19 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
 #pragma unroll
           for (int tj = t0 + ti; tj < TM; ++tj) sts2(bufA + fr.template p_c<TM>(t0 + ti, tj), c[ti * TM + tj]);
       }
-      __syncwarp();
+      psync();
       // ---- Estimate fields of this step
       if (io.every_step || k == io.steps - 1) {
         const int64_t row = (io.every_step ? (int64_t)k * io.nf : 0) + f;
         if (io.o_state != nullptr)
-          for (int idx = lane; idx < N; idx += 32) io.o_state[row * N + idx] = xs[idx];
-        if (io.o_innov != nullptr && lane < m) io.o_innov[row * m + lane] = sinn[lane];
-        if (io.o_meas != nullptr && lane < m) io.o_meas[row * m + lane] = sinn[kMP + lane];
+          for (int idx = plane; idx < N; idx += PT) io.o_state[row * N + idx] = xs[idx];
+        if (io.o_innov != nullptr && plane < m) io.o_innov[row * m + plane] = sinn[plane];
+        if (io.o_meas != nullptr && plane < m) io.o_meas[row * m + plane] = sinn[kMP + plane];
         if (io.o_gain != nullptr)
-          for (int idx = lane; idx < N * m; idx += 32) io.o_gain[row * (int64_t)(N * m) + idx] = sK[idx_small(idx / m, idx % m)];
+          for (int idx = plane; idx < N * m; idx += PT) io.o_gain[row * (int64_t)(N * m) + idx] = sK[idx_small(idx / m, idx % m)];
         if (io.o_covar != nullptr) {
           double* dst = io.o_covar + row * (int64_t)(N * N);
-          for (int idx = lane; idx < N * N; idx += 32) {
+          for (int idx = plane; idx < N * N; idx += PT) {
             const int r = idx / N, cc = idx % N;
             dst[idx] = bufA[idx_packed<TM>(r, cc)];
           }
@@ -455,25 +478,49 @@ __global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 128), 1) vani
       if (!finite) status = GKB_ERR_NONFINITE;
     }
     if (status == 0) {
-      for (int idx = lane; idx < N; idx += 32) io.x[f * N + idx] = xs[idx];
+      for (int idx = plane; idx < N; idx += PT) io.x[f * N + idx] = xs[idx];
       double* Pg = io.P + f * (int64_t)(N * N);
-      for (int idx = lane; idx < N * N; idx += 32) {
+      for (int idx = plane; idx < N * N; idx += PT) {
         const int r = idx / N, cc = idx % N;
         Pg[idx] = bufA[idx_packed<TM>(r, cc)];
       }
-    } else if (lane == 0 && io.status != nullptr && io.status[f] == 0) {
+    } else if (plane == 0 && io.status != nullptr && io.status[f] == 0) {
       io.status[f] = status;
     }
-    __syncwarp();
+    psync();
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(N <= 16 ? 512 : (N <= 32 ? 384 : 256), 1) vanilla_tile_kernel(const __grid_constant__ TileIo io) {
+  using SH = TileShape<N>;
+  constexpr int LDB = SH::LDB, PW = SH::PW;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slots = (int)(blockDim.x >> 5) / PW, slot = warp / PW;  // filters in flight in this CTA, this warp's
+  // CTA-shared model (Q is only ever a C-fragment initialiser: read straight from global / L2 once per step)
+  double* sF = smem;                // [N][LDB]
+  double* sH = sF + N * LDB;        // [8][LDB]  rows >= m are zero
+  double* sR = sH + kMP * LDB;      // [8][8]    padded with a unit diagonal
+  double* fbase = sR + kMP * 8 + (size_t)slot * SH::kPerFilter;
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) sF[idx_big<LDB>(idx / N, idx % N)] = io.F[idx];
+  for (int idx = threadIdx.x; idx < kMP * N; idx += blockDim.x) sH[idx_big<LDB>(idx / N, idx % N)] = io.H[idx];
+  for (int idx = threadIdx.x; idx < kMP * kMP; idx += blockDim.x) sR[idx_small(idx / kMP, idx % kMP)] = io.R[idx];
+  __syncthreads();
+  if constexpr (PW == 1) {
+    tile_run<N, 0>(io, sF, sH, sR, fbase, slot, slots, lane);
+  } else {
+    if ((warp & 1) == 0) tile_run<N, 0>(io, sF, sH, sR, fbase, slot, slots, lane);
+    else tile_run<N, 1>(io, sF, sH, sR, fbase, slot, slots, lane);
   }
 }
 
 template <int N>
 static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
-  constexpr int LDB = (N + 15) / 16 * 16;
-  constexpr int TM = N / 8;
+  using SH = TileShape<N>;
+  constexpr int LDB = SH::LDB, PW = SH::PW;
   constexpr size_t kShared = sizeof(double) * (N * LDB + kMP * LDB + kMP * 8);
-  constexpr size_t kPerWarp = sizeof(double) * (TM * (TM + 1) / 2 * 64 + N * LDB + 2 * N * 8 + 2 * N + 2 * kMP);
+  constexpr size_t kPerWarp = sizeof(double) * SH::kPerFilter;  // per filter in flight (one warp, or a pair for n > 32)
   static thread_local int cached_device = -1, sms = 148, max_smem = 227 * 1024;
   if (cached_device != device) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -482,7 +529,7 @@ static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
     cached_device = device;
   }
   int warps = (int)(((size_t)max_smem - kShared) / kPerWarp);
-  constexpr int kMaxWarps = N <= 16 ? 16 : (N <= 32 ? 12 : 4);  // register budget: 64 K / (32 x registers per thread)
+  constexpr int kMaxWarps = N <= 16 ? 16 : (N <= 32 ? 12 : 4);  // filters in flight; register budget: 64 K / (32 x registers per thread)
   if (warps > kMaxWarps) warps = kMaxWarps;
   if (warps < 1) return GKB_ERR_UNSUPPORTED;
   int64_t ctas = (io.nf + warps - 1) / warps;
@@ -491,7 +538,7 @@ static int launch_tile_shape(const TileIo& io, int device, cudaStream_t s) {
     const int w = atoi(e);
     if (w >= 1 && w <= warps) warps = w;
   }
-  vanilla_tile_kernel<N><<<(unsigned)ctas, warps * 32, kShared + kPerWarp * warps, s>>>(io);
+  vanilla_tile_kernel<N><<<(unsigned)ctas, warps * PW * 32, kShared + kPerWarp * warps, s>>>(io);
   return 0;
 }
 
