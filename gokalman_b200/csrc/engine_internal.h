@@ -11,6 +11,10 @@ namespace gkb {
 #define GKB_FOR_EACH_SHAPE(X) \
   X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 3) X(5, 1) X(5, 2) X(6, 1) X(6, 2) X(6, 3)
 
+// LDKF kinds (Vanilla / pure predictor / Information / Square root) also get n = 7 and 8 (the north star's "n <= 8"): slower
+// (the 8 x 8 intermediates no longer fit the registers: ptxas reports local memory) but correct, same parity bar.
+#define GKB_FOR_EACH_LTI_SHAPE(X) GKB_FOR_EACH_SHAPE(X) X(7, 1) X(7, 2) X(7, 3) X(8, 1) X(8, 2) X(8, 3)
+
 constexpr int kThreads = 128;  // threads per CTA for the register kernels
 
 // Host copy of everything a filter handle knows about its model (row-major, full matrices).

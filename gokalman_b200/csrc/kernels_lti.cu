@@ -295,7 +295,7 @@ static int launch_shape(const HostModel& hm, const LtiIo& io, cudaStream_t s) {
 int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
   if (hm.n == NN && hm.m == MM) return launch_shape<NN, MM>(hm, io, s);
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
 }

@@ -135,7 +135,7 @@ int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStrea
   int rc = GKB_ERR_UNSUPPORTED;
 #define GKB_CASE(NN, MM) \
   if (n == NN && m == MM) rc = run_setup<NN, MM>(dev, s);
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)
 #undef GKB_CASE
   if (rc == 0) {
     cudaMemcpyAsync(&h, dev, sizeof(SetupData), cudaMemcpyDeviceToHost, s);
