@@ -192,7 +192,11 @@ int gkb_shape_supported(int kind, int n, int m) {
   if (kind == GKB_VANILLA && tile_shape_supported(n, m)) return 1;
 #define GKB_CASE(NN, MM) \
   if (n == NN && m == MM) return 1;
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  if (kind == GKB_HYBRID || kind == GKB_SRIF) {
+    GKB_FOR_EACH_SHAPE(GKB_CASE)
+  } else {  // the LDKF kinds also have n = 7, 8 (batched Update kernels; the Monte Carlo harness stops at n = 6)
+    GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)
+  }
 #undef GKB_CASE
   return 0;
 }
@@ -959,7 +963,8 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   if (cfg->kind != GKB_VANILLA && cfg->kind != GKB_INFORMATION && cfg->kind != GKB_SQRT)
     return fail(GKB_ERR_ARG, "tested filter kind %d is not an LDKF kind", cfg->kind);
   const int n = cfg->n, m = cfg->m, c = cfg->c, steps = cfg->steps;
-  if (!gkb_shape_supported(cfg->kind, n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled kernel for n=%d m=%d", n, m);
+  if (n > 6 || !gkb_shape_supported(cfg->kind, n, m))  // the fused Monte Carlo kernels are compiled for n <= 6
+    return fail(GKB_ERR_UNSUPPORTED, "no compiled Monte Carlo kernel for n=%d m=%d", n, m);
   if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
   if (cfg->trials < 1 || steps < 1) return fail(GKB_ERR_ARG, "trials and steps must be >= 1");
   if (!cfg->F || !cfg->H || !cfg->Q || !cfg->R || !cfg->x0_truth || !cfg->x0_filter || !cfg->P0)

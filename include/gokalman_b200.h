@@ -66,7 +66,8 @@ typedef enum gkb_mem { GKB_HOST = 0, GKB_DEVICE = 1 } gkb_mem;
 const char* gkb_version(void);
 const char* gkb_last_error(void);
 int gkb_device_count(void);
-/* 1 if (kind, n, m) has a compiled kernel. */
+/* 1 if a filter of (kind, n, m) can be created: LDKF kinds n <= 8, m <= 3 (n = 5: m <= 2) plus the large-state Vanilla
+ * shapes; HYBRID / SRIF n <= 6.  (gkb_mc_chisquare has kernels for n <= 6 and reports GKB_ERR_UNSUPPORTED above.) */
 int gkb_shape_supported(int kind, int n, int m);
 
 /* ---- construction: replaces NewVanilla / NewPurePredictorVanilla / NewInformation /

@@ -105,7 +105,7 @@ def _compare(est_gpu, ests_ref, fields, tag):
             assert err <= TOL, (tag, fld, f, err)
 
 
-SHAPES = [(2, 1, 1), (3, 1, 1), (4, 2, 1), (6, 2, 0), (5, 2, 2), (3, 3, 1), (1, 1, 0)]
+SHAPES = [(2, 1, 1), (3, 1, 1), (4, 2, 1), (6, 2, 0), (5, 2, 2), (3, 3, 1), (1, 1, 0), (8, 3, 2), (7, 2, 1), (8, 1, 0)]
 
 
 @pytest.mark.parametrize("n,m,c", SHAPES)
