@@ -119,7 +119,7 @@ def run_ours_tile(args, rank, world, local):
                    "filters_per_gpu": nf, "epochs": steps, "n": n, "m": m, "failed_filters": bad,
                    "l2": "flushed between timed iterations (256 MiB memset)"},
         "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                     "traffic": measured_traffic("vanilla32", n == 32 and nf == 100000 and steps == 200),
+                     "traffic": measured_traffic("vanilla%d" % n, (n == 32 and nf == 100000 and steps == 200) or (n == 64 and nf == 26640 and steps == 100)),
                      "kernel": "vanilla_tile_kernel<%d>" % n, "kernel_ms": main_ms, "flops_per_unit": FLOPS_ALG,
                      "machine_tflops": ups * FLOPS_MACHINE / 1e12, "machine_flops_per_unit": FLOPS_MACHINE,
                      "peak_source": peak_src,
