@@ -248,7 +248,7 @@ __global__ void fill_state_tile_kernel(double* vec, double* mat, const double* x
   }
 }
 
-// NewVanilla for n in {16, 24, 32, 48, 64}, m <= 8: the warp-per-filter tensor-core path (kernels_tile.cu).
+// NewVanilla for n in {16, 24, ... 64}, m <= 8: the warp-per-filter tensor-core path (kernels_tile.cu).
 static int create_tile(int n, int m, int c, int64_t n_filters, int device, const double* x0, int x0_per_filter,
                        const double* P0, const double* F, const double* G, const double* H, const double* Q,
                        const double* R, gkb_filter** out) {

@@ -1,4 +1,4 @@
-// kernels_tile.cu -- large-state Vanilla.Update (vanilla.go:128-220) for n = 16 / 24 / 32 / 48 / 64, m <= 8:
+// kernels_tile.cu -- large-state Vanilla.Update (vanilla.go:128-220) for n = 16, 24, ... 64 (multiples of 8), m <= 8:
 // one WARP per filter, covariance resident in shared memory for all the steps of a call, every dense
 // product on the FP64 tensor-core path (mma.sync m8n8k4 f64, "DMMA").
 //
@@ -588,14 +588,16 @@ int launch_tile_gu(const double* G_dev, int n, int c, const double* u_dev, int s
   return 0;
 }
 
-int tile_shape_supported(int n, int m) { return (n == 16 || n == 24 || n == 32 || n == 48 || n == 64) && m >= 1 && m <= kMP; }
+int tile_shape_supported(int n, int m) { return n >= 16 && n <= 64 && n % 8 == 0 && m >= 1 && m <= kMP; }
 
 int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s) {
   switch (n) {
     case 16: return launch_tile_shape<16>(io, device, s);
     case 24: return launch_tile_shape<24>(io, device, s);
     case 32: return launch_tile_shape<32>(io, device, s);
+    case 40: return launch_tile_shape<40>(io, device, s);
     case 48: return launch_tile_shape<48>(io, device, s);
+    case 56: return launch_tile_shape<56>(io, device, s);
     case 64: return launch_tile_shape<64>(io, device, s);
     default: return GKB_ERR_UNSUPPORTED;
   }

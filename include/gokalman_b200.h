@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define GKB_MAX_N 8  /* one-filter-per-thread register kernels */
-#define GKB_TILE_MAX_N 64 /* large-state (warp-per-filter, FP64 tensor-core) Vanilla: n in {16, 24, 32, 48, 64}, m <= 8 */
+#define GKB_TILE_MAX_N 64 /* large-state (warp-per-filter, FP64 tensor-core) Vanilla: n in {16, 24, 32, 40, 48, 56, 64}, m <= 8 */
 #define GKB_TILE_MAX_M 8
 #define GKB_MAX_M 3
 #define GKB_MAX_C 4
@@ -75,7 +75,7 @@ int gkb_shape_supported(int kind, int n, int m);
  *      x0_per_filter != 0, [n][n_filters].  P0 is n x n (for GKB_INFORMATION x0/P0 are the
  *      information state i0 and matrix I0).  G may be NULL (c = 0).  Arrays are host pointers and
  *      are copied.  Only the upper triangle of P0, Q, R is read (mat64.SymDense semantics). */
-/* Large-state handles: GKB_VANILLA with n in {16, 24, 32, 48, 64} and m <= 8 (Noiseless noise: no replay samples)
+/* Large-state handles: GKB_VANILLA with n in {16, 24, 32, 40, 48, 56, 64} and m <= 8 (Noiseless noise: no replay samples)
  * runs one WARP per filter on the FP64 tensor-core path with the covariance resident in
  * shared memory.  Such a handle uses FILTER-MAJOR arrays everywhere -- x0 (per filter) [N][n],
  * state [N][n], covar [N][n*n], y [steps][N][m], outputs [steps][N][C] -- so that one filter's

@@ -43,10 +43,10 @@ def test_shape_table_and_version():
     for n, m in ((2, 1), (3, 1), (4, 1), (4, 2), (6, 2)):  # every BASELINE config shape of the register kernels
         for kind in range(6):
             assert lib.gkb_shape_supported(kind, n, m) == 1
-    for n in (16, 24, 32, 48, 64):  # large-state Vanilla (kernels_tile.cu); no other kind, no other n
+    for n in (16, 24, 32, 40, 48, 56, 64):  # large-state Vanilla (kernels_tile.cu); no other kind, no other n
         assert lib.gkb_shape_supported(0, n, 8) == 1 and lib.gkb_shape_supported(0, n, 1) == 1
         assert lib.gkb_shape_supported(2, n, 8) == 0 and lib.gkb_shape_supported(0, n, 9) == 0
-    assert lib.gkb_shape_supported(0, 40, 8) == 0 and lib.gkb_shape_supported(0, 128, 8) == 0
+    assert lib.gkb_shape_supported(0, 44, 8) == 0 and lib.gkb_shape_supported(0, 72, 8) == 0 and lib.gkb_shape_supported(0, 128, 8) == 0
     for kind in range(4):  # the LDKF kinds reach the north star's n <= 8; the NLDKF kinds stop at n = 6
         assert lib.gkb_shape_supported(kind, 8, 3) == 1 and lib.gkb_shape_supported(kind, 7, 1) == 1
         assert lib.gkb_shape_supported(kind, 9, 1) == 0

@@ -22,7 +22,7 @@ def _oracle_run(oracle, f, ys, x0=None):
     return [kf.Update(y, None) for y in ys]
 
 
-@pytest.mark.parametrize("n,m,nf", [(32, 8, 19), (32, 3, 9), (16, 8, 40), (16, 1, 5), (24, 5, 11), (64, 8, 7), (64, 2, 4), (48, 5, 5)])
+@pytest.mark.parametrize("n,m,nf", [(32, 8, 19), (32, 3, 9), (16, 8, 40), (16, 1, 5), (24, 5, 11), (64, 8, 7), (64, 2, 4), (48, 5, 5), (40, 8, 6), (56, 3, 5)])
 def test_tile_vanilla_every_step_matches_oracle(oracle, n, m, nf):
     gk = _gpu()
     f = fx.synth_lti(n, m, seed=100 + n + m)
