@@ -15,7 +15,7 @@ struct InfoOut {
 template <int N>
 GKB_DEV bool info_covariance(double (&Pc)[N * N], const double (&I)[N * (N + 1) / 2]) {
   sym_expand<N>(Pc, I);
-  int ierr = inverse_lu<N>(Pc);
+  int ierr = inverse_lu_fast<N>(Pc);
   if (ierr != 0) {
 #pragma unroll
     for (int i = 0; i < N * N; ++i) Pc[i] = 0.0;
@@ -80,7 +80,7 @@ GKB_DEV int info_step(const InfoModel<N, M>& md, double (&iv)[N], double (&I)[N 
     double T[N * N];
 #pragma unroll
     for (int i = 0; i < N * N; ++i) T[i] = z[i] + md.Qinv[i];
-    (void)inverse_lu<N>(T);
+    (void)inverse_lu_fast<N>(T);
     mul<N, N, N>(Mm, z, T);
 #pragma unroll
     for (int i = 0; i < N * N; ++i) Mm[i] = -Mm[i];

@@ -149,7 +149,7 @@ struct InfoTested {
       mulvec<N, N>(xs, Pc, iv);
 #pragma unroll
       for (int i = 0; i < N; ++i) e[i] = xt[i] - xs[i];
-      (void)inverse_lu<N>(Pc);  // PInv.Inverse(est.Covariance()), error ignored
+      (void)inverse_lu_fast<N>(Pc);  // PInv.Inverse(est.Covariance()), error ignored
       mulvec<N, N>(t, Pc, e);
       double q = 0.0;
 #pragma unroll

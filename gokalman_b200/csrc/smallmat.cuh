@@ -333,6 +333,28 @@ GKB_DEV bool inverse_lu_nopivot(double (&a)[N * N]) {
   return ok && (anorm * inorm <= 1e16);
 }
 
+// inverse_lu with the speculation in front: the straight-line no-interchange inverse on a copy, one vote, and the
+// general routine only when some lane of the warp needs an interchange or reports an error.  Same bits, same return
+// codes.  For call sites whose matrices are (near) symmetric positive definite -- information matrices, covariances --
+// where partial pivoting practically never swaps.
+template <int N>
+GKB_DEV int inverse_lu_fast(double (&a)[N * N]) {
+  if constexpr (N == 1) {
+    return inverse_lu<N>(a);
+  } else {
+    double t[N * N];
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) t[i] = a[i];
+    const bool ok = inverse_lu_nopivot<N>(t);
+    if (__all_sync(__activemask(), ok)) {
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) a[i] = t[i];
+      return 0;
+    }
+    return inverse_lu<N>(a);
+  }
+}
+
 // ---- lower Cholesky factor from the upper triangle (dpotf2); returns false if not PD -------------
 template <int N>
 GKB_DEV bool chol_lower(double (&L)[N * N], const double (&A)[N * N]) {
