@@ -292,7 +292,7 @@ int launch_householder(int n, int m, int64_t count, double* A, cudaStream_t s) {
 // Solve(): P0 = inv(Lambda) by LU (upper triangle kept, AsSymDense), xHat0 = P0 N.  The full dense Lambda is
 // accumulated in the reference's operation order.  Streams H [steps][m*n][N], observations [steps][m][N].
 template <int N, int M>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 batch_solve_kernel(const __grid_constant__ NlModel<N, M> md, int64_t nf, int steps, const double* __restrict__ H,
                    int h_shared, const double* __restrict__ real_obs, const double* __restrict__ computed_obs,
                    double* __restrict__ xhat0, double* __restrict__ P0, int32_t* __restrict__ status) {
@@ -303,11 +303,24 @@ batch_solve_kernel(const __grid_constant__ NlModel<N, M> md, int64_t nf, int ste
   for (int i = 0; i < N * N; ++i) Lam[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < N; ++i) Nv[i] = 0.0;
+  // The loop is a pure stream (128 B per measurement at n = 6, m = 2): the next measurement is requested before the
+  // arithmetic of the current one, and the register budget is capped (3 CTAs per SM) so that enough loads are in
+  // flight -- the one LU inverse after the loop is what would otherwise claim 250 registers.
+  double Hn[M * N], rn[M], cn[M];
+  nl_load<M * N>(Hn, H, h_shared, 0, nf, tid);
+  nl_load<M>(rn, real_obs, 0, 0, nf, tid);
+  nl_load<M>(cn, computed_obs, 0, 0, nf, tid);
   for (int k = 0; k < steps; ++k) {
     double Hk[M * N], ro[M], co[M];
-    nl_load<M * N>(Hk, H, h_shared, k, nf, tid);
-    nl_load<M>(ro, real_obs, 0, k, nf, tid);
-    nl_load<M>(co, computed_obs, 0, k, nf, tid);
+#pragma unroll
+    for (int i = 0; i < M * N; ++i) Hk[i] = Hn[i];
+#pragma unroll
+    for (int a = 0; a < M; ++a) { ro[a] = rn[a]; co[a] = cn[a]; }
+    if (k + 1 < steps) {
+      nl_load<M * N>(Hn, H, h_shared, k + 1, nf, tid);
+      nl_load<M>(rn, real_obs, 0, k + 1, nf, tid);
+      nl_load<M>(cn, computed_obs, 0, k + 1, nf, tid);
+    }
     double HtR[N * M];
 #pragma unroll
     for (int i = 0; i < N; ++i)
