@@ -1,6 +1,8 @@
 // kernels_tile.cu -- large-state Vanilla.Update (vanilla.go:128-220) for n = 16, 24, ... 64 (multiples of 8), m <= 8:
-// one WARP per filter, covariance resident in shared memory for all the steps of a call, every dense
-// product on the FP64 tensor-core path (mma.sync m8n8k4 f64, "DMMA").
+// one WARP per filter up to n = 32, a warp PAIR per filter above (TileShape, tile_run), covariance resident in
+// shared memory for all the steps of a call, every dense product on the FP64 tensor-core path (mma.sync m8n8k4
+// f64, "DMMA").  The stage table below is written for n = 32; the DMMA counts scale as in bench_tile.py:
+// dmma_per_update (2048 at n = 64).
 //
 // BASELINE configs[4]: synthetic 32-state filters with a shared LTI model and a
 // per-filter measurement stream.  Per update the reference does 8n^3 + ... = 331 k flop at n = 32, m = 8
