@@ -4,6 +4,7 @@ properties plus an exact (1e-10) oracle comparison on a handful of filters cut o
   configs[1]  Monte Carlo 10^6 trials x 1000 steps: the per-step sums over [0, 10^6) equal the sums over
               [0, 5*10^5) plus those over [5*10^5, 10^6) (Philox is keyed by the global trial index).
   configs[3]  hybrid CKF->EKF, 10^5 filters x 200 epochs streamed from HBM (device-resident C-ABI call).
+              SRIF, same size, through the speculative straight-line epoch.
   configs[4]  32-state vanilla, 10^5 filters x 200 steps.
 """
 import ctypes as C
@@ -89,6 +90,54 @@ def test_hybrid_full_size_subset_matches_oracle(oracle):
         assert ex <= max(TOL, 8 * sens), report
         assert eP <= max(TOL, 8 * sens), report
     print("hybrid full size (filter, err x, err P, reference FMA sensitivity):", report)
+
+
+def test_srif_full_size_subset_matches_oracle(oracle):
+    """configs[3], SRIF arm: 10^5 filters x 200 measurement epochs through the production kernel (the speculative
+    straight-line epoch on the packed triangular R, srif_step_tri), eight filters cut out and replayed through the
+    oracle.  Same calibrated bar as the hybrid run above: 1e-10, or 8x the reference formulas' own FMA sensitivity
+    on that filter where the statOD streams make 1e-10 unattainable for any fused arithmetic."""
+    import torch
+    import gokalman_b200 as gk
+    from gokalman_b200 import _lib as L
+    from bench_hybrid import make_streams
+    lib = gk.load()
+    nf, steps, n, m = 100000, 200, 6, 2
+    dev = torch.device("cuda", 0)
+    Phi, Ht, real, comp = make_streams(torch, nf, steps, 77, dev)
+    flags_np = np.full(steps, L.F_MEAS, dtype=np.uint8)
+    flags = torch.from_numpy(flags_np).to(dev)
+    P0 = np.diag([50, 50, 50, 1, 1, 1.0])
+    R = np.diag([1e-6, 1e-6])
+    kf, _ = gk.NewSRIF(np.zeros(n), P0, m, False, gk.NewNoiseless(np.diag([1e-12] * 3), R), n_filters=nf)
+    xs = torch.zeros(n, nf, dtype=torch.float64, device=dev)
+    Ps = torch.zeros(n * n, nf, dtype=torch.float64, device=dev)
+    st = torch.zeros(nf, dtype=torch.int32, device=dev)
+    out = L.Outputs()
+    out.mem, out.every_step = L.DEVICE, 0
+    out.state, out.covar, out.status = xs.data_ptr(), Ps.data_ptr(), st.data_ptr()
+    L.check(lib.gkb_nl_run(kf._h, steps, flags.data_ptr(), Phi.data_ptr(), 0, Ht.data_ptr(), 0, real.data_ptr(),
+                           comp.data_ptr(), None, L.DEVICE, C.byref(out)))
+    torch.cuda.synchronize()
+    assert int((st != 0).sum().item()) == 0
+    Pm = Ps.reshape(n, n, nf)
+    assert bool(torch.equal(Pm, Pm.transpose(0, 1)))              # Covariance() = inv(R) inv(R)^T, mirrored
+    assert bool((torch.diagonal(Pm, dim1=0, dim2=1) > 0).all())
+    pick = [0, 1, 31, 32, 49999, 77777, 99998, 99999]
+    idx = torch.tensor(pick, device=dev)
+    hPhi, hHt = Phi[:, :, idx].cpu().numpy(), Ht[:, :, idx].cpu().numpy()
+    hreal, hcomp = real[:, :, idx].cpu().numpy(), comp[:, :, idx].cpu().numpy()
+    xr, Pr = oracle.run_nl_batch(oracle.SRIF, np.zeros(n), P0, R, flags_np, hPhi, hHt, hreal, hcomp, threads=4)
+    xf, Pf = oracle.run_nl_batch(oracle.SRIF, np.zeros(n), P0, R, flags_np, hPhi, hHt, hreal, hcomp, threads=4, fma=True)
+    got_x, got_P = xs[:, idx].cpu().numpy(), Ps[:, idx].cpu().numpy()
+    report = []
+    for j in range(len(pick)):
+        sens = max(fx.scaled_err(xf[:, j], xr[:, j]), fx.scaled_err(Pf[:, j], Pr[:, j]))
+        ex, eP = fx.scaled_err(got_x[:, j], xr[:, j]), fx.scaled_err(got_P[:, j], Pr[:, j])
+        report.append((pick[j], ex, eP, sens))
+        assert ex <= max(TOL, 8 * sens), report
+        assert eP <= max(TOL, 8 * sens), report
+    print("srif full size (filter, err x, err P, reference FMA sensitivity):", report)
 
 
 def test_vanilla32_full_size_subset_matches_oracle(oracle):
