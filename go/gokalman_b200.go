@@ -217,6 +217,6 @@ func HouseholderTransf(A *mat64.Dense, n, m int) error {
 	return nil
 }
 
-// FilterMajor reports the array layout of a handle: large-state Vanilla handles (n = 16 / 24 / 32) take and
+// FilterMajor reports the array layout of a handle: large-state Vanilla handles (n = 16, 24, ... 64) take and
 // return filter-major arrays [N][C] instead of [C][N] (see gkb_filter_major in the header).
 func (kf *Vanilla) FilterMajor() bool { return C.gkb_filter_major(kf.h) != 0 }
