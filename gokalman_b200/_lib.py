@@ -41,7 +41,9 @@ class McConfig(C.Structure):
                 ("trials", C.c_int64), ("trial_offset", C.c_int64), ("steps", C.c_int),
                 ("controls", C.c_void_p), ("noise_mode", C.c_int), ("seed", C.c_uint64),
                 ("w", C.c_void_p), ("v", C.c_void_p), ("noise_mem", C.c_int),
-                ("with_nees", C.c_int), ("with_nis", C.c_int), ("info_raw_init", C.c_int), ("device", C.c_int)]
+                ("with_nees", C.c_int), ("with_nis", C.c_int), ("info_raw_init", C.c_int), ("device", C.c_int),
+                ("filter_F", C.c_void_p), ("filter_G", C.c_void_p), ("filter_H", C.c_void_p), ("filter_Q", C.c_void_p),
+                ("filter_R", C.c_void_p)]
 
 
 class McOutputs(C.Structure):
@@ -70,6 +72,7 @@ SYMBOLS = [
     ("gkb_set_replay_noise", _i, [_vp, _i, _vp, _vp, _i]),
     ("gkb_reset", _i, [_vp]),
     ("gkb_set_stream", _i, [_vp, _vp]),
+    ("gkb_set_strict", _i, [_vp, _i]),
     ("gkb_n_filters", _i64, [_vp]),
     ("gkb_filter_major", _i, [_vp]),
     ("gkb_step", _i, [_vp]),

@@ -627,6 +627,11 @@ class HybridKF(_NLDKF):
         self._Gamma = _arr(Gamma)
         self.sncEnabled = True
 
+    def SetStrict(self, on=True):
+        """Reference-order arithmetic (gkb_set_strict): dense products in the written order, no FMA contraction,
+        dense Joseph form -- the validation twin of the production kernels."""
+        _lib.check(_lib.load().gkb_set_strict(self._h, int(bool(on))))
+
     def SetNoise(self, n):
         Q, R = _mat(n.ProcessMatrix()), _mat(n.MeasurementMatrix())
         _lib.check(_lib.load().gkb_set_noise(self._h, _ptr(Q), R.shape[0], _ptr(R)))
@@ -718,20 +723,31 @@ class MonteCarloRuns:
         self._stats = None
 
     def _config(self, kind, tested, with_nees, with_nis, trials=None):
+        """gkb_mc_config: the truth generator is the pure predictor `self.kf` with ITS noise (montecarlo.go:92);
+        the tested filter -- any LDKF, chisquare.go:16 -- brings its OWN F / G / H and its own Noise's Q / R."""
         kf = self.kf
         cfg = _lib.McConfig()
         self._keep = keep = {}
         keep["F"], keep["H"] = _arr(kf.F), _mat(kf.H)
         keep["G"] = None if kf.G is None else _arr(kf.G)
         keep["Q"], keep["R"] = _mat(self.noise.ProcessMatrix()), _mat(self.noise.MeasurementMatrix())
-        if tested is not None:
-            tn = tested.Noise
-            keep["Q"], keep["R"] = _mat(tn.ProcessMatrix()), _mat(tn.MeasurementMatrix())
         keep["x0t"] = _arr(kf._x0)
         keep["x0f"] = _arr(tested._x0) if tested is not None else _arr(kf._x0)
         keep["P0"] = _arr(tested._P0) if tested is not None else _arr(kf._P0)
         keep["u"] = None if self.controls is None else _arr(self.controls).reshape(self.steps, -1)
         cfg.kind, cfg.n, cfg.m, cfg.c = kind, kf._n, kf._m, kf._c
+        if tested is not None:
+            if (tested._n, tested._m) != (kf._n, kf._m):  # the reference's mat64 products would panic
+                raise GkbError(-1, "tested filter is %dx%d, the Monte Carlo runs are %dx%d" % (tested._n, tested._m, kf._n, kf._m))
+            if tested.G is not None and kf._c and tested._c != kf._c:
+                raise GkbError(-1, "control (u)(%dx...) G(...x%d)" % (kf._c, tested._c))
+            tn = tested.Noise
+            keep["fF"], keep["fH"] = _arr(tested.F), _mat(tested.H)
+            # a tested filter without G ignores the controls (needCtrl false): an all-zero G says exactly that
+            keep["fG"] = (None if kf._c == 0 else np.zeros((kf._n, kf._c))) if tested.G is None else _arr(tested.G)
+            keep["fQ"], keep["fR"] = _mat(tn.ProcessMatrix()), _mat(tn.MeasurementMatrix())
+            for name, key in (("filter_F", "fF"), ("filter_G", "fG"), ("filter_H", "fH"), ("filter_Q", "fQ"), ("filter_R", "fR")):
+                setattr(cfg, name, None if keep[key] is None else keep[key].ctypes.data)
         for name, key in (("F", "F"), ("G", "G"), ("H", "H"), ("Q", "Q"), ("R", "R"), ("x0_truth", "x0t"),
                           ("x0_filter", "x0f"), ("P0", "P0"), ("controls", "u")):
             setattr(cfg, name, None if keep[key] is None else keep[key].ctypes.data)

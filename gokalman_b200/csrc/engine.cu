@@ -69,33 +69,50 @@ struct DevBuf {
 
 // CUDA-event bracket around the kernels of the last call on this thread.  The events are kept so
 // that gkb_last_kernel_ms() can be asked later, also after an asynchronous (device-pointer) call.
+// Events belong to the device that was current when they were created and can only be recorded on streams of
+// that device: one set per device (a host thread may drive handles on several GPUs), created on first use.
 struct LastTiming {
   cudaEvent_t e0 = nullptr, e1 = nullptr, m0 = nullptr, m1 = nullptr;  // whole call / dominant kernel
-  bool valid = false, main_valid = false;
 };
-thread_local LastTiming g_timing;
+constexpr int kMaxDevices = 64;
+thread_local LastTiming g_timing_dev[kMaxDevices];
+thread_local struct { int device = -1; bool valid = false, main_valid = false; } g_timing;
 
 struct Timer {
   cudaStream_t s;
+  LastTiming* t = nullptr;
+  bool ok = false;
+  // the calling code has made the handle's device current (check_device / cudaSetDevice) before timing
   explicit Timer(cudaStream_t st) : s(st) {
-    if (!g_timing.e0) {
-      cudaEventCreate(&g_timing.e0);
-      cudaEventCreate(&g_timing.e1);
-      cudaEventCreate(&g_timing.m0);
-      cudaEventCreate(&g_timing.m1);
-    }
+    int dev = -1;
     g_timing.valid = g_timing.main_valid = false;
-    cudaEventRecord(g_timing.e0, s);
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return;
+    t = &g_timing_dev[dev];
+    if (!t->e0) {
+      if (cudaEventCreate(&t->e0) != cudaSuccess || cudaEventCreate(&t->e1) != cudaSuccess ||
+          cudaEventCreate(&t->m0) != cudaSuccess || cudaEventCreate(&t->m1) != cudaSuccess) {
+        t->e0 = nullptr;
+        (void)cudaGetLastError();
+        return;
+      }
+    }
+    g_timing.device = dev;
+    ok = cudaEventRecord(t->e0, s) == cudaSuccess;
+    if (!ok) (void)cudaGetLastError();  // timing is best effort: never let it leak into the call's error check
   }
-  void main_begin() { cudaEventRecord(g_timing.m0, s); }
+  void main_begin() {
+    if (ok && cudaEventRecord(t->m0, s) != cudaSuccess) { ok = false; (void)cudaGetLastError(); }
+  }
   void main_end() {
-    cudaEventRecord(g_timing.m1, s);
-    g_timing.main_valid = true;
+    if (!ok) return;
+    if (cudaEventRecord(t->m1, s) == cudaSuccess) g_timing.main_valid = true;
+    else (void)cudaGetLastError();
   }
   void stop(int launches, bool /*sync*/) {
-    cudaEventRecord(g_timing.e1, s);
-    g_timing.valid = true;
     g_last_launches = launches;
+    if (!ok) return;
+    if (cudaEventRecord(t->e1, s) == cudaSuccess) g_timing.valid = true;
+    else (void)cudaGetLastError();
   }
 };
 
@@ -150,6 +167,7 @@ struct gkb_filter {
   cudaStream_t stream = cudaStreamLegacy;
   int step = 0;
   bool ekf = false;
+  bool strict = false;  // gkb_set_strict: reference-order arithmetic (hybrid)
   DevBuf vec, mat, vec0, mat0, status;
   DevBuf replay_w, replay_v;
   int replay_steps = 0;
@@ -168,15 +186,17 @@ const char* gkb_version(void) { return "gokalman_b200 0.1 (sm_100a)"; }
 const char* gkb_last_error(void) { return g_last_error.c_str(); }
 float gkb_last_kernel_ms(void) {
   if (!g_timing.valid) return -1.f;
-  if (cudaEventSynchronize(g_timing.e1) != cudaSuccess) return -1.f;
-  if (cudaEventElapsedTime(&g_last_ms, g_timing.e0, g_timing.e1) != cudaSuccess) return -1.f;
+  const LastTiming& t = g_timing_dev[g_timing.device];
+  if (cudaEventSynchronize(t.e1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&g_last_ms, t.e0, t.e1) != cudaSuccess) return -1.f;
   return g_last_ms;
 }
 float gkb_last_main_kernel_ms(void) {
   if (!g_timing.main_valid) return gkb_last_kernel_ms();
+  const LastTiming& t = g_timing_dev[g_timing.device];
   float ms = -1.f;
-  if (cudaEventSynchronize(g_timing.m1) != cudaSuccess) return -1.f;
-  if (cudaEventElapsedTime(&ms, g_timing.m0, g_timing.m1) != cudaSuccess) return -1.f;
+  if (cudaEventSynchronize(t.m1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, t.m0, t.m1) != cudaSuccess) return -1.f;
   return ms;
 }
 int gkb_last_kernel_launches(void) { return g_last_launches; }
@@ -435,6 +455,13 @@ int gkb_step(const gkb_filter* f) { return f ? f->step : 0; }
 int gkb_set_stream(gkb_filter* f, void* stream) {
   if (!f) return fail(GKB_ERR_ARG, "NULL handle");
   f->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamLegacy;
+  return 0;
+}
+
+int gkb_set_strict(gkb_filter* f, int on) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  if (f->hm.kind != GKB_HYBRID) return fail(GKB_ERR_UNSUPPORTED, "strict (reference-order) arithmetic is built for GKB_HYBRID handles");
+  f->strict = on != 0;
   return 0;
 }
 
@@ -816,6 +843,7 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
   OutPlan pl;
   if ((rc = plan_outputs(f, out, steps, innov_len, pl))) return rc;
   io.every_step = out ? out->every_step : 0;
+  io.strict = f->strict ? 1 : 0;
   io.o_state = pl.state; io.o_meas = pl.meas; io.o_innov = pl.innov; io.o_covar = pl.covar;
   io.o_pred = pl.pred; io.o_gain = pl.gain; io.o_obsdev = pl.obsdev;
   io.status = f->status.as<int32_t>();
@@ -941,16 +969,42 @@ int gkb_batch_solve(int n, int m, int steps, int64_t n_filters, int device, cons
 // ---- Monte Carlo + chi-square ------------------------------------------------------------------------
 
 namespace {
+// The derived matrices of a model depend only on the model: the one-thread setup kernel is rerun only when its
+// inputs change (a benchmark loop or a parameter sweep calls gkb_mc_chisquare many times with the same model).
 struct McSetupCache {
   bool valid = false;
   int ops = 0;
   HostModel in_hm, out_hm;
-  double in_x0f[GKB_MAX_N], out_x0f[GKB_MAX_N];
-  double in_P0[GKB_MAX_N * GKB_MAX_N], out_P0[GKB_MAX_N * GKB_MAX_N];
+  double in_x0[GKB_MAX_N], out_x0[GKB_MAX_N];
+  double in_A0[GKB_MAX_N * GKB_MAX_N], out_A0[GKB_MAX_N * GKB_MAX_N];
+  // runs (or replays) launch_model_setup(hm, ops, x0, A0); x0 / A0 are [GKB_MAX_N] / [GKB_MAX_N^2] arrays
+  int run(HostModel& hm, int ops_, double* x0, double* A0, cudaStream_t s) {
+    if (ops_ == 0) return 0;
+    const bool same = valid && ops == ops_ && memcmp(&in_hm, &hm, sizeof hm) == 0 &&
+                      memcmp(in_x0, x0, sizeof in_x0) == 0 && memcmp(in_A0, A0, sizeof in_A0) == 0;
+    if (same) {
+      hm = out_hm;
+      memcpy(x0, out_x0, sizeof out_x0);
+      memcpy(A0, out_A0, sizeof out_A0);
+      return 0;
+    }
+    valid = false;
+    ops = ops_;
+    in_hm = hm;
+    memcpy(in_x0, x0, sizeof in_x0);
+    memcpy(in_A0, A0, sizeof in_A0);
+    const int rc = launch_model_setup(hm, ops_, x0, A0, s);
+    if (rc) return rc;
+    out_hm = hm;
+    memcpy(out_x0, x0, sizeof out_x0);
+    memcpy(out_A0, A0, sizeof out_A0);
+    valid = true;
+    return 0;
+  }
 };
 struct McScratch {
-  DevBuf partial, out, u, gu, w, v, err;
-  McSetupCache setup;
+  DevBuf partial, out, u, gu, gu_f, w, v, err;
+  McSetupCache setup_truth, setup_filter;
   int device = -1;
 };
 thread_local McScratch g_mc;
@@ -963,7 +1017,7 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   if (cfg->kind != GKB_VANILLA && cfg->kind != GKB_INFORMATION && cfg->kind != GKB_SQRT)
     return fail(GKB_ERR_ARG, "tested filter kind %d is not an LDKF kind", cfg->kind);
   const int n = cfg->n, m = cfg->m, c = cfg->c, steps = cfg->steps;
-  if (n > 6 || !gkb_shape_supported(cfg->kind, n, m))  // the fused Monte Carlo kernels are compiled for n <= 6
+  if (!mc_shape_supported(cfg->kind, n, m))
     return fail(GKB_ERR_UNSUPPORTED, "no compiled Monte Carlo kernel for n=%d m=%d", n, m);
   if (c < 0 || c > GKB_MAX_C) return fail(GKB_ERR_UNSUPPORTED, "control size %d outside 0..%d", c, GKB_MAX_C);
   if (cfg->trials < 1 || steps < 1) return fail(GKB_ERR_ARG, "trials and steps must be >= 1");
@@ -979,49 +1033,44 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
     g_mc = McScratch();
     g_mc.device = cfg->device;
   }
-  HostModel hm;
-  memset(&hm, 0, sizeof hm);
-  hm.kind = cfg->kind; hm.n = n; hm.m = m; hm.c = c; hm.m_r = m; hm.rinv_dim = m;
-  memcpy(hm.F, cfg->F, sizeof(double) * n * n);
-  if (cfg->G && c > 0) memcpy(hm.G, cfg->G, sizeof(double) * n * c);
-  hm.need_ctrl = !(cfg->G == nullptr || c == 0 || is_nil(cfg->G, n * c));
-  memcpy(hm.H, cfg->H, sizeof(double) * m * n);
-  sym_from_upper(hm.Q, cfg->Q, n);
-  sym_from_upper(hm.R, cfg->R, m);
+  // tm: the truth generator (the pure predictor of NewMonteCarloRuns, montecarlo.go:92, with its AWGN's Q, R);
+  // hm: the tested filter's own model (chisquare.go:16 takes any LDKF) -- the truth's unless filter_* say otherwise
+  HostModel tm, hm;
+  memset(&tm, 0, sizeof tm);
+  tm.kind = GKB_PREDICTOR; tm.n = n; tm.m = m; tm.c = c; tm.m_r = m; tm.rinv_dim = m;
+  memcpy(tm.F, cfg->F, sizeof(double) * n * n);
+  if (cfg->G && c > 0) memcpy(tm.G, cfg->G, sizeof(double) * n * c);
+  tm.need_ctrl = !(cfg->G == nullptr || c == 0 || is_nil(cfg->G, n * c));
+  memcpy(tm.H, cfg->H, sizeof(double) * m * n);
+  sym_from_upper(tm.Q, cfg->Q, n);
+  sym_from_upper(tm.R, cfg->R, m);
+  hm = tm;
+  hm.kind = cfg->kind;
+  if (cfg->filter_F) memcpy(hm.F, cfg->filter_F, sizeof(double) * n * n);
+  if (cfg->filter_G && c > 0) {
+    memcpy(hm.G, cfg->filter_G, sizeof(double) * n * c);
+    hm.need_ctrl = !is_nil(cfg->filter_G, n * c);
+  }
+  if (cfg->filter_H) memcpy(hm.H, cfg->filter_H, sizeof(double) * m * n);
+  if (cfg->filter_Q) sym_from_upper(hm.Q, cfg->filter_Q, n);
+  if (cfg->filter_R) sym_from_upper(hm.R, cfg->filter_R, m);
   McIo io;
   memset(&io, 0, sizeof io);
   sym_from_upper(io.P0, cfg->P0, n);
   memcpy(io.x0_truth, cfg->x0_truth, sizeof(double) * n);
   memcpy(io.x0_filter, cfg->x0_filter, sizeof(double) * n);
-  int ops = kOpSqrtQ | kOpSqrtR;  // AWGN colouring (noise.go:146-153) and the sqrt filter's model
-  if (cfg->kind == GKB_INFORMATION) ops |= kOpFinv | kOpQinv | kOpRinv | (cfg->info_raw_init ? 0 : kOpFromState);
-  if (cfg->kind == GKB_SQRT) ops |= kOpCholA0;
-  // The derived matrices depend only on the model: redo the setup kernel only when it changes.
   {
-    McSetupCache& cs = g_mc.setup;
-    const bool same = cs.valid && cs.ops == ops && memcmp(&cs.in_hm, &hm, sizeof hm) == 0 &&
-                      memcmp(cs.in_x0f, io.x0_filter, sizeof io.x0_filter) == 0 &&
-                      memcmp(cs.in_P0, io.P0, sizeof io.P0) == 0;
-    if (!same) {
-      cs.valid = false;
-      cs.ops = ops;
-      cs.in_hm = hm;
-      memcpy(cs.in_x0f, io.x0_filter, sizeof io.x0_filter);
-      memcpy(cs.in_P0, io.P0, sizeof io.P0);
-      rc = launch_model_setup(hm, ops, io.x0_filter, io.P0, s);
-      if (rc) return fail(rc, "model setup failed (%d)", rc);
-      cs.out_hm = hm;
-      memcpy(cs.out_x0f, io.x0_filter, sizeof io.x0_filter);
-      memcpy(cs.out_P0, io.P0, sizeof io.P0);
-      cs.valid = true;
-    } else {
-      hm = cs.out_hm;
-      memcpy(io.x0_filter, cs.out_x0f, sizeof io.x0_filter);
-      memcpy(io.P0, cs.out_P0, sizeof io.P0);
-    }
+    // truth: AWGN colouring chol(Q), chol(R) (distmv.NewNormal, noise.go:146-153)
+    double x0s[GKB_MAX_N] = {0}, A0s[GKB_MAX_N * GKB_MAX_N] = {0};
+    if ((rc = g_mc.setup_truth.run(tm, kOpSqrtQ | kOpSqrtR, x0s, A0s, s))) return fail(rc, "truth model setup failed (%d)", rc);
+    // tested filter: its constructor's derived matrices, from ITS model
+    int ops = 0;
+    if (cfg->kind == GKB_INFORMATION) ops = kOpFinv | kOpQinv | kOpRinv | (cfg->info_raw_init ? 0 : kOpFromState);
+    if (cfg->kind == GKB_SQRT) ops = kOpSqrtQ | kOpSqrtR | kOpCholA0;
+    if ((rc = g_mc.setup_filter.run(hm, ops, io.x0_filter, io.P0, s))) return fail(rc, "tested-filter model setup failed (%d)", rc);
   }
-  memcpy(io.LQ, hm.sqrtQ, sizeof(double) * n * n);
-  memcpy(io.LR, hm.sqrtR, sizeof(double) * m * m);
+  memcpy(io.LQ, tm.sqrtQ, sizeof(double) * n * n);
+  memcpy(io.LR, tm.sqrtR, sizeof(double) * m * m);
   if (cfg->noise_mode == GKB_NOISE_PHILOX) {
     for (int i = 0; i < n * n; ++i)
       if (!std::isfinite(io.LQ[i])) return fail(GKB_ERR_ARG, "process noise invalid: Q is not positive definite (noise.go:149-151)");
@@ -1037,17 +1086,28 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   io.with_nis = cfg->with_nis;
   io.want_xstats = (out->sum_d || out->sum_dd || out->x_ref) ? 1 : 0;
   const int cols = mc_cols(n, io.want_xstats);
-  if (cfg->controls && c > 0 && hm.need_ctrl) {
+  if (cfg->controls && c > 0 && (tm.need_ctrl || hm.need_ctrl)) {
     // montecarlo.go:98-104 replaces a single control vector by zeros: an all-zero control stream adds
-    // +0.0 to every prediction, so it is elided; otherwise G u is formed once per step for all trials.
+    // +0.0 to every prediction, so it is elided; otherwise G u is formed once per step for all trials --
+    // with the truth's G and, when the tested filter carries another G, with that one too.
     bool any = false;
     for (size_t i = 0; i < (size_t)steps * c && !any; ++i) any = cfg->controls[i] != 0.0;
     if (any) {
       if ((rc = g_mc.u.ensure(sizeof(double) * (size_t)steps * c))) return rc;
-      if ((rc = g_mc.gu.ensure(sizeof(double) * (size_t)steps * n))) return rc;
       GKB_CUDA(cudaMemcpyAsync(g_mc.u.p, cfg->controls, sizeof(double) * (size_t)steps * c, cudaMemcpyHostToDevice, s));
-      launch_gu(hm.G, n, c, g_mc.u.as<double>(), steps, g_mc.gu.as<double>(), s);
-      io.gu = g_mc.gu.as<double>();
+      if (tm.need_ctrl) {
+        if ((rc = g_mc.gu.ensure(sizeof(double) * (size_t)steps * n))) return rc;
+        launch_gu(tm.G, n, c, g_mc.u.as<double>(), steps, g_mc.gu.as<double>(), s);
+        io.gu = g_mc.gu.as<double>();
+      }
+      const bool same_g = tm.need_ctrl == hm.need_ctrl && memcmp(tm.G, hm.G, sizeof tm.G) == 0;
+      if (same_g) {
+        io.gu_f = io.gu;
+      } else if (hm.need_ctrl) {
+        if ((rc = g_mc.gu_f.ensure(sizeof(double) * (size_t)steps * n))) return rc;
+        launch_gu(hm.G, n, c, g_mc.u.as<double>(), steps, g_mc.gu_f.as<double>(), s);
+        io.gu_f = g_mc.gu_f.as<double>();
+      }
     }
   }
   if (cfg->noise_mode == GKB_NOISE_REPLAY) {
@@ -1097,20 +1157,22 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   if ((rc = g_mc.out.ensure(sizeof(double) * (size_t)steps * cols))) return rc;
   io.partial = g_mc.partial.as<double>();
   const bool sync = out->mem != GKB_DEVICE;
-  Timer tm(s);
+  Timer timer(s);
   if (steps > kMcChunk) GKB_CUDA(cudaMemsetAsync(io.partial, 0, pbytes, s));  // chunked flush accumulates into the rows
   int grid = 0;
-  tm.main_begin();
-  rc = launch_mc(hm, io, cfg->device, &grid, s);
-  tm.main_end();
+  timer.main_begin();
+  rc = launch_mc(tm, hm, io, cfg->device, &grid, s);
+  timer.main_end();
   if (rc) return fail(rc, "no Monte Carlo kernel for kind=%d n=%d m=%d", hm.kind, n, m);
   const double scale = out->sums_only ? 1.0 : 1.0 / (double)cfg->trials;  // stat.Mean, chisquare.go:85-92
   launch_mc_finish(io.partial, grid, steps, cols, scale, g_mc.out.as<double>(), s);
-  tm.stop(2, sync);
+  timer.stop(2, sync);
   GKB_CUDA(cudaGetLastError());
   const cudaMemcpyKind back = out->mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   const double* o = g_mc.out.as<double>();
   const size_t sb = sizeof(double) * (size_t)steps;
+  if (out->first_error)  // chisquare.go:40-42 panics when the tested filter's Update fails: the caller must see it
+    GKB_CUDA(cudaMemcpyAsync(out->first_error, io.first_error, sizeof(int32_t), back, s));
   if (out->nis) GKB_CUDA(cudaMemcpyAsync(out->nis, o, sb, back, s));
   if (out->nees) GKB_CUDA(cudaMemcpyAsync(out->nees, o + steps, sb, back, s));
   if (io.want_xstats) {

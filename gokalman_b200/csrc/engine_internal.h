@@ -71,6 +71,7 @@ struct NlIo {
   int* sched;           // TMA production path: [1 + ceil(nf / 32)] ints of scheduler scratch (task counter + per-group flags)
   int chunks, chunk_len;  // filled by the launcher: epochs are run in `chunks` chunks of `chunk_len`
   int every_step;
+  int strict;  // gkb_set_strict: reference-order arithmetic (filters_strict.cuh), hybrid only
   double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain, *o_obsdev;
   int32_t* status;
 };
@@ -98,7 +99,8 @@ struct McIo {
   int64_t trials;
   int64_t trial_offset;
   int steps;
-  const double* gu;  // device [steps][n]: G u per step, nullptr = no (or all-zero) control
+  const double* gu;    // device [steps][n]: G u per step of the TRUTH generator, nullptr = no (or all-zero) control
+  const double* gu_f;  // the same for the tested filter's own G (== gu when both carry the same G)
   int noise_mode;
   unsigned long long seed;
   const double* w;  // replay [steps][n][trials]
@@ -158,7 +160,9 @@ int launch_tile_gu(const double* G_dev, int n, int c, const double* u_dev, int s
 // Upper bound on the CTAs launch_mc will use (rows of McIo::partial to allocate, zero-filled).
 int mc_max_grid(int device);
 // Picks a persistent grid (SM count x resident CTAs per SM, capped by the work) and launches.
-int launch_mc(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+// tm: the truth generator's model (F, G, H; its chol(Q), chol(R) are in io.LQ / io.LR); hm: the tested filter's.
+int launch_mc(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int mc_shape_supported(int kind, int n, int m);
 int launch_mc_finish(const double* partial, int grid, int steps, int cols, double scale, double* out_cols,
                      cudaStream_t s);
 

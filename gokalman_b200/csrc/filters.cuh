@@ -37,6 +37,7 @@ struct InfoModel {  // information.go:84-95
   double H[M * N];
   double Qinv[N * N];
   double Rinv[M * M];
+  double R[M * M];  // the filter's CURRENT measurement noise (GetNoise().MeasurementMatrix()): chi-square NIS only
   int rinv_dim;  // 1 => scalar broadcast path (information.go:197-199)
   int c;
   int need_ctrl;

@@ -1,0 +1,311 @@
+// filters_strict.cuh -- the REFERENCE-ORDER ("strict") evaluation of the filter steps.
+//
+// The production steps (filters.cuh, filters_nl.cuh) keep covariances packed, contract a*b+c into FMAs and
+// evaluate the Joseph update with the products by the identity removed.  On well-conditioned problems that agrees
+// with the reference to ~1e-14; on the statOD configuration (R = 1e-6 against P0 = 10) forming (I - K H) P-bar
+// cancels to eps |P-bar| absolute and any change of rounding moves the result by eps |P-bar| / |P+|.  This file is
+// the same step written exactly as the reference executes it -- every product a full dense product in the written
+// order (hybrid.go:114-182), every a*b+c rounded twice (__dmul_rn / __dadd_rn: Go on amd64 never fuses), IEEE
+// divisions, the explicit LU inverse of mat64.Dense.Inverse, the dense Joseph form, AsSymDense at the end -- so that
+// the GPU can be held to the north star's 1e-10 on EVERY configuration (it lands at ~1e-15: the only differences
+// left are none), and so that the fast production kernels can be measured against it on all 10^5 filters of a run
+// instead of on the handful the CPU oracle can replay.  Selected per handle with gkb_set_strict().
+#pragma once
+#include "filters_nl.cuh"
+
+namespace gkb {
+namespace strict {
+
+GKB_DEV double mul2(double a, double b) { return __dmul_rn(a, b); }
+GKB_DEV double add2(double a, double b) { return __dadd_rn(a, b); }
+GKB_DEV double div2(double a, double b) { return __ddiv_rn(a, b); }
+
+// C[R x C] = A[R x K] B[K x C]: gonum dgemm, sequential sum over the inner index starting from 0
+template <int R, int K, int C>
+GKB_DEV void mul(double (&out)[R * C], const double (&A)[R * K], const double (&B)[K * C]) {
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < K; ++l) s = add2(s, mul2(A[i * K + l], B[l * C + j]));
+      out[i * C + j] = s;
+    }
+}
+// C[R x C] = A[R x K] B^T, B is [C x K]
+template <int R, int K, int C>
+GKB_DEV void mul_nt(double (&out)[R * C], const double (&A)[R * K], const double (&B)[C * K]) {
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < K; ++l) s = add2(s, mul2(A[i * K + l], B[j * K + l]));
+      out[i * C + j] = s;
+    }
+}
+template <int R, int C>
+GKB_DEV void mulvec(double (&y)[R], const double (&A)[R * C], const double (&x)[C]) {
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < C; ++j) s = add2(s, mul2(A[i * C + j], x[j]));
+    y[i] = s;
+  }
+}
+
+// mat64.Dense.Inverse: dgetf2 (partial pivoting, first index of the largest |.|) + dtrti2 + dgetri, then the
+// ||A||inf ||inv(A)||inf <= 1e16 test.  Returns 0 ok, 1 exactly singular, 2 ill-conditioned (output = the inverse).
+template <int N>
+GKB_DEV int inverse(double (&a)[N * N]) {
+  double anorm = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s = add2(s, fabs(a[i * N + j]));
+    if (s > anorm) anorm = s;
+  }
+  int piv[N];
+  bool singular = false;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    int p = j;
+    double pmax = fabs(a[j * N + j]);
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      const double v = fabs(a[i * N + j]);
+      if (v > pmax) { pmax = v; p = i; }
+    }
+    piv[j] = p;
+    if (pmax != 0.0) {
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) {
+        const bool sw = (p == i);
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
+          const double t0 = a[j * N + l], t1 = a[i * N + l];
+          a[j * N + l] = sw ? t1 : t0;
+          a[i * N + l] = sw ? t0 : t1;
+        }
+      }
+      if (fabs(a[j * N + j]) >= 2.2250738585072014e-308) {
+        const double rinv = div2(1.0, a[j * N + j]);
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) a[i * N + j] = mul2(a[i * N + j], rinv);
+      } else {
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) a[i * N + j] = div2(a[i * N + j], a[j * N + j]);
+      }
+    } else {
+      singular = true;
+    }
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      const double lij = a[i * N + j];
+#pragma unroll
+      for (int l = j + 1; l < N; ++l) a[i * N + l] = add2(a[i * N + l], -mul2(lij, a[j * N + l]));
+    }
+  }
+  if (singular) return 1;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {  // dtrti2, upper, non-unit
+    a[j * N + j] = div2(1.0, a[j * N + j]);
+    const double ajj = -a[j * N + j];
+#pragma unroll
+    for (int i = 0; i < j; ++i) {
+      double t = mul2(a[i * N + i], a[i * N + j]);
+#pragma unroll
+      for (int l = i + 1; l < j; ++l) t = add2(t, mul2(a[i * N + l], a[l * N + j]));
+      a[i * N + j] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < j; ++i) a[i * N + j] = mul2(a[i * N + j], ajj);
+  }
+#pragma unroll
+  for (int j = N - 2; j >= 0; --j) {  // dgetri, unblocked (j = N-1 only clears nothing)
+    double work[N];
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      work[i] = a[i * N + j];
+      a[i * N + j] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int l = j + 1; l < N; ++l) t = add2(t, mul2(a[i * N + l], work[l]));
+      a[i * N + j] = add2(a[i * N + j], mul2(-1.0, t));
+    }
+  }
+#pragma unroll
+  for (int j = N - 2; j >= 0; --j) {
+#pragma unroll
+    for (int jp = j + 1; jp < N; ++jp) {
+      const bool sw = (piv[j] == jp);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double t0 = a[i * N + j], t1 = a[i * N + jp];
+        a[i * N + j] = sw ? t1 : t0;
+        a[i * N + jp] = sw ? t0 : t1;
+      }
+    }
+  }
+  double inorm = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s = add2(s, fabs(a[i * N + j]));
+    if (s > inorm) inorm = s;
+  }
+  return (mul2(anorm, inorm) <= 1e16) ? 0 : 2;
+}
+
+// helper.go:65-84 AsSymDense: error when an off-diagonal pair differs by more than 1e-6 absolute AND more than 1e-2
+// relative (floats.EqualWithinAbsOrRel); on success the upper triangle is mirrored (mat64.SymDense reads only it).
+template <int N>
+GKB_DEV bool as_sym(double (&A)[N * N]) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      const double a = A[j * N + i], b = A[i * N + j];
+      const double d = fabs(a - b);
+      const bool eq = (a == b) || (d <= 1e-6) || (d / fmax(fabs(a), fabs(b)) <= 1e-2);
+      ok = ok && eq;
+    }
+  if (!ok) return false;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) A[i * N + j] = A[j * N + i];
+  return true;
+}
+
+// hybrid.go:104-204 fullUpdate, statement by statement.  x, P (dense, mirrored upper triangle): previous estimate
+// in, new one out (untouched when an error is returned).  Ppred / K / innov / obsdev: the Estimate fields.
+template <int N, int M>
+GKB_DEV int hybrid_step(const NlModel<N, M>& md, double (&x)[N], double (&P)[N * N], const double (&Phi)[N * N],
+                        const double (&Ht)[M * N], const double (&real_obs)[M], const double (&computed_obs)[M],
+                        const double* __restrict__ Gamma, bool has_meas, bool ekf, bool snc, double (&Ppred)[N * N],
+                        double (&K)[N * M], double (&innov)[M], double (&obsdev)[M]) {
+  // 114-117
+  double Pbar[N * N];
+  {
+    double PhiP[N * N];
+    mul<N, N, N>(PhiP, Phi, P);
+    mul_nt<N, N, N>(Pbar, PhiP, Phi);
+  }
+  if (snc && Gamma != nullptr) {  // 118-123: P-bar + (Gamma Q) Gamma^T
+    const int q = md.q;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double gq[GKB_MAX_Q];
+#pragma unroll
+      for (int a = 0; a < GKB_MAX_Q; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < GKB_MAX_Q; ++b)
+          if (a < q && b < q) s = add2(s, mul2(__ldg(Gamma + i * q + b), md.Q[b * q + a]));
+        gq[a] = s;
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < GKB_MAX_Q; ++a)
+          if (a < q) s = add2(s, mul2(gq[a], __ldg(Gamma + j * q + a)));
+        Pbar[i * N + j] = add2(Pbar[i * N + j], s);
+      }
+    }
+  }
+  if (!has_meas) {  // Predict(): 125-143
+    double xbar[N];
+    if (ekf) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) xbar[i] = 0.0;
+    } else {
+      mulvec<N, N>(xbar, Phi, x);
+    }
+    if (!as_sym<N>(Pbar)) return GKB_ERR_ASYMMETRIC;
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = xbar[i];
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) { P[i] = Pbar[i]; Ppred[i] = Pbar[i]; }
+#pragma unroll
+    for (int a = 0; a < M; ++a) { innov[a] = 0.0; obsdev[a] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < N * M; ++i) K[i] = 0.0;
+    return 0;
+  }
+  // 146-153
+  double PHt[N * M];
+  mul_nt<N, N, M>(PHt, Pbar, Ht);  // P-bar Ht^T (the transposed copy of the reference holds the same numbers)
+  double S[M * M];
+  mul<M, N, M>(S, Ht, PHt);
+#pragma unroll
+  for (int i = 0; i < M * M; ++i) S[i] = add2(S[i], md.R[i]);
+  if (inverse<M>(S) != 0) return GKB_ERR_SINGULAR_S;
+  double Kn[N * M];
+  mul<N, M, M>(Kn, PHt, S);
+  // 156-173
+  double y[M], inn[M], xhat[N];
+#pragma unroll
+  for (int a = 0; a < M; ++a) { y[a] = add2(real_obs[a], -computed_obs[a]); inn[a] = 0.0; }
+  if (ekf) {
+    mulvec<N, M>(xhat, Kn, y);
+  } else {
+    double xbar[N], t1[M];
+    mulvec<N, N>(xbar, Phi, x);
+    mulvec<M, N>(t1, Ht, xbar);
+#pragma unroll
+    for (int a = 0; a < M; ++a) inn[a] = add2(y[a], -t1[a]);
+    mulvec<N, M>(xhat, Kn, inn);
+#pragma unroll
+    for (int i = 0; i < N; ++i) xhat[i] = add2(xbar[i], xhat[i]);
+  }
+  // 174-182: dense Joseph form ((I - K H) P-bar) (I - K H)^T + (K R) K^T
+  double Pn[N * N];
+  {
+    double KH[N * N];
+    mul<N, M, N>(KH, Kn, Ht);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) KH[i * N + j] = add2(i == j ? 1.0 : 0.0, -KH[i * N + j]);
+    double T1[N * N];
+    mul<N, N, N>(T1, KH, Pbar);
+    mul_nt<N, N, N>(Pn, T1, KH);
+    double KR[N * M];
+    mul<N, M, M>(KR, Kn, md.R);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < M; ++a) s = add2(s, mul2(KR[i * M + a], Kn[j * M + a]));
+        Pn[i * N + j] = add2(Pn[i * N + j], s);
+      }
+  }
+  // 184-192
+  if (!as_sym<N>(Pbar)) return GKB_ERR_ASYMMETRIC;
+  if (!as_sym<N>(Pn)) return GKB_ERR_ASYMMETRIC;
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = xhat[i];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) { P[i] = Pn[i]; Ppred[i] = Pbar[i]; }
+#pragma unroll
+  for (int i = 0; i < N * M; ++i) K[i] = Kn[i];
+#pragma unroll
+  for (int a = 0; a < M; ++a) { innov[a] = inn[a]; obsdev[a] = y[a]; }
+  return 0;
+}
+
+}  // namespace strict
+}  // namespace gkb

@@ -275,6 +275,7 @@ static int launch_shape(const HostModel& hm, const LtiIo& io, cudaStream_t s) {
       if (hm.rinv_dim == 1) md.Rinv[0] = hm.Rinv[0];
       else for (int i = 0; i < M * M; ++i) md.Rinv[i] = hm.Rinv[i];
       md.rinv_dim = hm.rinv_dim;
+      for (int i = 0; i < M * M; ++i) md.R[i] = hm.R[i];
       fill_common<N, M>(hm, md.G, md.H, md.c, md.need_ctrl);
       info_update_kernel<N, M><<<grid, kThreads, 0, s>>>(md, io);
       return 0;

@@ -29,17 +29,27 @@ __global__ void __launch_bounds__(256) mc_finish_kernel(const double* __restrict
 }
 #endif  // GKB_MC_PART == 0
 
+// mm: the truth generator (tm: F, G, H; io: chol(Q), chol(R), x0) plus the tested filter's initial estimate
 template <int N, int M>
-static void fill_mc_model(const HostModel& hm, const McIo& io, McModel<N, M>& mm, const double* A0) {
-  for (int i = 0; i < N * N; ++i) { mm.F[i] = hm.F[i]; mm.LQ[i] = io.LQ[i]; mm.A0[i] = A0[i]; }
+static void fill_mc_model(const HostModel& tm, const McIo& io, McModel<N, M>& mm, const double* A0) {
+  for (int i = 0; i < N * N; ++i) { mm.F[i] = tm.F[i]; mm.LQ[i] = io.LQ[i]; mm.A0[i] = A0[i]; }
   for (int i = 0; i < M * M; ++i) mm.LR[i] = io.LR[i];
   for (int i = 0; i < N * GKB_MAX_C; ++i) mm.G[i] = 0.0;
   for (int i = 0; i < N; ++i)
-    for (int j = 0; j < hm.c; ++j) mm.G[i * hm.c + j] = hm.G[i * hm.c + j];
-  for (int i = 0; i < M * N; ++i) mm.H[i] = hm.H[i];
+    for (int j = 0; j < tm.c; ++j) mm.G[i * tm.c + j] = tm.G[i * tm.c + j];
+  for (int i = 0; i < M * N; ++i) mm.H[i] = tm.H[i];
   for (int i = 0; i < N; ++i) { mm.x0_truth[i] = io.x0_truth[i]; mm.x0_filter[i] = io.x0_filter[i]; }
-  mm.c = hm.c;
-  mm.need_ctrl = hm.need_ctrl;
+  mm.c = tm.c;
+  mm.need_ctrl = tm.need_ctrl;
+}
+// the tested filter's own G (only its shape and need_ctrl matter to the kernels: G u arrives precomputed in io.gu_f)
+template <class Model, int N>
+static void fill_tested_ctrl(const HostModel& hm, Model& md) {
+  for (int i = 0; i < N * GKB_MAX_C; ++i) md.G[i] = 0.0;
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < hm.c; ++j) md.G[i * hm.c + j] = hm.G[i * hm.c + j];
+  md.c = hm.c;
+  md.need_ctrl = hm.need_ctrl;
 }
 
 template <class Kern>
@@ -68,21 +78,20 @@ static int pick_grid(Kern kern, size_t smem, int64_t trials, int device) {
 
 #if GKB_MC_PART == 1
 template <int N, int M>
-static int launch_mc_shape_vanilla(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+static int launch_mc_shape_vanilla(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
   const size_t smem = sizeof(double) * (kIcdfSegments * kIcdfCoefs + kWarps * kChunk * cols);
   int grid = 1;
   const bool lean = io.noise_mode == GKB_NOISE_PHILOX && !io.want_xstats && !io.truth_x && !io.truth_y &&
-                    !io.noise_w && !io.noise_v && !io.status;
+                    !io.noise_w && !io.noise_v && !io.status && io.gu_f == io.gu;
   McModel<N, M> mm;
-  fill_mc_model<N, M>(hm, io, mm, io.P0);
+  fill_mc_model<N, M>(tm, io, mm, io.P0);
   {
       VanillaModel<N, M> md;
       for (int i = 0; i < N * N; ++i) { md.F[i] = hm.F[i]; md.Q[i] = hm.Q[i]; }
       for (int i = 0; i < M * M; ++i) md.R[i] = hm.R[i];
-      for (int i = 0; i < N * GKB_MAX_C; ++i) md.G[i] = mm.G[i];
       for (int i = 0; i < M * N; ++i) md.H[i] = hm.H[i];
-      md.c = hm.c; md.need_ctrl = hm.need_ctrl;
+      fill_tested_ctrl<decltype(md), N>(hm, md);
       if (lean && io.gu == nullptr) {
         auto kern = mc_chisquare_kernel<N, M, VanillaTested<N, M>, true, true>;
         *grid_out = grid = pick_grid(kern, smem, io.trials, device);
@@ -100,9 +109,9 @@ static int launch_mc_shape_vanilla(const HostModel& hm, const McIo& io, int devi
       }
 }
 
-int launch_mc_vanilla(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+int launch_mc_vanilla(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
-  if (hm.n == NN && hm.m == MM) return launch_mc_shape_vanilla<NN, MM>(hm, io, device, grid_out, s);
+  if (hm.n == NN && hm.m == MM) return launch_mc_shape_vanilla<NN, MM>(tm, hm, io, device, grid_out, s);
   GKB_FOR_EACH_SHAPE(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
@@ -111,22 +120,22 @@ int launch_mc_vanilla(const HostModel& hm, const McIo& io, int device, int* grid
 
 #if GKB_MC_PART == 2
 template <int N, int M>
-static int launch_mc_shape_info(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+static int launch_mc_shape_info(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
   const size_t smem = sizeof(double) * (kIcdfSegments * kIcdfCoefs + kWarps * kChunk * cols);
   int grid = 1;
   const bool lean = io.noise_mode == GKB_NOISE_PHILOX && !io.want_xstats && !io.truth_x && !io.truth_y &&
-                    !io.noise_w && !io.noise_v && !io.status;
+                    !io.noise_w && !io.noise_v && !io.status && io.gu_f == io.gu;
   McModel<N, M> mm;
-  fill_mc_model<N, M>(hm, io, mm, io.P0);
+  fill_mc_model<N, M>(tm, io, mm, io.P0);
   {
       InfoModel<N, M> md;
       for (int i = 0; i < N * N; ++i) { md.Finv[i] = hm.Finv[i]; md.Qinv[i] = hm.Qinv[i]; }
       for (int i = 0; i < M * M; ++i) md.Rinv[i] = hm.Rinv[i];
       md.rinv_dim = hm.rinv_dim;
-      for (int i = 0; i < N * GKB_MAX_C; ++i) md.G[i] = mm.G[i];
+      for (int i = 0; i < M * M; ++i) md.R[i] = hm.R[i];
       for (int i = 0; i < M * N; ++i) md.H[i] = hm.H[i];
-      md.c = hm.c; md.need_ctrl = hm.need_ctrl;
+      fill_tested_ctrl<decltype(md), N>(hm, md);
       if (lean) {
         auto kern = mc_chisquare_kernel<N, M, InfoTested<N, M>, true>;
         *grid_out = grid = pick_grid(kern, smem, io.trials, device);
@@ -140,9 +149,9 @@ static int launch_mc_shape_info(const HostModel& hm, const McIo& io, int device,
       }
 }
 
-int launch_mc_info(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+int launch_mc_info(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
-  if (hm.n == NN && hm.m == MM) return launch_mc_shape_info<NN, MM>(hm, io, device, grid_out, s);
+  if (hm.n == NN && hm.m == MM) return launch_mc_shape_info<NN, MM>(tm, hm, io, device, grid_out, s);
   GKB_FOR_EACH_SHAPE(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
@@ -151,21 +160,20 @@ int launch_mc_info(const HostModel& hm, const McIo& io, int device, int* grid_ou
 
 #if GKB_MC_PART == 3
 template <int N, int M>
-static int launch_mc_shape_sqrt(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+static int launch_mc_shape_sqrt(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
   const size_t smem = sizeof(double) * (kIcdfSegments * kIcdfCoefs + kWarps * kChunk * cols);
   int grid = 1;
   const bool lean = io.noise_mode == GKB_NOISE_PHILOX && !io.want_xstats && !io.truth_x && !io.truth_y &&
-                    !io.noise_w && !io.noise_v && !io.status;
+                    !io.noise_w && !io.noise_v && !io.status && io.gu_f == io.gu;
   McModel<N, M> mm;
-  fill_mc_model<N, M>(hm, io, mm, io.P0);
+  fill_mc_model<N, M>(tm, io, mm, io.P0);
   {
       SqrtModel<N, M> md;
       for (int i = 0; i < N * N; ++i) { md.F[i] = hm.F[i]; md.sqrtQ[i] = hm.sqrtQ[i]; }
       for (int i = 0; i < M * M; ++i) md.sqrtR[i] = hm.sqrtR[i];
-      for (int i = 0; i < N * GKB_MAX_C; ++i) md.G[i] = mm.G[i];
       for (int i = 0; i < M * N; ++i) md.H[i] = hm.H[i];
-      md.c = hm.c; md.need_ctrl = hm.need_ctrl;
+      fill_tested_ctrl<decltype(md), N>(hm, md);
       if (lean) {
         auto kern = mc_chisquare_kernel<N, M, SqrtTested<N, M>, true>;
         *grid_out = grid = pick_grid(kern, smem, io.trials, device);
@@ -179,9 +187,9 @@ static int launch_mc_shape_sqrt(const HostModel& hm, const McIo& io, int device,
       }
 }
 
-int launch_mc_sqrt(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+int launch_mc_sqrt(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
-  if (hm.n == NN && hm.m == MM) return launch_mc_shape_sqrt<NN, MM>(hm, io, device, grid_out, s);
+  if (hm.n == NN && hm.m == MM) return launch_mc_shape_sqrt<NN, MM>(tm, hm, io, device, grid_out, s);
   GKB_FOR_EACH_SHAPE(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
@@ -195,17 +203,26 @@ int mc_max_grid(int device) {
   return sms * kMcMaxCtasPerSm;
 }
 
-int launch_mc_vanilla(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
-int launch_mc_info(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
-int launch_mc_sqrt(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_vanilla(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_info(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_sqrt(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
 
-int launch_mc(const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+int launch_mc(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   switch (hm.kind) {
-    case GKB_VANILLA: return launch_mc_vanilla(hm, io, device, grid_out, s);
-    case GKB_INFORMATION: return launch_mc_info(hm, io, device, grid_out, s);
-    case GKB_SQRT: return launch_mc_sqrt(hm, io, device, grid_out, s);
+    case GKB_VANILLA: return launch_mc_vanilla(tm, hm, io, device, grid_out, s);
+    case GKB_INFORMATION: return launch_mc_info(tm, hm, io, device, grid_out, s);
+    case GKB_SQRT: return launch_mc_sqrt(tm, hm, io, device, grid_out, s);
     default: return GKB_ERR_UNSUPPORTED;
   }
+}
+
+int mc_shape_supported(int kind, int n, int m) {
+  if (kind != GKB_VANILLA && kind != GKB_INFORMATION && kind != GKB_SQRT) return 0;
+#define GKB_CASE(NN, MM) \
+  if (n == NN && m == MM) return 1;
+  GKB_FOR_EACH_SHAPE(GKB_CASE)
+#undef GKB_CASE
+  return 0;
 }
 
 int launch_mc_finish(const double* partial, int grid, int steps, int cols, double scale, double* out_cols,

@@ -156,7 +156,32 @@ struct InfoTested {
       for (int i = 0; i < N; ++i) q = fma(e[i], t[i], q);
       nees = q;
     }
-    if (with_nis) nis = 0.0;  // Innovation() is the n-vector i+: the reference's NIS product panics unless n == m
+    if (with_nis) {
+      // chisquare.go:61-77 with est.Innovation() = i+ (information.go:272-274): the product Pyy^-1 i+ only has
+      // matching dimensions when n == m (the host rejects NIS for every other shape, as mat64 would panic)
+      if constexpr (N == M) {
+        double Pp[N * N], PHt[N * M], Pyy[M * M], t[M];
+        info_covariance<N>(Pp, o.Ipred);  // PredCovariance() = inv(I-), zeros when not invertible
+        mul_nt<N, N, M>(PHt, Pp, md.H);
+#pragma unroll
+        for (int a = 0; a < M; ++a)
+#pragma unroll
+          for (int b = 0; b < M; ++b) {
+            double s2 = md.H[a * N] * PHt[b];
+#pragma unroll
+            for (int l = 1; l < N; ++l) s2 = fma(md.H[a * N + l], PHt[l * M + b], s2);
+            Pyy[a * M + b] = s2 + md.R[a * M + b];
+          }
+        (void)inverse_lu<M>(Pyy);
+        mulvec<M, M>(t, Pyy, iv);
+        double q = 0.0;
+#pragma unroll
+        for (int a = 0; a < M; ++a) q = fma(iv[a], t[a], q);
+        nis = q;
+      } else {
+        nis = 0.0;
+      }
+    }
     return 0;
   }
 };
@@ -320,6 +345,14 @@ mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_con
 #pragma unroll
           for (int i = 0; i < N; ++i) gu[i] = __ldg(io.gu + (int64_t)k * N + i);
         }
+        // the tested filter's own control term (its G may differ from the truth's; LEAN runs share one stream)
+        double guf[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) guf[i] = gu[i];
+        if (!LEAN && io.gu_f != io.gu) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) guf[i] = io.gu_f ? __ldg(io.gu_f + (int64_t)k * N + i) : 0.0;
+        }
         // ---- truth: pure-predictor Vanilla.Update (vanilla.go:138-179): measurement from the
         //      PREVIOUS state, then the state advances (montecarlo.go:110-113)
         double yt[M];
@@ -363,7 +396,7 @@ mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_con
         }
         // ---- tested filter + chi-square samples (chisquare.go:39-77)
         double nees = 0.0, nis = 0.0;
-        int err = kf.update(md, yt, gu, xt, io.with_nees != 0, io.with_nis != 0, nees, nis);
+        int err = kf.update(md, yt, guf, xt, io.with_nees != 0, io.with_nis != 0, nees, nis);
         if (err != 0) {
           if (status == 0) status = err;
           nees = 0.0;

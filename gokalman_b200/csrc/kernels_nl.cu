@@ -9,6 +9,7 @@
 
 #include "engine_internal.h"
 #include "filters_nl.cuh"
+#include "filters_strict.cuh"
 
 namespace gkb {
 
@@ -92,6 +93,62 @@ hybrid_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constan
   for (int i = 0; i < N; ++i)
 #pragma unroll
     for (int j = 0; j < N; ++j) io.mat[(int64_t)(i * N + j) * io.nf + tid] = P[sym_idx<N>(i, j)];
+  if (io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
+}
+
+// The same run in REFERENCE-ORDER arithmetic (filters_strict.cuh: dense products in the written order, no FMA
+// contraction, dense Joseph form, AsSymDense): the validation twin of hybrid_run_kernel, selected per handle with
+// gkb_set_strict().  Every call shape of the general kernel is supported (every-step outputs, SNC, shared streams).
+template <int N, int M>
+__global__ void __launch_bounds__(kThreads)
+hybrid_run_strict_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant__ NlIo io) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= io.nf) return;
+  double x[N], P[N * N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = io.vec[(int64_t)i * io.nf + tid];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j)  // the stored matrix is the mirrored upper triangle (AsSymDense)
+      P[i * N + j] = io.mat[(int64_t)((i <= j) ? (i * N + j) : (j * N + i)) * io.nf + tid];
+  int status = 0;
+  for (int k = 0; k < io.steps; ++k) {
+    const unsigned fl = io.flags ? io.flags[k] : (unsigned)GKB_F_MEAS;
+    const bool has_meas = (fl & GKB_F_MEAS) != 0, ekf = (fl & GKB_F_EKF) != 0, snc = (fl & GKB_F_SNC) != 0;
+    double Phi[N * N], Ht[M * N], ro[M], co[M];
+    nl_load<N * N>(Phi, io.Phi, io.phi_shared, k, io.nf, tid);
+    if (has_meas) {
+      nl_load<M * N>(Ht, io.Htilde, io.h_shared, k, io.nf, tid);
+      nl_load<M>(ro, io.real_obs, 0, k, io.nf, tid);
+      nl_load<M>(co, io.computed_obs, 0, k, io.nf, tid);
+    } else {
+#pragma unroll
+      for (int i = 0; i < M * N; ++i) Ht[i] = 0.0;
+#pragma unroll
+      for (int a = 0; a < M; ++a) { ro[a] = 0.0; co[a] = 0.0; }
+    }
+    double Ppred[N * N], K[N * M], innov[M], obsdev[M];
+    const double* Gk = (snc && io.Gamma) ? io.Gamma + (int64_t)k * N * md.q : nullptr;
+    int err = strict::hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, Gk, has_meas, ekf, snc, Ppred, K, innov, obsdev);
+    if (err != 0) {
+      if (status == 0) status = err;
+      continue;
+    }
+    if (io.every_step || k == io.steps - 1) {
+      nl_out<N>(io.o_state, k, io.every_step, x, io.nf, tid);
+      nl_out<M>(io.o_meas, k, io.every_step, ro, io.nf, tid);
+      nl_out<M>(io.o_innov, k, io.every_step, innov, io.nf, tid);
+      nl_out<M>(io.o_obsdev, k, io.every_step, obsdev, io.nf, tid);
+      nl_out<N * M>(io.o_gain, k, io.every_step, K, io.nf, tid);
+      nl_out<N * N>(io.o_covar, k, io.every_step, P, io.nf, tid);
+      nl_out<N * N>(io.o_pred, k, io.every_step, Ppred, io.nf, tid);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) io.vec[(int64_t)i * io.nf + tid] = x[i];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) io.mat[(int64_t)i * io.nf + tid] = P[i];
   if (io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
 }
 
@@ -399,6 +456,10 @@ static int launch_nl_shape(const HostModel& hm, const NlIo& io, cudaStream_t s) 
   md.q = hm.q;
   const bool srif = hm.kind == GKB_SRIF;
   if (hm.kind != GKB_HYBRID && !srif) return GKB_ERR_UNSUPPORTED;
+  if (io.strict && !srif) {  // reference-order arithmetic (gkb_set_strict): the validation twin of the kernels below
+    hybrid_run_strict_kernel<N, M><<<grid, kThreads, 0, s>>>(md, io);
+    return 0;
+  }
   // production configuration (per-filter streams, final outputs only): the TMA kernels of kernels_nl_tma.cu
   if (launch_nl_tma(hm, io, s) == 0) return 0;
   if (srif) {

@@ -113,6 +113,13 @@ int gkb_reset(gkb_filter* f);
 /* Stream the handle's kernels and copies are enqueued on (a cudaStream_t; NULL = the legacy
  * default stream, which is the default). */
 int gkb_set_stream(gkb_filter* f, void* stream);
+/* Reference-order ("strict") arithmetic for a GKB_HYBRID handle: every product of hybrid.go:114-182 as a full
+ * dense product in the written order, no fused multiply-adds (Go on amd64 never fuses), IEEE divisions, the
+ * dense Joseph form and AsSymDense (GKB_ERR_ASYMMETRIC can be raised in this mode) -- the arithmetic the
+ * reference itself executes, at a fraction of the production kernels' speed.  For validation: the fast kernels
+ * restructure the Joseph update and use FMAs, which moves ill-conditioned runs (statOD: R = 1e-6 against
+ * P0 = 10) by more than 1e-10.  on = 0 (default) selects the production kernels. */
+int gkb_set_strict(gkb_filter* f, int on);
 int64_t gkb_n_filters(const gkb_filter* f);
 /* 1 when the handle's per-filter arrays are filter-major [N][C] (large-state handles), 0 for SoA [C][N]. */
 int gkb_filter_major(const gkb_filter* f);
@@ -205,7 +212,8 @@ typedef enum gkb_noise_mode {
 typedef struct gkb_mc_config {
   int kind;               /* tested filter: GKB_VANILLA, GKB_INFORMATION (from state) or GKB_SQRT */
   int n, m, c;
-  const double *F, *G, *H, *Q, *R; /* host; model shared by the truth generator and the filter   */
+  const double *F, *G, *H, *Q, *R; /* host; the TRUTH generator's model (and the tested filter's too
+                                      unless filter_* below are given)                            */
   const double* x0_truth; /* [n]                                                                */
   const double* x0_filter;/* [n]                                                                */
   const double* P0;       /* [n*n]                                                              */
@@ -221,6 +229,11 @@ typedef struct gkb_mc_config {
   int info_raw_init;      /* GKB_INFORMATION only: x0_filter / P0 already are (i0, I0) as given to
                              NewInformation, instead of (x0, P0) as given to NewInformationFromState */
   int device;
+  /* The tested filter's OWN model -- NewChiSquare takes any LDKF (chisquare.go:16,39) with its own F / G / H and
+   * its own Noise (Q, R), e.g. a deliberately mis-tuned Q against a fixed truth.  Each pointer: host, same
+   * shape as the truth generator's matrix above, or NULL = identical to it.  F, G, H, Q, R above are the pure
+   * predictor's (montecarlo.go:92) and colour the truth's AWGN; NIS uses the tested H and R (chisquare.go:64-66). */
+  const double *filter_F, *filter_G, *filter_H, *filter_Q, *filter_R;
 } gkb_mc_config;
 
 typedef struct gkb_mc_outputs {

@@ -1127,6 +1127,12 @@ int gko_mc_chisquare(const gko_mc_config* cfg, double* nis_means, double* nees_m
   }
   int rc = 0;
   int nthreads = cfg->threads > 1 ? cfg->threads : 1;
+  /* the tested filter's own model (chisquare.go:16: any LDKF) */
+  const double* tF = cfg->tF ? cfg->tF : cfg->F;
+  const double* tG = cfg->tG ? cfg->tG : cfg->G;
+  const double* tH = cfg->tH ? cfg->tH : cfg->H;
+  const double* tQ = cfg->tQ ? cfg->tQ : cfg->Q;
+  const double* tR = cfg->tR ? cfg->tR : cfg->R;
 #ifdef _OPENMP
 #pragma omp parallel num_threads(nthreads)
 #endif
@@ -1137,14 +1143,13 @@ int gko_mc_chisquare(const gko_mc_config* cfg, double* nis_means, double* nees_m
     gko_filter* kf = NULL;
     switch (cfg->kind) {
       case GKO_VANILLA:
-        kf = gko_new_vanilla(n, m, c, cfg->x0_filter, cfg->P0, cfg->F, cfg->G, cfg->H, cfg->Q, cfg->R, 0);
+        kf = gko_new_vanilla(n, m, c, cfg->x0_filter, cfg->P0, tF, tG, tH, tQ, tR, 0);
         break;
       case GKO_INFORMATION:
-        kf = gko_new_information_from_state(n, m, c, cfg->x0_filter, cfg->P0, cfg->F, cfg->G, cfg->H,
-                                            cfg->Q, cfg->R);
+        kf = gko_new_information_from_state(n, m, c, cfg->x0_filter, cfg->P0, tF, tG, tH, tQ, tR);
         break;
       case GKO_SQRT:
-        kf = gko_new_sqrt(n, m, c, cfg->x0_filter, cfg->P0, cfg->F, cfg->G, cfg->H, cfg->Q, cfg->R);
+        kf = gko_new_sqrt(n, m, c, cfg->x0_filter, cfg->P0, tF, tG, tH, tQ, tR);
         break;
     }
     gko_estimate* te = (gko_estimate*)malloc(sizeof(gko_estimate));
@@ -1205,10 +1210,10 @@ int gko_mc_chisquare(const gko_mc_config* cfg, double* nis_means, double* nees_m
           nees_s[(size_t)k * trials + s] = v;
         }
         if (nis_s) { /* 61-77 */
-          gko_transpose(Ht, cfg->H, m, n);
+          gko_transpose(Ht, tH, m, n); /* kf.GetMeasurementMatrix(), kf.GetNoise().MeasurementMatrix(): 64-66 */
           gko_mul(Pyy0, fe->pred_covar, Ht, n, n, m);
-          gko_mul(Pyy, cfg->H, Pyy0, m, n, m);
-          for (int i = 0; i < m * m; ++i) Pyy[i] = Pyy[i] + cfg->R[i];
+          gko_mul(Pyy, tH, Pyy0, m, n, m);
+          for (int i = 0; i < m * m; ++i) Pyy[i] = Pyy[i] + tR[i];
           gko_inverse(Pyy, Pyy, m, NULL);
           gko_mulvec(t2, Pyy, fe->innov, m, m);
           double v = 0.0;

@@ -151,6 +151,9 @@ typedef struct gko_mc_config {
   int64_t trial_offset;
   int with_nees, with_nis;
   int threads;                /* OpenMP threads over trials; <= 1 = serial like the reference  */
+  /* The tested filter's OWN model (chisquare.go:16 takes any LDKF: its F/G/H and its Noise's Q/R), each NULL =
+   * the same matrix as the truth generator's above.  NIS uses the tested filter's H and R (chisquare.go:64-66). */
+  const double *tF, *tG, *tH, *tQ, *tR;
 } gko_mc_config;
 
 /* Returns 0 or an error code.  nis_means / nees_means are [steps] (chisquare.go:94 returns them

@@ -75,6 +75,7 @@ class McConfig(C.Structure):
         ("controls", C.c_void_p), ("w", C.c_void_p), ("v", C.c_void_p),
         ("seed", C.c_uint64), ("trial_offset", C.c_int64),
         ("with_nees", C.c_int), ("with_nis", C.c_int), ("threads", C.c_int),
+        ("tF", C.c_void_p), ("tG", C.c_void_p), ("tH", C.c_void_p), ("tQ", C.c_void_p), ("tR", C.c_void_p),
     ]
 
 
@@ -427,8 +428,10 @@ def philox_normals(seed, trial, step, count):
 
 def mc_chisquare(kind, F, G, H, Q, R, x0_truth, x0_filter, P0, trials, steps, controls=None, w=None, v=None,
                  seed=0, trial_offset=0, with_nees=True, with_nis=True, threads=1, want_stats=False,
-                 want_truth=False):
-    """montecarlo.go NewMonteCarloRuns + chisquare.go NewChiSquare. Returns dict with NIS/NEES means."""
+                 want_truth=False, tested=None):
+    """montecarlo.go NewMonteCarloRuns + chisquare.go NewChiSquare. Returns dict with NIS/NEES means.
+    tested: optional dict with the tested filter's OWN F / G / H / Q / R (chisquare.go:16 takes any LDKF); a
+    missing key = the truth generator's matrix."""
     F, G, H, n, m, c = _dims(F, G, H)
     keep = [F, G, H, _a(Q), np.atleast_2d(_a(R)), _a(x0_truth), _a(x0_filter), _a(P0), _a(controls), _a(w), _a(v)]
     cfg = McConfig()
@@ -438,6 +441,11 @@ def mc_chisquare(kind, F, G, H, Q, R, x0_truth, x0_filter, P0, trials, steps, co
     cfg.trials, cfg.steps = trials, steps
     cfg.seed, cfg.trial_offset = seed, trial_offset
     cfg.with_nees, cfg.with_nis, cfg.threads = int(with_nees), int(with_nis), threads
+    for key in ("F", "G", "H", "Q", "R"):
+        a = None if not tested or tested.get(key) is None else np.atleast_2d(_a(tested[key]))
+        if a is not None:
+            keep.append(a)
+            setattr(cfg, "t" + key, a.ctypes.data)
     nis, nees = np.zeros(steps), np.zeros(steps)
     mean = np.zeros((steps, n)) if want_stats else None
     std = np.zeros((steps, n)) if want_stats else None

@@ -43,7 +43,11 @@ def test_mc_full_size_shard_sums_add_up():
     assert 0.9 < nis.mean() / trials < 1.1 and 2.5 < nees.mean() / trials < 3.5
 
 
-def test_hybrid_full_size_subset_matches_oracle(oracle):
+def test_hybrid_full_size_production_vs_oracle_labelled_bar(oracle):
+    """PRODUCTION kernel (FMA, packed P, restructured Joseph) on the full-size statOD run against the oracle.  The
+    parity bar proper (plain 1e-10) is held by the STRICT kernel in test_gpu_strict.py; the bar here is explicitly a
+    "production-vs-reference-rounding" bar: max(1e-10, 8 x the spread the reference's own formulas show on the same
+    filter between unfused and fused evaluation)."""
     import torch
     import gokalman_b200 as gk
     from gokalman_b200 import _lib as L
@@ -95,8 +99,8 @@ def test_hybrid_full_size_subset_matches_oracle(oracle):
 def test_srif_full_size_subset_matches_oracle(oracle):
     """configs[3], SRIF arm: 10^5 filters x 200 measurement epochs through the production kernel (the speculative
     straight-line epoch on the packed triangular R, srif_step_tri), eight filters cut out and replayed through the
-    oracle.  Same calibrated bar as the hybrid run above: 1e-10, or 8x the reference formulas' own FMA sensitivity
-    on that filter where the statOD streams make 1e-10 unattainable for any fused arithmetic."""
+    oracle at the PLAIN 1e-10 (the square-root form does not share the hybrid's cancellation: observed <= 2e-14); the
+    reference formulas' own fused-vs-unfused spread is printed next to it."""
     import torch
     import gokalman_b200 as gk
     from gokalman_b200 import _lib as L
@@ -135,8 +139,8 @@ def test_srif_full_size_subset_matches_oracle(oracle):
         sens = max(fx.scaled_err(xf[:, j], xr[:, j]), fx.scaled_err(Pf[:, j], Pr[:, j]))
         ex, eP = fx.scaled_err(got_x[:, j], xr[:, j]), fx.scaled_err(got_P[:, j], Pr[:, j])
         report.append((pick[j], ex, eP, sens))
-        assert ex <= max(TOL, 8 * sens), report
-        assert eP <= max(TOL, 8 * sens), report
+        assert ex <= TOL, report
+        assert eP <= TOL, report
     print("srif full size (filter, err x, err P, reference FMA sensitivity):", report)
 
 

@@ -101,7 +101,7 @@ def _compare(est_gpu, ests_ref, fields, tag):
             ref = np.stack([np.asarray(getattr(ests_ref[f][k], getters[fld])()) for k in range(steps)])
             got = g[..., f] if nf > 1 else g
             got = got.reshape(ref.shape)
-            err = fx.scaled_err(got, ref)
+            err = fx.scaled_err_steps(got, ref)  # every step scaled by its own max-abs
             assert err <= TOL, (tag, fld, f, err)
 
 

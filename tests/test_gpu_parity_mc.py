@@ -195,3 +195,80 @@ def test_chisquare_errors_mirror_reference():
         gk.NewChiSquare(notpred, runs, [np.zeros(1), np.zeros(1)], True, False)
     nis, nees = gk.NewChiSquare(notpred, runs, [np.zeros(1)], True, True)
     assert len(nis) == len(nees) == 10
+
+
+@pytest.mark.parametrize("kind", ["vanilla", "information", "sqrt"])
+def test_chisquare_tested_filter_carries_its_own_model(oracle, kind):
+    """chisquare.go:16-42,64-66: NewChiSquare runs ANY LDKF -- with its own F / G / H and its own Noise -- on the
+    stored truth.  Here the truth is the robot model and the tested filter is deliberately mis-tuned: Q ten times
+    too small, a slightly wrong F, another G, a scaled H row and another R.  The GPU must (a) equal the oracle
+    running the same two-model experiment to 1e-10 and (b) differ visibly from the matched-filter statistics
+    (that difference is what NEES / NIS exist to show)."""
+    gk = _gpu()
+    f = _robot()
+    steps, trials = 100, 400
+    controls = list(fx.robot_controls(steps))
+    tF = f["F"] + np.array([[0.0, 0.01], [0.0, -0.02]])
+    tG = 0.9 * f["G"]
+    tH = np.array([[1.05, 0.0]])
+    tQ, tR = 0.1 * f["Q"], np.array([[0.08]])
+    mckf, _ = gk.NewPurePredictorVanilla(f["x0_truth"], f["P0"], f["F"], f["G"], f["H"], gk.NewAWGN(f["Q"], f["R"], seed=77))
+    ctor = {"vanilla": gk.NewVanilla, "information": gk.NewInformationFromState, "sqrt": gk.NewSquareRoot}[kind]
+    tested, _ = ctor(f["x0"], f["P0"], tF, tG, tH, gk.NewNoiseless(tQ, tR))
+    matched, _ = ctor(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewNoiseless(f["Q"], f["R"]))
+    runs = gk.NewMonteCarloRuns(trials, steps, 1, controls, mckf)
+    with_nis = kind != "information"
+    nis, nees = gk.NewChiSquare(tested, runs, controls, True, with_nis)
+    nis_m, nees_m = gk.NewChiSquare(matched, runs, controls, True, with_nis)
+    tx, ty, w, v = runs.Truth(with_noise=True)
+    okind = {"vanilla": oracle.VANILLA, "information": oracle.INFORMATION, "sqrt": oracle.SQRT}[kind]
+    ref = oracle.mc_chisquare(okind, f["F"], f["G"], f["H"], f["Q"], f["R"], f["x0_truth"], f["x0"], f["P0"], trials, steps,
+                              controls=np.stack(controls), w=np.ascontiguousarray(w.transpose(2, 0, 1)),
+                              v=np.ascontiguousarray(v.transpose(2, 0, 1)), with_nees=True, with_nis=with_nis,
+                              tested=dict(F=tF, G=tG, H=tH, Q=tQ, R=tR), want_truth=True)
+    # the truth is the PREDICTOR's trajectory (its own Q / R colour the noise), whatever the tested filter carries
+    assert fx.scaled_err(tx, ref["truth_x"].transpose(1, 2, 0)) <= TOL
+    assert fx.scaled_err(nees, ref["NEES"]) <= TOL, fx.scaled_err(nees, ref["NEES"])
+    if with_nis:
+        assert fx.scaled_err(nis, ref["NIS"]) <= TOL, fx.scaled_err(nis, ref["NIS"])
+    # the mis-tuned filter is visibly inconsistent: its NEES is far from the matched filter's (and from n = 2)
+    assert np.mean(nees[20:]) > 1.5 * np.mean(nees_m[20:]), (np.mean(nees[20:]), np.mean(nees_m[20:]))
+    if with_nis:
+        assert abs(np.mean(nis[20:]) - np.mean(nis_m[20:])) > 0.1
+
+
+def test_chisquare_information_nis_when_n_equals_m(oracle):
+    """chisquare.go:61-77 with an information filter: Innovation() is the n-vector i+ (information.go:272-274), so
+    the NIS product only has matching dimensions when n == m; then it is i+^T inv(H inv(I-) H^T + R) i+."""
+    gk = _gpu()
+    rng = np.random.default_rng(12)
+    n = m = 2
+    F = np.array([[1.0, 0.1], [-0.05, 0.98]])
+    H = np.array([[1.0, 0.2], [0.0, 1.0]])
+    Q, R = np.array([[2e-2, 1e-3], [1e-3, 1e-2]]), np.array([[0.05, 0.01], [0.01, 0.08]])
+    x0, P0 = np.array([0.3, -0.2]), np.diag([2.0, 1.0])
+    steps, trials = 60, 200
+    mckf, _ = gk.NewPurePredictorVanilla(x0, P0, F, None, H, gk.NewAWGN(Q, R, seed=5))
+    kf, _ = gk.NewInformationFromState(x0, P0, F, None, H, gk.NewNoiseless(Q, R))
+    runs = gk.NewMonteCarloRuns(trials, steps, m, None, mckf)
+    nis, nees = gk.NewChiSquare(kf, runs, None, True, True)
+    _, _, w, v = runs.Truth(with_noise=True)
+    ref = oracle.mc_chisquare(oracle.INFORMATION, F, None, H, Q, R, x0, x0, P0, trials, steps,
+                              w=np.ascontiguousarray(w.transpose(2, 0, 1)), v=np.ascontiguousarray(v.transpose(2, 0, 1)))
+    assert np.all(nis > 0)
+    assert fx.scaled_err(nees, ref["NEES"]) <= TOL, fx.scaled_err(nees, ref["NEES"])
+    assert fx.scaled_err(nis, ref["NIS"]) <= TOL, fx.scaled_err(nis, ref["NIS"])
+
+
+def test_chisquare_failed_update_is_reported():
+    """chisquare.go:40-42: the reference panics when the tested filter's Update returns an error.  A tested filter
+    with P0 = 0, Q = 0, R = 0 has S = H P- H^T + R = 0 at the first step (vanilla.go:164-167): the call must raise,
+    not return silently biased means."""
+    gk = _gpu()
+    f = _jerk3()
+    mckf, _ = gk.NewPurePredictorVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewAWGN(f["Q"], f["R"], seed=3))
+    bad, _ = gk.NewVanilla(f["x0"], np.zeros((3, 3)), f["F"], f["G"], f["H"], gk.NewNoiseless(np.zeros((3, 3)), np.zeros((1, 1))))
+    runs = gk.NewMonteCarloRuns(64, 10, 1, [np.zeros(1)], mckf)
+    with pytest.raises(gk.GkbError) as ei:
+        gk.NewChiSquare(bad, runs, [np.zeros(1)], True, True)
+    assert ei.value.code == -2
