@@ -46,6 +46,12 @@ class McConfig(C.Structure):
                 ("filter_R", C.c_void_p)]
 
 
+class OdConfig(C.Structure):
+    _fields_ = [("mu", C.c_double), ("j2", C.c_double), ("re", C.c_double), ("dt", C.c_double),
+                ("orbit0", C.c_void_p), ("orbit_mem", C.c_int), ("station", C.c_void_p), ("truth_obs", C.c_void_p),
+                ("sigma_range", C.c_double), ("sigma_rate", C.c_double), ("seed", C.c_uint64), ("filter_offset", C.c_int64)]
+
+
 class McOutputs(C.Structure):
     _fields_ = [("mem", C.c_int), ("sums_only", C.c_int),
                 ("nis", C.c_void_p), ("nees", C.c_void_p), ("sum_d", C.c_void_p), ("sum_dd", C.c_void_p), ("x_ref", C.c_void_p),
@@ -78,6 +84,8 @@ SYMBOLS = [
     ("gkb_step", _i, [_vp]),
     ("gkb_update", _i, [_vp, _i, _vp, _i, _vp, _i, C.POINTER(Outputs)]),
     ("gkb_nl_run", _i, [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(Outputs)]),
+    ("gkb_od_synthesize", _i, [C.POINTER(OdConfig), _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    ("gkb_od_run", _i, [_vp, C.POINTER(OdConfig), _i, _vp, C.POINTER(Outputs)]),
     ("gkb_get_state", _i, [_vp, _vp, _vp]),
     ("gkb_set_state", _i, [_vp, _vp, _vp]),
     ("gkb_smooth_all", _i, [_i, _i, _i64, _i, _vp, _i, _vp, _vp, _i, _vp]),

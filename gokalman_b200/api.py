@@ -632,6 +632,20 @@ class HybridKF(_NLDKF):
         dense Joseph form -- the validation twin of the production kernels."""
         _lib.check(_lib.load().gkb_set_strict(self._h, int(bool(on))))
 
+    def RunOD(self, scenario, orbit0, sigma_range, sigma_rate, seed, flags=None, every_step=False, filter_offset=0):
+        """The fused OD run (gkb_od_run): per epoch the reference orbit / STM / range + range-rate partials /
+        observations of every filter are computed on the device (gokalman_b200.od.Scenario holds the per-epoch
+        station and truth tables) and consumed by Prepare + Update / Predict in the same kernel.  orbit0:
+        [6, n_filters] initial reference orbits, or None to continue from the orbits the handle holds.
+        Returns the batched Estimate (State / Covariance, final or every epoch)."""
+        steps = scenario.steps
+        flags = scenario.flags if flags is None else np.ascontiguousarray(np.asarray(flags, dtype=np.uint8))
+        cfg = scenario.config(orbit0, sigma_range, sigma_rate, seed, filter_offset)
+        out, fields, status = self._alloc_out(steps, every_step, ("state", "covar"), self._m)
+        _lib.check(_lib.load().gkb_od_run(self._h, C.byref(cfg), steps, flags.ctypes.data, C.byref(out)))
+        self._raise_status(status)
+        return Estimate(self._n, self._m, fields, status)
+
     def SetNoise(self, n):
         Q, R = _mat(n.ProcessMatrix()), _mat(n.MeasurementMatrix())
         _lib.check(_lib.load().gkb_set_noise(self._h, _ptr(Q), R.shape[0], _ptr(R)))

@@ -178,6 +178,8 @@ struct gkb_filter {
   bool tile = false;
   DevBuf tile_model;  // F [n*n], Q [n*n], H [8][n], R [8][8]
   DevBuf sched;       // NLDKF production kernel: task counter + one flag per group of 32 filters
+  DevBuf orbit, od_tab;  // gkb_od_run: reference orbits [6][nf]; per-epoch station + truth-observation tables
+  bool has_orbit = false;
 };
 
 extern "C" {
@@ -251,7 +253,7 @@ static int finish_create(gkb_filter* f, const double* x0, int x0_per_filter, con
 static void destroy_filter(gkb_filter* f) {
   if (!f) return;
   cudaSetDevice(f->device);
-  DevBuf* bufs[] = {&f->sched, &f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
+  DevBuf* bufs[] = {&f->orbit, &f->od_tab, &f->sched, &f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
                     &f->in_a, &f->in_b, &f->in_c, &f->in_d, &f->in_e, &f->in_f, &f->o_state, &f->o_meas, &f->o_innov,
                     &f->o_covar, &f->o_pred, &f->o_gain, &f->o_obsdev};
   for (DevBuf* b : bufs) b->release();
@@ -855,6 +857,121 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
   GKB_CUDA(cudaGetLastError());
   f->step += steps;
   if ((rc = copy_back(f, out, pl))) return rc;
+  if (sync) GKB_CUDA(cudaStreamSynchronize(f->stream));
+  return 0;
+}
+
+// ---- orbit-determination inputs on the device ---------------------------------------------------------------
+namespace {
+int od_params(const gkb_od_config* cfg, OdParams& c) {
+  if (!cfg) return fail(GKB_ERR_ARG, "NULL OD configuration");
+  if (!(cfg->mu > 0.0) || !(cfg->dt > 0.0) || !(cfg->re >= 0.0)) return fail(GKB_ERR_ARG, "OD configuration: mu, dt must be > 0");
+  if (!cfg->station || !cfg->truth_obs) return fail(GKB_ERR_ARG, "OD configuration: station / truth_obs tables are NULL");
+  c.mu = cfg->mu;
+  c.kj2 = 1.5 * cfg->j2 * cfg->mu * cfg->re * cfg->re;
+  c.h = cfg->dt;
+  c.sigma[0] = cfg->sigma_range;
+  c.sigma[1] = cfg->sigma_rate;
+  c.seed = cfg->seed;
+  c.filter_offset = cfg->filter_offset;
+  return 0;
+}
+}  // namespace
+
+int gkb_od_synthesize(const gkb_od_config* cfg, int steps, int64_t n_filters, int device, double* Phi, double* Htilde,
+                      double* real_obs, double* computed_obs, int mem, double* orbit_out) {
+  OdParams c;
+  int rc = od_params(cfg, c);
+  if (rc) return rc;
+  if (!cfg->orbit0 || !Phi || !Htilde || !real_obs || !computed_obs) return fail(GKB_ERR_ARG, "NULL argument");
+  if (steps < 1 || n_filters < 1) return fail(GKB_ERR_ARG, "steps and n_filters must be >= 1");
+  if ((rc = check_device(device))) return rc;
+  cudaStream_t s = cudaStreamLegacy;
+  const size_t ob = sizeof(double) * 6 * (size_t)n_filters, tb = sizeof(double) * 8 * (size_t)steps;
+  const size_t per = sizeof(double) * (size_t)steps * n_filters;
+  DevBuf dorb, dtab, dphi, dh, dr, dc;
+  auto cleanup = [&]() { dorb.release(); dtab.release(); dphi.release(); dh.release(); dr.release(); dc.release(); };
+  if ((rc = dorb.ensure(ob)) || (rc = dtab.ensure(tb))) { cleanup(); return rc; }
+  cudaMemcpyAsync(dorb.p, cfg->orbit0, ob, cfg->orbit_mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dtab.p, cfg->station, sizeof(double) * 6 * (size_t)steps, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dtab.as<double>() + 6 * (size_t)steps, cfg->truth_obs, sizeof(double) * 2 * (size_t)steps, cudaMemcpyHostToDevice, s);
+  double *pphi = Phi, *ph = Htilde, *pr = real_obs, *pc = computed_obs;
+  if (mem != GKB_DEVICE) {
+    if ((rc = dphi.ensure(per * 36)) || (rc = dh.ensure(per * 12)) || (rc = dr.ensure(per * 2)) || (rc = dc.ensure(per * 2))) { cleanup(); return rc; }
+    pphi = dphi.as<double>(); ph = dh.as<double>(); pr = dr.as<double>(); pc = dc.as<double>();
+  }
+  Timer tm(s);
+  launch_od_synth(c, n_filters, steps, dorb.as<double>(), dtab.as<double>(), dtab.as<double>() + 6 * (size_t)steps, pphi, ph, pr, pc, s);
+  tm.stop(1, true);
+  if (mem != GKB_DEVICE) {
+    cudaMemcpyAsync(Phi, pphi, per * 36, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(Htilde, ph, per * 12, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(real_obs, pr, per * 2, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(computed_obs, pc, per * 2, cudaMemcpyDeviceToHost, s);
+  }
+  if (orbit_out) cudaMemcpyAsync(orbit_out, dorb.p, ob, mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);  // the scratch tables are freed below: always complete the work first
+  cleanup();
+  if (e != cudaSuccess) return fail(GKB_ERR_CUDA, "OD synthesis failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int gkb_od_run(gkb_filter* f, const gkb_od_config* cfg, int steps, const uint8_t* flags, const gkb_outputs* out) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  const HostModel& hm = f->hm;
+  if (hm.kind != GKB_HYBRID || hm.n != 6 || hm.m != 2)
+    return fail(GKB_ERR_UNSUPPORTED, "gkb_od_run needs a GKB_HYBRID handle with n = 6, m = 2 (position / velocity state, range + range-rate)");
+  OdParams c;
+  int rc = od_params(cfg, c);
+  if (rc) return rc;
+  if (steps < 1) return fail(GKB_ERR_ARG, "steps must be >= 1");
+  if (!cfg->orbit0 && !f->has_orbit) return fail(GKB_ERR_ARG, "gkb_od_run: no reference orbits yet (orbit0 is NULL on the first call)");
+  if (out && (out->meas || out->innov || out->pred_covar || out->gain || out->obs_dev))
+    return fail(GKB_ERR_UNSUPPORTED, "gkb_od_run writes state / covar / status only");
+  if (flags)
+    for (int k = 0; k < steps; ++k)
+      if (flags[k] & GKB_F_SNC) return fail(GKB_ERR_UNSUPPORTED, "gkb_od_run: SNC epochs are not supported");
+  if (cudaSetDevice(f->device) != cudaSuccess) return fail(GKB_ERR_CUDA, "cudaSetDevice failed");
+  const size_t ob = sizeof(double) * 6 * (size_t)f->nf;
+  if ((rc = f->orbit.ensure(ob))) return rc;
+  if (cfg->orbit0) {
+    GKB_CUDA(cudaMemcpyAsync(f->orbit.p, cfg->orbit0, ob, cfg->orbit_mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, f->stream));
+    f->has_orbit = true;
+  }
+  // per-epoch tables: station [steps][6], truth observation [steps][2], flags [steps] (after them, 8-byte aligned)
+  const size_t tb = sizeof(double) * 8 * (size_t)steps;
+  if ((rc = f->od_tab.ensure(tb + (size_t)steps + 8))) return rc;
+  double* dst = f->od_tab.as<double>();
+  GKB_CUDA(cudaMemcpyAsync(dst, cfg->station, sizeof(double) * 6 * (size_t)steps, cudaMemcpyHostToDevice, f->stream));
+  GKB_CUDA(cudaMemcpyAsync(dst + 6 * (size_t)steps, cfg->truth_obs, sizeof(double) * 2 * (size_t)steps, cudaMemcpyHostToDevice, f->stream));
+  uint8_t* dfl = nullptr;
+  if (flags) {
+    dfl = reinterpret_cast<uint8_t*>(dst + 8 * (size_t)steps);
+    GKB_CUDA(cudaMemcpyAsync(dfl, flags, (size_t)steps, cudaMemcpyHostToDevice, f->stream));
+  }
+  NlIo io;
+  memset(&io, 0, sizeof io);
+  io.nf = f->nf;
+  io.steps = steps;
+  io.vec = f->vec.as<double>();
+  io.mat = f->mat.as<double>();
+  io.flags = dfl;
+  io.strict = f->strict ? 1 : 0;
+  OutPlan pl;
+  if ((rc = plan_outputs(f, out, steps, hm.m, pl))) return rc;
+  io.every_step = out ? out->every_step : 0;
+  io.o_state = pl.state;
+  io.o_covar = pl.covar;
+  io.status = f->status.as<int32_t>();
+  const bool sync = !(out && out->mem == GKB_DEVICE);
+  Timer tm(f->stream);
+  rc = launch_od_run(hm, c, io, f->orbit.as<double>(), dst, dst + 6 * (size_t)steps, f->stream);
+  if (rc) return fail(rc, "no fused OD kernel for this handle");
+  tm.stop(1, sync);
+  GKB_CUDA(cudaGetLastError());
+  f->step += steps;
+  if ((rc = copy_back(f, out, pl))) return rc;
+  // the pageable-host table copies above are staged synchronously by the runtime, so `cfg`'s arrays may be reused
   if (sync) GKB_CUDA(cudaStreamSynchronize(f->stream));
   return 0;
 }

@@ -152,6 +152,23 @@ int launch_householder(int n, int m, int64_t count, double* A, cudaStream_t s);
 int launch_batch_solve(int n, int m, const double* R_host, int64_t nf, int steps, const double* H, int h_shared,
                        const double* real_obs, const double* computed_obs, double* xhat0, double* P0, int32_t* status,
                        cudaStream_t s);
+// Orbit-determination inputs on the device (kernels_od.cu; OdParams in od_synth.cuh).  orbit [6][nf] is read and
+// advanced; station [steps][6] and tobs [steps][2] are device tables shared by the batch.
+struct OdParams {
+  double mu;        // km^3 / s^2
+  double kj2;       // 1.5 J2 mu Re^2
+  double h;         // seconds per epoch (one RK4 step)
+  double sigma[2];  // standard deviation of the range [km] / range-rate [km/s] measurement noise
+  unsigned long long seed;
+  long long filter_offset;  // global index of this batch's filter 0 (Philox is keyed by the global index)
+};
+// rows of the per-(filter, epoch) block od_step produces, in stream order: Phi, Htilde, real, computed
+constexpr int kOdPhi = 0, kOdH = 36, kOdReal = 48, kOdComp = 50, kOdRows = 52;
+int launch_od_synth(const OdParams& c, int64_t nf, int steps, double* orbit, const double* station, const double* tobs,
+                    double* Phi, double* Ht, double* real_obs, double* comp_obs, cudaStream_t s);
+// The fused run: synthesis + hybrid CKF / EKF step per epoch, no streams in HBM (n = 6, m = 2 only).
+int launch_od_run(const HostModel& hm, const OdParams& c, const NlIo& io, double* orbit, const double* station,
+                  const double* tobs, cudaStream_t s);
 // Large-state Vanilla (kernels_tile.cu): n in {16, 24, 32}, m <= 8.
 int tile_shape_supported(int n, int m);
 int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s);

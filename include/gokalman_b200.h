@@ -165,6 +165,39 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
                const double* Htilde, int h_shared, const double* real_obs, const double* computed_obs,
                const double* Gamma, int in_mem, const gkb_outputs* out);
 
+/* ---- Orbit-determination inputs ON THE DEVICE: what the reference's callers compute with the `smd` propagator
+ *      before every Prepare(Phi, Htilde) + Update(real, computed) (hybrid_test.go:159-294: reference orbit, its
+ *      state-transition matrix, range / range-rate partials and computed observations), for a whole batch.
+ *      Per filter: a reference orbit (ECI r [km], v [km/s]) propagated with two-body + J2 dynamics, ONE classical
+ *      RK4 step of `dt` seconds per epoch on the state and on the variational equations (Phi = STM over the epoch).
+ *      Per epoch, shared by the batch: the tracking station's ECI position / velocity at the END of the epoch and
+ *      the truth's noise-free (range, range-rate) there; every filter's real observation is that plus
+ *      sigma * N(0, 1) from Philox keyed by (seed, filter_offset + filter, epoch).  Outputs per (filter, epoch):
+ *      Phi [36], Htilde [12] = d(range, range-rate)/d(r, v), real [2], computed [2] -- the inputs of gkb_nl_run. */
+typedef struct gkb_od_config {
+  double mu;              /* gravitational parameter, km^3/s^2                                            */
+  double j2;              /* J2 zonal coefficient (0 = pure two-body)                                      */
+  double re;              /* equatorial radius, km                                                         */
+  double dt;              /* seconds per epoch                                                             */
+  const double* orbit0;   /* [6][n_filters] initial reference orbits; gkb_od_run: NULL = continue          */
+  int orbit_mem;          /* GKB_HOST or GKB_DEVICE (orbit0)                                               */
+  const double* station;  /* host [steps][6]                                                               */
+  const double* truth_obs;/* host [steps][2]                                                               */
+  double sigma_range, sigma_rate;
+  uint64_t seed;
+  int64_t filter_offset;  /* global index of filter 0 (multi-GPU shards keep one noise stream per filter)  */
+} gkb_od_config;
+/* Writes the streams ([steps][C][n_filters], C = 36 / 12 / 2 / 2; `mem` = where the four arrays live) and, when
+ * orbit_out != NULL ([6][n_filters], same `mem`), the reference orbits after the last epoch. */
+int gkb_od_synthesize(const gkb_od_config* cfg, int steps, int64_t n_filters, int device, double* Phi, double* Htilde,
+                      double* real_obs, double* computed_obs, int mem, double* orbit_out);
+/* The fused run on a GKB_HYBRID handle with n = 6, m = 2: per epoch the synthesis above and then
+ * Prepare + Update / Predict (flags as in gkb_nl_run, host array or NULL = Update every epoch; no SNC), in one
+ * kernel -- Phi / Htilde / observations live in registers and never reach HBM.  Bit-identical to gkb_od_synthesize
+ * followed by gkb_nl_run on its streams.  Outputs: state / covar (+ status), final or every step.  Honours
+ * gkb_set_strict.  The handle keeps the advanced reference orbits: cfg->orbit0 = NULL continues from them. */
+int gkb_od_run(gkb_filter* f, const gkb_od_config* cfg, int steps, const uint8_t* flags, const gkb_outputs* out);
+
 /* ---- SmoothAll (hybrid.go:209-238, srif.go:165-192): backward sweep over the stored estimates of a
  *      run, in place.  For k = steps-2 .. 0:  S = inv(Phi[k+1]);  state[k] = S state[k+1];
  *      covar[k] = S covar[k+1] S^T -- each step reads the values the previous one wrote, like the

@@ -170,6 +170,12 @@ double gko_icdf_normal(uint32_t k);
 /* The oracle's standard-normal stream: normal #j (j = 0..n+m-1) of (seed, trial, step). */
 void gko_philox_normals(uint64_t seed, uint64_t trial, uint32_t step, int count, double* z);
 
+/* gko_od.c: the engine's OD-input synthesis restated as the generic RK4 on the 6 + 36 state / STM equations
+ * (two-body + J2), range / range-rate partials and observations.  Streams are SoA [step][component][filter]. */
+int gko_od_synth(double mu, double j2, double re, double dt, int64_t nf, int steps, const double* orbit0,
+                 const double* station, const double* truth_obs, double sigma_range, double sigma_rate, uint64_t seed,
+                 int64_t filter_offset, double* Phi, double* Ht, double* real_obs, double* comp_obs, double* orbit_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,7 +81,7 @@ class McConfig(C.Structure):
 
 def build(force=False):
     """Compile oracle/_build/libgko.so with the committed Makefile (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("gko.c", "gko_linalg.c", "gko.h", "gko_linalg.h", "Makefile",
+    srcs = [os.path.join(_HERE, f) for f in ("gko.c", "gko_linalg.c", "gko_od.c", "gko.h", "gko_linalg.h", "Makefile",
                                                os.path.join("..", "include", "gokalman_b200_icdf.inc"))]
     if (not force and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
@@ -455,3 +455,22 @@ def mc_chisquare(kind, F, G, H, Q, R, x0_truth, x0_filter, P0, trials, steps, co
     if rc != 0:
         raise OracleError(rc)
     return {"NIS": nis, "NEES": nees, "mean": mean, "std": std, "truth_x": tx, "truth_y": ty}
+
+
+def od_synth(mu, j2, re, dt, orbit0, station, truth_obs, sigma_range, sigma_rate, seed, filter_offset=0):
+    """gko_od.c: the engine's OD-input synthesis as the generic RK4 on state + STM.  orbit0 [6, nf]; station
+    [steps, 6]; truth_obs [steps, 2].  Returns Phi [steps, 36, nf], Ht [steps, 12, nf], real, computed [steps, 2, nf],
+    final orbits [6, nf]."""
+    orbit0, station, truth_obs = _a(orbit0), _a(station), _a(truth_obs)
+    nf, steps = orbit0.shape[1], station.shape[0]
+    Phi, Ht = np.zeros((steps, 36, nf)), np.zeros((steps, 12, nf))
+    real, comp, orb = np.zeros((steps, 2, nf)), np.zeros((steps, 2, nf)), np.zeros((6, nf))
+    L = lib()
+    L.gko_od_synth.restype = C.c_int
+    L.gko_od_synth.argtypes = [C.c_double] * 4 + [C.c_int64, C.c_int] + [C.c_void_p] * 3 + [C.c_double, C.c_double,
+                               C.c_uint64, C.c_int64] + [C.c_void_p] * 5
+    rc = L.gko_od_synth(mu, j2, re, dt, nf, steps, _p(orbit0), _p(station), _p(truth_obs), sigma_range, sigma_rate, seed,
+                        filter_offset, _p(Phi), _p(Ht), _p(real), _p(comp), _p(orb))
+    if rc != 0:
+        raise OracleError(rc)
+    return Phi, Ht, real, comp, orb

@@ -141,6 +141,11 @@ def scaled_err_steps(a, ref):
         return 0.0
     a, ref = a.reshape(a.shape[0], -1), ref.reshape(ref.shape[0], -1)
     floor = np.max(np.abs(ref), axis=1, keepdims=True)
+    if ref.shape[1] == 1:
+        # a ONE-entry array (m = 1: Measurement(), Innovation()) has no max-abs other than the entry itself, so
+        # per-step scaling would be the bare per-entry relative error, which SURVEY section 7 calls ill-posed (the
+        # entry crosses zero while its absolute error is set by the state's scale): its floor is the run's max-abs
+        floor = np.full_like(floor, np.max(np.abs(ref)))
     d = np.abs(a - ref)
     den = np.maximum(np.abs(ref), floor)
     err = np.where(den > 0.0, d / np.where(den > 0.0, den, 1.0), d)

@@ -53,7 +53,7 @@ def test_gpu_smooth_all_identity():
     Ht = rng.standard_normal((steps, m, n, nf))
     real = rng.standard_normal((steps, m, nf))
     comp = real + 0.05 * rng.standard_normal((steps, m, nf))
-    kf, _ = gk.NewHybridKF(np.zeros(n), np.diag([10, 10, 10, 1, 1, 1.0]), gk.NewNoiseless(None, np.diag([1e-2, 1e-2])), m,
+    kf, _ = gk.NewHybridKF(np.zeros(n), np.diag([10, 10, 10, 1, 1, 1.0]), gk.NewNoiseless(np.diag([1e-12] * 3), np.diag([1e-2, 1e-2])), m,
                            n_filters=nf)
     est = kf.RunBatch(np.full(steps, L.F_MEAS, dtype=np.uint8), Phi, Ht, real, comp, None, every_step=True)
     last_x, last_P = est.State()[-1].copy(), est.Covariance()[-1].copy()

@@ -1,0 +1,115 @@
+"""Device-side orbit-determination inputs (gkb_od_synthesize) and the fused OD run (gkb_od_run).
+
+  * the streams the device produces (closed-form RK4 STM, partials, observations) equal the oracle's GENERIC RK4 on
+    the 6 + 36 state / variational equations to 1e-10, per step, on App. D's scenario (LEO a = 7000 km, i = 30 deg,
+    three stations, 10 degree mask, sigma^2 = 1e-6);
+  * the STM is a real STM: Phi maps a small initial perturbation onto the propagated difference of two orbits;
+  * the fused run is BIT-IDENTICAL to synthesise-then-gkb_nl_run (production and strict kernels), hence inherits
+    the strict kernel's 1e-10 parity against the oracle's hybrid filter run on the oracle's own streams.
+"""
+import numpy as np
+import pytest
+
+import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+P0 = np.diag([10, 10, 10, 1, 1, 1.0])
+R = np.diag([1e-6, 1e-6])
+Q = np.diag([1e-12] * 3)
+
+
+def _setup(nf, steps, dt=10.0, always=False):
+    import gokalman_b200 as gk
+    from gokalman_b200 import od
+    gk.load()
+    scn = od.Scenario(steps, dt, od.leo_truth0(), always_track=always, theta0=2.5)  # first pass at epoch 29
+    orbit0 = od.perturbed_orbits(od.leo_truth0(), nf, seed=11)
+    return gk, od, scn, orbit0
+
+
+def test_od_streams_match_generic_rk4_oracle(oracle):
+    gk, od, scn, orbit0 = _setup(nf=70, steps=120)
+    Phi, Ht, real, comp, orb = od.synthesize(scn, orbit0, 1e-3, 1e-3, seed=5)
+    rPhi, rHt, rreal, rcomp, rorb = oracle.od_synth(scn.mu, scn.j2, scn.re, scn.dt, orbit0, scn.station, scn.truth_obs,
+                                                    1e-3, 1e-3, 5)
+    for f in (0, 31, 32, 69):
+        # the four 3 x 3 blocks of the STM have very different magnitudes (1, h, G h, 1): each is held to 1e-10 of
+        # its own scale at every step
+        P, rP = Phi[:, :, f].reshape(-1, 6, 6), rPhi[:, :, f].reshape(-1, 6, 6)
+        for a, b in ((slice(0, 3), slice(0, 3)), (slice(0, 3), slice(3, 6)), (slice(3, 6), slice(0, 3)), (slice(3, 6), slice(3, 6))):
+            assert fx.scaled_err_steps(P[:, a, b], rP[:, a, b]) <= TOL, (f, a, b)
+        H, rH = Ht[:, :, f].reshape(-1, 2, 6), rHt[:, :, f].reshape(-1, 2, 6)
+        assert fx.scaled_err_steps(H[:, 0, :3], rH[:, 0, :3]) <= TOL
+        assert fx.scaled_err_steps(H[:, 1, :3], rH[:, 1, :3]) <= TOL
+        assert np.array_equal(H[:, 1, 3:], H[:, 0, :3]) and not np.any(H[:, 0, 3:])
+        assert fx.scaled_err_steps(real[:, :, f], rreal[:, :, f]) <= 1e-13
+        assert fx.scaled_err_steps(comp[:, :, f], rcomp[:, :, f]) <= TOL
+        assert fx.scaled_err(orb[:, f], rorb[:, f]) <= 1e-12
+    # same epochs, same truth: the measurement noise differs per filter and has the requested spread
+    noise = (real - scn.truth_obs[:, :, None])
+    assert abs(noise.std() - 1e-3) < 5e-5 and abs(noise.mean()) < 5e-5
+
+
+def test_od_stm_maps_perturbations():
+    """Phi(t_{k+1}, t_k) dx_k ~= dx_{k+1} for two neighbouring reference orbits (first order in the 1 m offset)."""
+    gk, od, scn, _ = _setup(nf=2, steps=50)
+    x0 = od.leo_truth0()
+    orbit0 = np.stack([x0, x0 + np.array([1e-3, -2e-3, 1.5e-3, 1e-6, 2e-6, -1e-6])], axis=1)
+    _, _, _, _, orb_end = od.synthesize(scn, orbit0, 0.0, 0.0, seed=1)
+    Phi, _, _, _, _ = od.synthesize(scn, orbit0, 0.0, 0.0, seed=1)
+    dx = orbit0[:, 1] - orbit0[:, 0]
+    for k in range(scn.steps):
+        dx = Phi[k, :, 0].reshape(6, 6) @ dx
+    d_end = orb_end[:, 1] - orb_end[:, 0]
+    assert np.max(np.abs(dx - d_end) / np.max(np.abs(d_end))) < 1e-5
+    # and the truth table agrees with the device propagation of the unperturbed orbit (same RK4, host numpy)
+    assert fx.scaled_err(orb_end[:, 0], scn.truth[-1]) <= 1e-12
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_od_fused_run_is_bit_identical_to_streams(oracle, strict):
+    """gkb_od_run == gkb_od_synthesize + gkb_nl_run, bit for bit (both kernels call the same od_step), with the 10
+    degree mask (Predict epochs between passes) and CKF -> EKF; and, for the strict kernel, 1e-10 against the oracle's
+    hybrid filter fed with the ORACLE's streams."""
+    gk, od, scn, orbit0 = _setup(nf=66, steps=400)
+    assert 0 < np.count_nonzero(scn.flags & 1) < scn.steps  # passes and gaps
+    Phi, Ht, real, comp, _ = od.synthesize(scn, orbit0, 1e-3, 1e-3, seed=9)
+    nf = orbit0.shape[1]
+
+    def make():
+        kf, _ = gk.NewHybridKF(np.zeros(6), P0, gk.NewNoiseless(Q, R), 2, n_filters=nf)
+        kf.SetStrict(strict)
+        return kf
+    a = make().RunBatch(scn.flags, Phi, Ht, real, comp, None, every_step=False, want=("state", "covar"))
+    b = make().RunOD(scn, orbit0, 1e-3, 1e-3, seed=9)
+    assert np.all(a.status == 0) and np.all(b.status == 0)
+    assert np.array_equal(a.State(), b.State())
+    assert np.array_equal(a.Covariance(), b.Covariance())
+    if strict:
+        rPhi, rHt, rreal, rcomp, _ = oracle.od_synth(scn.mu, scn.j2, scn.re, scn.dt, orbit0[:, :4], scn.station, scn.truth_obs,
+                                                     1e-3, 1e-3, 9)
+        xr, Pr = oracle.run_nl_batch(oracle.HYBRID, np.zeros(6), P0, R, scn.flags, rPhi, rHt, rreal, rcomp, threads=2)
+        xf, Pf = oracle.run_nl_batch(oracle.HYBRID, np.zeros(6), P0, R, scn.flags, np.ascontiguousarray(Phi[:, :, :4]),
+                                     np.ascontiguousarray(Ht[:, :, :4]), np.ascontiguousarray(real[:, :, :4]),
+                                     np.ascontiguousarray(comp[:, :, :4]), threads=2)
+        for f in range(4):
+            # the filter arithmetic: GPU strict vs the oracle on the SAME (device-made) streams -- the parity bar
+            assert fx.scaled_err(b.State()[:, f], xf[:, f]) <= TOL
+            assert fx.scaled_err(b.Covariance()[:, :, f].reshape(-1), Pf[:, f]) <= TOL
+        print("end-to-end (oracle streams + oracle filter) vs fused device run, x / P:",
+              [(fx.scaled_err(b.State()[:, f], xr[:, f]), fx.scaled_err(b.Covariance()[:, :, f].reshape(-1), Pr[:, f])) for f in range(4)])
+
+
+def test_od_run_converges_on_the_truth():
+    """Physics sanity of the whole fused path: after a day of passes the estimated deviation x-hat brings the
+    (1 km, 1 m/s)-perturbed reference orbit back onto the truth -- position error far below the initial 1 km."""
+    gk, od, scn, orbit0 = _setup(nf=64, steps=2000, dt=10.0)
+    kf, _ = gk.NewHybridKF(np.zeros(6), P0, gk.NewNoiseless(Q, R), 2, n_filters=64)
+    kf.DisableEKF()
+    flags = (scn.flags & ~np.uint8(2))  # CKF throughout: x-hat accumulates the deviation of the un-rectified reference
+    est = kf.RunOD(scn, orbit0, 1e-3, 1e-3, seed=3, flags=flags)
+    _, _, _, _, orb_end = od.synthesize(scn, orbit0, 1e-3, 1e-3, seed=3)
+    err0 = np.linalg.norm(orbit0[:3] - od.leo_truth0()[:3, None], axis=0)
+    err = np.linalg.norm((orb_end + est.State())[:3] - scn.truth[-1][:3, None], axis=0)
+    assert np.median(err0) > 1.0 and np.median(err) < 0.05, (np.median(err0), np.median(err))
