@@ -7,6 +7,7 @@
 // caller can bracket them with its own CUDA events.  There is no CPU path anywhere in this file.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -178,6 +179,10 @@ struct gkb_filter {
   bool tile = false;
   DevBuf tile_model;  // F [n*n], Q [n*n], H [8][n], R [8][8]
   DevBuf sched;       // NLDKF production kernel: task counter + one flag per group of 32 filters
+  // host-stream pipeline of gkb_nl_run: two staging sets, a copy stream, "copied" / "consumed" events per set
+  DevBuf st_phi[2], st_h[2], st_r[2], st_c[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   DevBuf orbit, od_tab;  // gkb_od_run: reference orbits [6][nf]; per-epoch station + truth-observation tables
   bool has_orbit = false;
 };
@@ -253,7 +258,13 @@ static int finish_create(gkb_filter* f, const double* x0, int x0_per_filter, con
 static void destroy_filter(gkb_filter* f) {
   if (!f) return;
   cudaSetDevice(f->device);
-  DevBuf* bufs[] = {&f->orbit, &f->od_tab, &f->sched, &f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
+  if (f->copy_stream) {
+    cudaStreamSynchronize(f->copy_stream);
+    cudaStreamDestroy(f->copy_stream);
+    for (int b = 0; b < 2; ++b) { cudaEventDestroy(f->ev_h2d[b]); cudaEventDestroy(f->ev_done[b]); }
+  }
+  DevBuf* bufs[] = {&f->st_phi[0], &f->st_phi[1], &f->st_h[0], &f->st_h[1], &f->st_r[0], &f->st_r[1], &f->st_c[0], &f->st_c[1],
+                    &f->orbit, &f->od_tab, &f->sched, &f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
                     &f->in_a, &f->in_b, &f->in_c, &f->in_d, &f->in_e, &f->in_f, &f->o_state, &f->o_meas, &f->o_innov,
                     &f->o_covar, &f->o_pred, &f->o_gain, &f->o_obsdev};
   for (DevBuf* b : bufs) b->release();
@@ -787,6 +798,26 @@ int gkb_update(gkb_filter* f, int steps, const double* y, int y_shared, const do
   return 0;
 }
 
+// One launch of the NLDKF kernels over epochs [k0, k0 + len) of a call of `total` epochs: the stream pointers in `io`
+// already point at epoch k0; every-step outputs are offset to row k0, final-estimate outputs are written by the
+// launch that ends the call.  The state travels between launches through the handle's state arrays.
+static int nl_launch_epochs(gkb_filter* f, NlIo io, const OutPlan& pl, int innov_len, int k0, int len, int total) {
+  const HostModel& hm = f->hm;
+  const int n = hm.n, m = hm.m;
+  io.steps = len;
+  const bool last = (k0 + len == total);
+  const size_t row = (size_t)k0 * f->nf;
+  auto at = [&](double* base, int comps) -> double* {
+    if (!base) return nullptr;
+    if (io.every_step) return base + row * comps;
+    return last ? base : nullptr;
+  };
+  io.o_state = at(pl.state, n); io.o_meas = at(pl.meas, m); io.o_innov = at(pl.innov, innov_len);
+  io.o_covar = at(pl.covar, n * n); io.o_pred = at(pl.pred, n * n); io.o_gain = at(pl.gain, n * m);
+  io.o_obsdev = at(pl.obsdev, m);
+  return launch_nl_run(hm, io, f->stream);
+}
+
 int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi, int phi_shared,
                const double* Htilde, int h_shared, const double* real_obs, const double* computed_obs,
                const double* Gamma, int in_mem, const gkb_outputs* out) {
@@ -823,6 +854,87 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
   io.steps = steps;
   io.vec = f->vec.as<double>();
   io.mat = f->mat.as<double>();
+  io.phi_shared = phi_shared;
+  io.h_shared = h_shared;
+  if ((rc = f->sched.ensure(sizeof(int) * (size_t)((f->nf + 31) / 32 + 1)))) return rc;
+  io.sched = f->sched.as<int>();
+  const int innov_len = (hm.kind == GKB_SRIF) ? n : m;
+  OutPlan pl;
+  if ((rc = plan_outputs(f, out, steps, innov_len, pl))) return rc;
+  io.every_step = out ? out->every_step : 0;
+  io.strict = f->strict ? 1 : 0;
+  io.status = f->status.as<int32_t>();
+  const bool sync = !(in_mem == GKB_DEVICE && (!out || out->mem == GKB_DEVICE));
+
+  // ---- host-resident per-filter streams: the call is PCIe-bound (416 B per filter-epoch at n = 6, m = 2 against
+  // ~20 B/ns of PCIe), so the epochs are cut into chunks that travel through two staging sets on a copy stream
+  // while the kernels of the previous chunk run: the device never waits for more than one chunk, the staging
+  // memory is bounded (2 x ~256 MB instead of the whole stream), and the copy engine is kept busy back to back.
+  const size_t per_epoch = sizeof(double) * (size_t)f->nf *
+                           ((phi_shared ? 0 : n * n) + ((Htilde && !h_shared) ? m * n : 0) + (real_obs ? m : 0) + (computed_obs ? m : 0));
+  int chunk = steps;
+  if (in_mem != GKB_DEVICE && per_epoch > 0) {
+    const size_t target = (size_t)256 << 20;
+    chunk = (int)std::max<size_t>(2, target / per_epoch);
+    if (const char* e = getenv("GKB_NL_H2D_CHUNK")) chunk = std::max(1, atoi(e));  // tests force tiny chunks
+  }
+  if (in_mem != GKB_DEVICE && chunk < steps) {
+    if (!f->copy_stream) {
+      GKB_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        GKB_CUDA(cudaEventCreateWithFlags(&f->ev_h2d[b], cudaEventDisableTiming));
+        GKB_CUDA(cudaEventCreateWithFlags(&f->ev_done[b], cudaEventDisableTiming));
+      }
+    }
+    // shared (small) streams and the flags are staged whole, once
+    const void *dfl = nullptr, *dphi_sh = nullptr, *dh_sh = nullptr, *dg = nullptr;
+    if ((rc = stage_in(f, f->in_a, flags, (size_t)steps, in_mem, &dfl))) return rc;
+    if (phi_shared && (rc = stage_in(f, f->in_b, Phi, sizeof(double) * (size_t)steps * n * n, in_mem, &dphi_sh))) return rc;
+    if (Htilde && h_shared && (rc = stage_in(f, f->in_c, Htilde, sizeof(double) * (size_t)steps * m * n, in_mem, &dh_sh))) return rc;
+    if (hm.kind == GKB_HYBRID && Gamma && hm.q > 0)
+      if ((rc = stage_in(f, f->in_f, Gamma, sizeof(double) * (size_t)steps * n * hm.q, in_mem, &dg))) return rc;
+    const size_t nfz = (size_t)f->nf;
+    const size_t b_phi = phi_shared ? 0 : sizeof(double) * n * n * nfz, b_h = (Htilde && !h_shared) ? sizeof(double) * m * n * nfz : 0;
+    const size_t b_o = sizeof(double) * m * nfz;
+    for (int b = 0; b < 2; ++b) {
+      if (b_phi && (rc = f->st_phi[b].ensure(b_phi * chunk))) return rc;
+      if (b_h && (rc = f->st_h[b].ensure(b_h * chunk))) return rc;
+      if (real_obs && (rc = f->st_r[b].ensure(b_o * chunk))) return rc;
+      if (computed_obs && (rc = f->st_c[b].ensure(b_o * chunk))) return rc;
+    }
+    GKB_CUDA(cudaStreamSynchronize(f->stream));  // the staging sets may still be read by an earlier asynchronous call
+    Timer tm(f->stream);
+    int launches = 0;
+    for (int k0 = 0, c = 0; k0 < steps; k0 += chunk, ++c) {
+      const int len = std::min(chunk, steps - k0), b = c & 1;
+      cudaStream_t cs = f->copy_stream;
+      if (c >= 2) GKB_CUDA(cudaStreamWaitEvent(cs, f->ev_done[b], 0));  // the kernels of chunk c - 2 are done with set b
+      if (b_phi) GKB_CUDA(cudaMemcpyAsync(f->st_phi[b].p, Phi + (size_t)k0 * n * n * nfz, b_phi * len, cudaMemcpyHostToDevice, cs));
+      if (b_h) GKB_CUDA(cudaMemcpyAsync(f->st_h[b].p, Htilde + (size_t)k0 * m * n * nfz, b_h * len, cudaMemcpyHostToDevice, cs));
+      if (real_obs) GKB_CUDA(cudaMemcpyAsync(f->st_r[b].p, real_obs + (size_t)k0 * m * nfz, b_o * len, cudaMemcpyHostToDevice, cs));
+      if (computed_obs) GKB_CUDA(cudaMemcpyAsync(f->st_c[b].p, computed_obs + (size_t)k0 * m * nfz, b_o * len, cudaMemcpyHostToDevice, cs));
+      GKB_CUDA(cudaEventRecord(f->ev_h2d[b], cs));
+      GKB_CUDA(cudaStreamWaitEvent(f->stream, f->ev_h2d[b], 0));
+      NlIo ioc = io;
+      ioc.flags = dfl ? static_cast<const uint8_t*>(dfl) + k0 : nullptr;
+      ioc.Phi = phi_shared ? static_cast<const double*>(dphi_sh) + (size_t)k0 * n * n : f->st_phi[b].as<double>();
+      ioc.Htilde = !Htilde ? nullptr : (h_shared ? static_cast<const double*>(dh_sh) + (size_t)k0 * m * n : f->st_h[b].as<double>());
+      ioc.real_obs = real_obs ? f->st_r[b].as<double>() : nullptr;
+      ioc.computed_obs = computed_obs ? f->st_c[b].as<double>() : nullptr;
+      ioc.Gamma = dg ? static_cast<const double*>(dg) + (size_t)k0 * n * hm.q : nullptr;
+      rc = nl_launch_epochs(f, ioc, pl, innov_len, k0, len, steps);
+      if (rc) return fail(rc, "no kernel for kind=%d n=%d m=%d", hm.kind, n, m);
+      GKB_CUDA(cudaEventRecord(f->ev_done[b], f->stream));
+      ++launches;
+    }
+    tm.stop(launches, true);
+    GKB_CUDA(cudaGetLastError());
+    f->step += steps;
+    if ((rc = copy_back(f, out, pl))) return rc;
+    GKB_CUDA(cudaStreamSynchronize(f->stream));
+    return 0;
+  }
+
   const void *dfl = nullptr, *dphi = nullptr, *dh = nullptr, *dr = nullptr, *dc = nullptr, *dg = nullptr;
   if ((rc = stage_in(f, f->in_a, flags, (size_t)steps, in_mem, &dfl))) return rc;
   if ((rc = stage_in(f, f->in_b, Phi, sizeof(double) * (size_t)steps * n * n * (phi_shared ? 1 : f->nf), in_mem, &dphi))) return rc;
@@ -833,25 +945,12 @@ int gkb_nl_run(gkb_filter* f, int steps, const uint8_t* flags, const double* Phi
     if ((rc = stage_in(f, f->in_f, Gamma, sizeof(double) * (size_t)steps * n * hm.q, in_mem, &dg))) return rc;
   io.flags = static_cast<const uint8_t*>(dfl);
   io.Phi = static_cast<const double*>(dphi);
-  io.phi_shared = phi_shared;
   io.Htilde = static_cast<const double*>(dh);
-  io.h_shared = h_shared;
   io.real_obs = static_cast<const double*>(dr);
   io.computed_obs = static_cast<const double*>(dc);
   io.Gamma = static_cast<const double*>(dg);
-  if ((rc = f->sched.ensure(sizeof(int) * (size_t)((f->nf + 31) / 32 + 1)))) return rc;
-  io.sched = f->sched.as<int>();
-  const int innov_len = (hm.kind == GKB_SRIF) ? n : m;
-  OutPlan pl;
-  if ((rc = plan_outputs(f, out, steps, innov_len, pl))) return rc;
-  io.every_step = out ? out->every_step : 0;
-  io.strict = f->strict ? 1 : 0;
-  io.o_state = pl.state; io.o_meas = pl.meas; io.o_innov = pl.innov; io.o_covar = pl.covar;
-  io.o_pred = pl.pred; io.o_gain = pl.gain; io.o_obsdev = pl.obsdev;
-  io.status = f->status.as<int32_t>();
-  const bool sync = !(in_mem == GKB_DEVICE && (!out || out->mem == GKB_DEVICE));
   Timer tm(f->stream);
-  rc = launch_nl_run(hm, io, f->stream);
+  rc = nl_launch_epochs(f, io, pl, innov_len, 0, steps, steps);
   if (rc) return fail(rc, "no kernel for kind=%d n=%d m=%d", hm.kind, n, m);
   tm.stop(1, sync);
   GKB_CUDA(cudaGetLastError());

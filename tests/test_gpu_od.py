@@ -102,14 +102,20 @@ def test_od_fused_run_is_bit_identical_to_streams(oracle, strict):
 
 
 def test_od_run_converges_on_the_truth():
-    """Physics sanity of the whole fused path: after a day of passes the estimated deviation x-hat brings the
-    (1 km, 1 m/s)-perturbed reference orbit back onto the truth -- position error far below the initial 1 km."""
-    gk, od, scn, orbit0 = _setup(nf=64, steps=2000, dt=10.0)
-    kf, _ = gk.NewHybridKF(np.zeros(6), P0, gk.NewNoiseless(Q, R), 2, n_filters=64)
-    kf.DisableEKF()
+    """Physics sanity of the whole fused path (CKF, un-rectified reference orbits 50 m / 5 cm/s off the truth): after
+    2000 epochs with six station passes the reference orbits have drifted kilometres from the truth, and the
+    estimated deviation x-hat brings them back to within metres (same figures as the CPU oracle: median 3 m)."""
+    import gokalman_b200 as gk
+    from gokalman_b200 import od
+    gk.load()
+    nf, steps = 64, 2000
+    scn = od.Scenario(steps, 10.0, od.leo_truth0(), theta0=2.5)
+    orbit0 = od.perturbed_orbits(od.leo_truth0(), nf, sigma_r=0.05, sigma_v=5e-5, seed=11)
+    kf, _ = gk.NewHybridKF(np.zeros(6), P0, gk.NewNoiseless(Q, R), 2, n_filters=nf)
     flags = (scn.flags & ~np.uint8(2))  # CKF throughout: x-hat accumulates the deviation of the un-rectified reference
     est = kf.RunOD(scn, orbit0, 1e-3, 1e-3, seed=3, flags=flags)
+    assert np.all(est.status == 0)
     _, _, _, _, orb_end = od.synthesize(scn, orbit0, 1e-3, 1e-3, seed=3)
-    err0 = np.linalg.norm(orbit0[:3] - od.leo_truth0()[:3, None], axis=0)
+    drift = np.linalg.norm(orb_end[:3] - scn.truth[-1][:3, None], axis=0)
     err = np.linalg.norm((orb_end + est.State())[:3] - scn.truth[-1][:3, None], axis=0)
-    assert np.median(err0) > 1.0 and np.median(err) < 0.05, (np.median(err0), np.median(err))
+    assert np.median(drift) > 1.0 and np.median(err) < 0.02, (np.median(drift), np.median(err))

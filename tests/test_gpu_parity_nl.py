@@ -409,3 +409,33 @@ def test_householder_and_srif_update_kats_on_device(oracle):
     ref = np.stack([oracle.householder_transf(batch[:, :, j].copy(), 6, 2) for j in range(50)], axis=2)
     got3 = gk.HouseholderTransf(batch.copy(), 6, 2)
     assert fx.scaled_err(got3, ref) <= 1e-13
+
+
+@pytest.mark.parametrize("kind", ["hybrid", "srif"])
+def test_host_stream_pipeline_is_bit_identical(kind, monkeypatch):
+    """gkb_nl_run with HOST streams cuts the epochs into chunks that travel through two staging sets on a copy
+    stream while the previous chunk's kernels run (engine.cu).  Forced to 3- and 7-epoch chunks (ragged last chunk,
+    a 1-epoch tail) the results -- final and every-step outputs -- equal the single-shot call bit for bit."""
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS, F_EKF
+    rng = np.random.default_rng(77)
+    n, m, nf, steps = 6, 2, 70, 22
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    flags = np.array([(F_MEAS if k % 6 != 4 else 0) | (F_EKF if k >= 9 else 0) for k in range(steps)], dtype=np.uint8)
+    P0, R = np.diag([10, 10, 10, 1, 1, 1.0]), np.diag([1e-2, 1e-2])
+
+    def run(every):
+        if kind == "hybrid":
+            kf, _ = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(np.diag([1e-12] * 3), R), m, n_filters=nf)
+        else:
+            kf, _ = gk.NewSRIF(np.zeros(n), P0, m, False, gk.NewNoiseless(np.diag([1e-12] * 3), R), n_filters=nf)
+        est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=every, want=("state", "covar"))
+        return est.State().copy(), est.Covariance().copy(), kf.GetState()
+    monkeypatch.setenv("GKB_NL_H2D_CHUNK", "1000")
+    ref = {every: run(every) for every in (False, True)}
+    for chunk in ("3", "7"):
+        monkeypatch.setenv("GKB_NL_H2D_CHUNK", chunk)
+        for every in (False, True):
+            x, P, (vec, mat) = run(every)
+            assert np.array_equal(x, ref[every][0]) and np.array_equal(P, ref[every][1]), (chunk, every)
+            assert np.array_equal(vec, ref[every][2][0]) and np.array_equal(mat, ref[every][2][1])
