@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- filter-updates/sec of the batched Kalman hot path on N B200s (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mc_jerk3|hybrid6] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--impl ours|reference] [--no-sub]
 
-One "step" = one pass of the hot path over one batch of synthetic input:
-  mc_jerk3 (default, BASELINE configs[1]): 10^6 Monte Carlo trials x 1000 filter steps per GPU of the
-      3-state jerk model -- Philox noise -> truth -> vanilla KF -> NEES/NIS reduction, fused in one
-      kernel; multi-GPU shards trials (weak scaling) and all-reduces the 2 x 1000 per-step sums (NCCL).
-  hybrid6 (BASELINE configs[3]): 10^5 six-state hybrid CKF->EKF filters x S epochs with per-filter,
-      per-epoch Phi / Htilde / observations streamed from HBM.
-Prints ONE JSON line (rank 0).  `value` is timed with everything resident in HBM; `e2e` goes through
-the public host-buffer API (host<->device copies inside the timed region).  --impl reference times
-the CPU oracle (the reference itself is Go + un-vendored gonum and cannot be built in this image).
+One "step" = one pass of the hot path over one batch of synthetic input.  Workloads:
+  hybrid6 (DEFAULT: BASELINE configs[3], the north star's Target config): 10^5 six-state hybrid CKF->EKF filters per
+      GPU x 1000 epochs, per-filter per-epoch Phi / Htilde / observations (416 B per filter-update) resident in HBM:
+      41.6 GB per GPU, synthesised on the device from a LEO statOD scenario (gkb_od_synthesize: two-body + J2 STM,
+      range / range-rate partials, App. D constants).  `value` = production kernel (TMA pipelines); `e2e` = the
+      fused OD run through the public API (host: initial orbits in, final estimates out); the same line carries the
+      host-fed-streams figure against the measured PCIe bandwidth.  Multi-GPU: disjoint filter ranges, no collective.
+  srif6 (configs[3], SRIF arm), mc_jerk3 (configs[1]: 10^6 Monte Carlo trials x 1000 steps + chi-square, one NCCL
+      all-reduce of the NEES / NIS sums), mc_robot_info / mc_robot_sqrt (configs[2]), vanilla32 / vanilla64 (configs[4]).
+Unless --no-sub is given the default run appends `"sub"`: short records of hybrid6 in STRICT (reference-order,
+bit-exact) arithmetic, srif6, mc_jerk3 (weak and, at N > 1, strong scaling) and vanilla32, each with its own clocks.
+Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle on the same workload (the reference itself is
+Go + un-vendored gonum and cannot be built in this image).
 """
 import argparse
 import ctypes as C
@@ -57,31 +61,77 @@ MC_WORKLOADS = {
 # helpers
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / clock-event reasons sampled DURING the timed region.  In-process NVML at a 5 ms period
+    (the timed regions here are tenths of a second: `nvidia-smi -lms 100` would see one or two samples), with the
+    nvidia-smi loop of B200_PROFILING.md as the fallback when NVML is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, period_s=0.005):
+        self.idx, self.period, self.proc, self.lines = gpu_index, period_s, None, []
+        self.samples, self._stop, self.t, self.h, self.src = [], threading.Event(), None, None, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: go through the UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
 
     def start(self):
         try:
+            self.nv, self.h = self._nvml_handle()
+            self.max_sm = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.src = "nvml, %g ms period" % (1e3 * self.period)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.h = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.src = "nvidia-smi -lms 20"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.h is not None:
+            self._stop.set()
+            self.t.join(timeout=1.0)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "samples": 0, "reasons": ["no samples"], "source": self.src}
+            sm = [x[0] for x in self.samples]
+            reasons = sorted({name for _, _, r in self.samples for bit, name in self.REASONS if r & bit})
+            load = [x for x in sm if x >= 0.5 * self.max_sm] or sm
+            return {"sm_mhz": statistics.median(load), "sm_max_mhz": self.max_sm, "power_w_max": max(x[1] for x in self.samples),
+                    "samples": len(sm), "reasons": reasons, "source": self.src}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -100,28 +150,42 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load" = samples at or above half the max clock (idle samples precede the first launch)
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no samples"], "source": self.src}
         load = [s for s in sm if s >= 0.5 * max(mx)] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": self.src}
 
 
 def fp64_peak():
     """DFMA TFLOP/s: measured live with tools/peak_fp64 when built, else the committed measurement."""
-    exe = os.path.join(ROOT, "tools", "peak_fp64")
-    if os.path.exists(exe):
-        try:
-            r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-            d = json.loads(r.stdout.strip().splitlines()[-1])
-            return d["dfma_tflops_sustained"], "measured live: tools/peak_fp64 DFMA sustained (MEASURED_PEAKS.json has no FP64 entry)"
-        except Exception:
-            pass
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_peak_fp64.json")))
-        return d["dfma_tflops_sustained"], "profiles/r01_peak_fp64.json (DFMA sustained, measured on this pool's B200)"
-    except Exception:
-        return 34.2, "fallback constant (profiles/r01_peak_fp64.json)"
+    dfma, _, src = fp64_peaks_all()
+    return dfma, src + ", DFMA sustained"
+
+
+_PEAK_CACHE = {}
+
+
+def fp64_peaks_all():
+    """(dfma_sustained, dmma_burst, source) in TFLOP/s: tools/peak_fp64 run once per process, else the committed
+    measurement."""
+    if "v" not in _PEAK_CACHE:
+        d, src = None, None
+        exe = os.path.join(ROOT, "tools", "peak_fp64")
+        if os.path.exists(exe):
+            try:
+                r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                src = "measured live: tools/peak_fp64 (MEASURED_PEAKS.json has no FP64 entry)"
+            except Exception:
+                d = None
+        if d is None:
+            try:
+                d = json.load(open(os.path.join(ROOT, "profiles", "r01_peak_fp64.json")))
+                src = "profiles/r01_peak_fp64.json (measured on this pool's B200)"
+            except Exception:
+                d, src = {"dfma_tflops_sustained": 34.2, "dmma_m8n8k4_tflops_burst": 37.1}, "fallback constants (profiles/r01_peak_fp64.json)"
+        _PEAK_CACHE["v"] = (d["dfma_tflops_sustained"], d.get("dmma_m8n8k4_tflops_burst", 37.1), src)
+    return _PEAK_CACHE["v"]
 
 
 def measured_traffic(workload, is_default_config):
@@ -131,7 +195,13 @@ def measured_traffic(workload, is_default_config):
     if not is_default_config:
         return None
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[workload]["traffic"]
+        # the hybrid / SRIF bench configuration changed in round 2 (1000 epochs): only the round-2 capture applies
+        names = ("r02_traffic.json",) if workload.startswith(("hybrid", "srif")) else ("r02_traffic.json", "r01_traffic.json")
+        for name in names:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if workload in d and d[workload].get("traffic") is not None:
+                return d[workload]["traffic"]
+        return None
     except Exception:
         return None
 
@@ -182,21 +252,29 @@ def mc_config_struct(L, f, trials, trial_offset, steps, device, workload="mc_jer
     return cfg, keep
 
 
-def run_ours_mc(args, rank, world, local):
+def run_ours_mc(args, rank, world, local, workload=None, sub=False, strong=False):
+    """strong=False: `--trials` Monte Carlo trials PER GPU (weak scaling); strong=True: `--trials` trials in TOTAL,
+    sharded over the ranks by contiguous global trial ranges (Philox is keyed by the global trial index)."""
     import torch
     import torch.distributed as dist
     import gokalman_b200 as gk
     from gokalman_b200 import _lib as L
+    from gokalman_b200.sharding import shard_range
 
     lib = gk.load()
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    trials, steps = args.trials, args.filter_steps
-    wl = args.workload
+    total_trials, steps = args.trials, args.filter_steps
+    wl = workload or args.workload
     spec = MC_WORKLOADS[wl]
     f = mc_model(wl)
-    cfg, keep = mc_config_struct(L, f, trials, rank * trials, steps, local, wl)
+    if strong:
+        lo, hi = shard_range(total_trials, rank, world)
+        trials, offset, all_trials = hi - lo, lo, total_trials
+    else:
+        trials, offset, all_trials = total_trials, rank * total_trials, total_trials * world
+    n_steps = args.steps if not sub else max(3, min(args.steps, 10))
+    n_warm = args.warmup if not sub else 3
+    cfg, keep = mc_config_struct(L, f, trials, offset, steps, local, wl)
     sums = torch.zeros(2, steps, dtype=torch.float64, device="cuda")
     out = L.McOutputs()
     out.mem, out.sums_only = L.DEVICE, 1
@@ -207,7 +285,7 @@ def run_ours_mc(args, rank, world, local):
         L.check(lib.gkb_mc_chisquare(C.byref(cfg), C.byref(out)))
         if world > 1:
             dist.all_reduce(sums)  # the one collective of the path: 2 x steps doubles (NCCL)
-        return sums / float(trials * world)
+        return sums / float(all_trials)
 
     def barrier():
         if world > 1:
@@ -215,18 +293,18 @@ def run_ours_mc(args, rank, world, local):
         torch.cuda.synchronize()
 
     peak_tf, peak_src = fp64_peak() if rank == 0 else (None, None)
-    for _ in range(args.warmup):
+    for _ in range(n_warm):
         flush.zero_()
         means = step_device()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
     kern_ms = []
     barrier()
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(n_steps):
         flush.zero_()  # L2 flush between timed iterations (outside the per-step event bracket)
         ev[i][0].record()
         means = step_device()
@@ -240,19 +318,33 @@ def run_ours_mc(args, rank, world, local):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)  # max over ranks
     total_ms = float(total_ms.item())
-    units = float(trials) * steps * world * args.steps
+    units = float(all_trials) * steps * n_steps
     value = units / (total_ms * 1e-3)
     nis_mean, nees_mean = float(means[0].mean().item()), float(means[1].mean().item())
+    if sub:  # a sub-record of the default run: device-resident figure only
+        if rank != 0:
+            return None
+        main_ms = statistics.mean(kern_ms)
+        achieved_tf = spec["flops"] * float(trials) * steps / (main_ms * 1e-3) / 1e12
+        return {"value": value, "unit": "filter-updates/s", "n_gpus": world, "steps": n_steps, "warmup": n_warm,
+                "ms_per_step": total_ms / n_steps, "scaling": "strong" if strong else "weak",
+                "config": {"workload": spec["label"], "trials_total": all_trials, "trials_this_gpu": trials, "filter_steps": steps,
+                           "collective": "one NCCL all-reduce of 2 x %d doubles per step" % steps if world > 1 else "none (1 GPU)",
+                           "nis_mean": nis_mean, "nees_mean": nees_mean},
+                "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                             "kernel": spec["kernel"], "kernel_ms": main_ms, "flops_per_unit": spec["flops"], "peak_source": peak_src},
+                "allreduce_and_glue_ms": total_ms / n_steps - main_ms,
+                "gpu_launches": int(lib.gkb_last_kernel_launches()) * n_steps, "clocks": clocks}
 
     # ---- e2e: the public API with HOST buffers (model + controls in, NIS/NEES means out), every step
     controls = [np.zeros(1)] if spec["controls"] == "zero" else list(mc_controls(wl, steps))
     def step_e2e():
-        runs = gk.NewMonteCarloRuns(trials, steps, 1, controls, mckf, trial_offset=rank * trials)
+        runs = gk.NewMonteCarloRuns(trials, steps, 1, controls, mckf, trial_offset=offset)
         nis, nees = gk.NewChiSquare(chikf, runs, controls, bool(spec["nees"]), bool(spec["nis"]))
         if world > 1:
             t = torch.from_numpy(np.stack([nis, nees]) * trials).cuda()
             dist.all_reduce(t)
-            nis, nees = (t / float(trials * world)).cpu().numpy()
+            nis, nees = (t / float(all_trials)).cpu().numpy()
         return nis, nees
     mckf, _ = gk.NewPurePredictorVanilla(f["x0"], f["P0"], f["F"], f["G"], f["H"], gk.NewAWGN(f["Q"], f["R"], seed=SEED),
                                          device=local)
@@ -270,7 +362,7 @@ def run_ours_mc(args, rank, world, local):
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = float(trials) * steps * world * n_e2e / (float(e2e_ms.item()) * 1e-3)
+    e2e_value = float(all_trials) * steps * n_e2e / (float(e2e_ms.item()) * 1e-3)
     nn, mm = keep["F"].shape[0], keep["H"].shape[0]
     h2d = 8 * (nn * nn + nn + mm * nn + nn * nn + mm * mm + nn + nn + nn * nn + steps * 1)  # F,G,H,Q,R,x0,x0,P0 + controls
     d2h = 8 * 2 * steps + 4                                   # NIS, NEES means + the error word
@@ -283,9 +375,9 @@ def run_ours_mc(args, rank, world, local):
     line = {
         "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": spec["label"],
-                   "trials_per_gpu": trials, "filter_steps": steps, "n": nn, "m": mm, "c": 1, "noise": "philox4x32-10 + table inverse normal CDF, in-kernel",
+                   "trials_per_gpu": trials, "trials_total": all_trials, "filter_steps": steps, "n": nn, "m": mm, "c": 1, "noise": "philox4x32-10 + table inverse normal CDF, in-kernel",
                    "sharding": "trials split by rank, one NCCL all-reduce of 2 x %d doubles per step" % steps,
                    "l2": "flushed between timed iterations (256 MiB memset)", "nis_mean": nis_mean, "nees_mean": nees_mean},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
@@ -380,10 +472,14 @@ def oracle_filter_rate(workload, nf, steps, threads):
         gko.run_vanilla_batch(f["x0"], f["P0"], f["F"], f["H"], f["Q"], f["R"], y, threads=threads, want_covar=False)
         dt = time.perf_counter() - t0
     else:
-        Phi, Ht, real, comp = np_od_streams(nf, steps, 1234)
+        # the bench's statOD scenario (bench_hybrid.od_scenario), streams made by the oracle's own synthesis
+        from gokalman_b200 import od  # host-side numpy tables only: no engine call on this path
+        scn = od.Scenario(steps, 10.0, od.leo_truth0(), always_track=True, theta0=2.5)
+        orbit0 = od.perturbed_orbits(od.leo_truth0(), nf, sigma_r=1.0, sigma_v=1e-3, seed=1234)
+        Phi, Ht, real, comp, _ = gko.od_synth(scn.mu, scn.j2, scn.re, scn.dt, orbit0, scn.station, scn.truth_obs, 1e-3, 1e-3, 1234)
         srif = workload == "srif6"
         P0 = np.diag([50, 50, 50, 1, 1, 1.0]) if srif else np.diag([10, 10, 10, 1, 1, 1.0])
-        flags = np.array([1 | (0 if srif else (2 if k >= 15 else 0)) for k in range(steps)], dtype=np.uint8)
+        flags = np.full(steps, 1, dtype=np.uint8) if srif else np.ascontiguousarray(scn.flags)
         t0 = time.perf_counter()
         gko.run_nl_batch(gko.SRIF if srif else gko.HYBRID, np.zeros(6), P0, np.diag([1e-6, 1e-6]), flags, Phi, Ht, real, comp,
                          threads=threads)
@@ -393,6 +489,7 @@ def oracle_filter_rate(workload, nf, steps, threads):
 
 FILTER_WORKLOADS = {
     "hybrid6": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
+    "hybrid6_strict": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
     "srif6": "srif6: 6-state SRIF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
     "vanilla32": "vanilla32: synthetic 32-state vanilla KF, m = 8 (BASELINE configs[4])",
     "vanilla64": "vanilla64: synthetic 64-state vanilla KF, m = 8 (the n = 64 shape of BASELINE configs[4])",
@@ -436,7 +533,10 @@ def run_reference_filters(args, rank, world):
         "impl": "reference", "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": FILTER_WORKLOADS[wl], "epochs": steps},
+        "config": {"workload": FILTER_WORKLOADS[wl], "filters_per_gpu": 26640 if wl == "vanilla64" else 100000,
+                   "epochs": args.filter_steps if wl in ("hybrid6", "hybrid6_strict", "srif6") else (100 if wl == "vanilla64" else 200),
+                   "n": int(wl[7:]) if wl.startswith("vanilla") else 6, "m": 8 if wl.startswith("vanilla") else 2,
+                   "sample_filters": nf, "sample_epochs": steps},
         "cpu_baseline": {"value": value, "unit": "filter-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "filter-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU oracle port (C, OpenMP); the reference is Go + un-vendored gonum and cannot be built in this image",
@@ -474,16 +574,49 @@ def run_reference(args, rank, world):
     }
 
 
+def run_subrecords(args, rank, world, local, shared):
+    """Short records of the other BASELINE configs, appended to the default (hybrid6) line: same process, same
+    clocks discipline, device-resident figures only."""
+    from bench_hybrid import run_ours_hybrid
+    from bench_tile import run_ours_tile
+    sub = {}
+
+    def add(name, fn):
+        try:
+            sub[name] = fn()
+        except Exception as e:  # a sub-record must never take the headline down with it
+            sub[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+    add("hybrid6_strict", lambda: run_ours_hybrid(args, rank, world, local, workload="hybrid6_strict", sub=True, shared=shared))
+    add("srif6", lambda: run_ours_hybrid(args, rank, world, local, workload="srif6", sub=True, shared=shared))
+    shared.clear()  # frees the 41.6 GB of streams
+    import torch
+    torch.cuda.empty_cache()
+    mc_args = argparse.Namespace(**vars(args))
+    mc_args.trials, mc_args.filter_steps = 1000000, 1000
+    add("mc_jerk3", lambda: run_ours_mc(mc_args, rank, world, local, workload="mc_jerk3", sub=True))
+    if world > 1:
+        add("mc_jerk3_strong", lambda: run_ours_mc(mc_args, rank, world, local, workload="mc_jerk3", sub=True, strong=True))
+    tile_args = argparse.Namespace(**vars(args))
+    tile_args.workload, tile_args.trials, tile_args.filter_steps = "vanilla32", 1000000, 1000  # = that workload's defaults
+    add("vanilla32", lambda: run_ours_tile(tile_args, rank, world, local, sub=True))
+    return sub
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mc_jerk3", choices=["mc_jerk3", "mc_robot_info", "mc_robot_sqrt", "hybrid6", "srif6", "vanilla32", "vanilla64"])
-    ap.add_argument("--trials", type=int, default=1000000, help="Monte Carlo trials (filters) per GPU")
-    ap.add_argument("--filter-steps", type=int, default=1000, help="filter steps per trial")
+    ap.add_argument("--workload", default="hybrid6", choices=["hybrid6", "hybrid6_strict", "srif6", "mc_jerk3", "mc_robot_info",
+                                                              "mc_robot_sqrt", "vanilla32", "vanilla64"])
+    ap.add_argument("--trials", type=int, default=1000000, help="Monte Carlo trials per GPU (MC workloads) / filters per GPU "
+                    "(filter workloads: the default means 10^5, or 26 640 for vanilla64)")
+    ap.add_argument("--filter-steps", type=int, default=1000, help="filter steps / epochs per trial (vanilla32 / vanilla64: the "
+                    "default means 200 / 100)")
+    ap.add_argument("--strong", action="store_true", help="MC workloads: --trials is the TOTAL over all GPUs (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="default workload only: skip the sub-records of the other configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local = dist_env()
@@ -492,15 +625,26 @@ def main():
         if line is not None:
             print(json.dumps(line), flush=True)
         return
-    if args.workload in ("hybrid6", "srif6"):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    shared = {}
+    if args.workload in ("hybrid6", "hybrid6_strict", "srif6"):
         from bench_hybrid import run_ours_hybrid
-        line = run_ours_hybrid(args, rank, world, local)
+        line = run_ours_hybrid(args, rank, world, local, shared=shared)
     elif args.workload in ("vanilla32", "vanilla64"):
         from bench_tile import run_ours_tile
         line = run_ours_tile(args, rank, world, local)
     else:
-        line = run_ours_mc(args, rank, world, local)
+        line = run_ours_mc(args, rank, world, local, strong=args.strong)
+    sub = None
+    if args.workload == "hybrid6" and not args.no_sub:
+        sub = run_subrecords(args, rank, world, local, shared)
     if line is not None:
+        if sub is not None:
+            line["sub"] = sub
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = (cpu_baseline(workload=args.workload) if args.workload in MC_WORKLOADS
                                     else cpu_baseline_filters(args.workload))

@@ -21,18 +21,16 @@ def dmma_per_update(n):
     return tm * tm * ks + up * ks + tm * ks + ks + 2 * tm + 2 * up + tm * (ks + 2) + 2 * up
 
 
-def run_ours_tile(args, rank, world, local):
+def run_ours_tile(args, rank, world, local, sub=False):
     import torch
     import torch.distributed as dist
     import gokalman_b200 as gk
     from gokalman_b200 import _lib as L
-    from bench import ClockSampler, fp64_peak, measured_traffic
+    from bench import ClockSampler, fp64_peak, fp64_peaks_all, measured_traffic
     import fixtures as fx
 
     lib = gk.load()
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, m = int(os.environ.get('GKB_BENCH_TILE_N', '64' if args.workload == "vanilla64" else '32')), 8
     # n = 64: 3 warps (filters) per SM fit the shared memory -> 444 filters per wave; 26 640 = 60 waves
     nf = args.trials if args.trials != 1000000 else (100000 if n <= 32 else 26640)
@@ -61,17 +59,19 @@ def run_ours_tile(args, rank, world, local):
         torch.cuda.synchronize()
 
     peak_tf, peak_src = fp64_peak() if rank == 0 else (None, None)
-    for _ in range(args.warmup):
+    dmma_peak = fp64_peaks_all()[1] if rank == 0 else None
+    n_steps = args.steps if not sub else max(3, min(args.steps, 10))
+    for _ in range(args.warmup if not sub else 3):
         step_device()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
     kern_ms = []
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(n_steps):
         flush.zero_()
         ev[i][0].record()
         step_device()
@@ -84,8 +84,30 @@ def run_ours_tile(args, rank, world, local):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
-    value = float(nf) * steps * world * args.steps / (total_ms * 1e-3)
+    value = float(nf) * steps * world * n_steps / (total_ms * 1e-3)
     bad = int((status != 0).sum().item())
+
+    def roofline(main_ms):
+        ups = float(nf) * steps / (main_ms * 1e-3)
+        machine_tf = ups * FLOPS_MACHINE / 1e12
+        return {"bound": "tensor", "achieved": machine_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": machine_tf / dmma_peak,
+                "traffic": measured_traffic("vanilla%d" % n, (n == 32 and nf == 100000 and steps == 200) or (n == 64 and nf == 26640 and steps == 100)),
+                "kernel": "vanilla_tile_kernel<%d>" % n, "kernel_ms": main_ms,
+                "machine_flops_per_unit": FLOPS_MACHINE, "algorithmic_flops_per_unit": FLOPS_ALG,
+                "algorithmic_tflops": ups * FLOPS_ALG / 1e12,
+                "peak_source": "FP64 tensor (mma.sync.m8n8k4.f64) peak measured by tools/peak_fp64; " + str(peak_src),
+                "note": "achieved = EXECUTED flops (%d DMMA x 512 flop per update) against the measured DMMA peak -- a pipe "
+                        "utilisation, never above 1; algorithmic_tflops counts the reference's dense %.0f flop per update "
+                        "(SURVEY App. B), which the kernel does not execute (symmetry + restructured Joseph form)"
+                        % (dmma_per_update(n), FLOPS_ALG)}
+    if sub:
+        if rank != 0:
+            return None
+        return {"value": value, "unit": "filter-updates/s", "n_gpus": world, "steps": n_steps, "warmup": 3,
+                "ms_per_step": total_ms / n_steps, "scaling": "weak",
+                "config": {"workload": "vanilla%d: synthetic %d-state vanilla KF, m = 8, warp-per-filter FP64 DMMA (BASELINE configs[4])" % (n, n),
+                           "filters_per_gpu": nf, "epochs": steps, "failed_filters": bad},
+                "roofline": roofline(statistics.mean(kern_ms)), "gpu_launches": n_steps, "clocks": clocks}
 
     # ---- e2e: public host-buffer API (measurements in, final state out)
     hy = np.ascontiguousarray(y.permute(0, 2, 1).cpu().numpy())  # [steps, m, nf] as UpdateBatch takes it
@@ -108,8 +130,6 @@ def run_ours_tile(args, rank, world, local):
     if rank != 0:
         return None
     main_ms = statistics.mean(kern_ms)
-    ups = float(nf) * steps / (main_ms * 1e-3)
-    tf = ups * FLOPS_ALG / 1e12
     return {
         "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -118,14 +138,7 @@ def run_ours_tile(args, rank, world, local):
                                % (n, n, "" if n == 32 else "; the n = %d shape of the same kernel" % n),
                    "filters_per_gpu": nf, "epochs": steps, "n": n, "m": m, "failed_filters": bad,
                    "l2": "flushed between timed iterations (256 MiB memset)"},
-        "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                     "traffic": measured_traffic("vanilla%d" % n, (n == 32 and nf == 100000 and steps == 200) or (n == 64 and nf == 26640 and steps == 100)),
-                     "kernel": "vanilla_tile_kernel<%d>" % n, "kernel_ms": main_ms, "flops_per_unit": FLOPS_ALG,
-                     "machine_tflops": ups * FLOPS_MACHINE / 1e12, "machine_flops_per_unit": FLOPS_MACHINE,
-                     "peak_source": peak_src,
-                     "note": "achieved counts the reference's dense %.0f flop per update (SURVEY App. B); the kernel executes "
-                             "%.0f (symmetry + restructured Joseph form), so frac can exceed 1; machine_tflops is the executed "
-                             "rate" % (FLOPS_ALG, FLOPS_MACHINE)},
+        "roofline": roofline(main_ms),
         "e2e": {"value": e2e_value, "unit": "filter-updates/s", "h2d_bytes_per_step": 8 * steps * nf * m,
                 "d2h_bytes_per_step": 8 * nf * n + 4 * nf, "api": "Vanilla.UpdateBatch (host buffers)"},
         "gpu_launches": args.steps, "clocks": clocks, "wall_s": wall,
