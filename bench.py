@@ -501,7 +501,7 @@ def filter_sample_size(workload, cores, target_s):
     nf0 = cores * 8
     rate, _ = oracle_filter_rate(workload, nf0, steps, cores)  # calibration
     per_filter_bytes = steps * (64 if workload.startswith("vanilla") else 416)
-    nf = int(min(rate * target_s / steps, 2e9 / per_filter_bytes))
+    nf = int(min(rate * target_s / steps, 6e9 / per_filter_bytes))
     return max(cores, nf // cores * cores), steps
 
 

@@ -160,10 +160,20 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
 
     peak_tf, peak_src = fp64_peak() if rank == 0 else (None, None)
     hbm, hbm_src = hbm_peak()
-    n_steps = args.steps if not sub else max(3, min(args.steps, 10))
+    n_steps = args.steps
     for _ in range(args.warmup if not sub else 3):
         step_device()
     barrier()
+    if sub:  # long enough a timed region for the clock sampler: >= 0.15 s
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        step_device()
+        w1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every rank must loop the same number of times
+        n_steps = int(min(200, max(10, np.ceil(150.0 / max(float(t.item()), 1e-3)))))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -194,14 +204,18 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
         #      station / truth tables, flags), final state + covariance (+ status) out, every step
         kf2 = make()
         h_orbit = torch.from_numpy(orbit0).pin_memory().numpy()
-        kf2.RunOD(scn, h_orbit, SIGMA, SIGMA, seed=1234 + rank, filter_offset=rank * nf)
+        # caller-owned pinned result buffers (the D2H then runs at PCIe speed instead of through pageable staging)
+        h_out = {"state": torch.zeros(n * nf, dtype=torch.float64).pin_memory().numpy(),
+                 "covar": torch.zeros(n * n * nf, dtype=torch.float64).pin_memory().numpy(),
+                 "status": torch.zeros(nf, dtype=torch.int32).pin_memory().numpy()}
+        kf2.RunOD(scn, h_orbit, SIGMA, SIGMA, seed=1234 + rank, filter_offset=rank * nf, out_buffers=h_out)
         barrier()
         n_e2e = max(1, min(args.steps, 5))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_e2e):
             L.check(lib.gkb_reset(kf2._h))
-            est = kf2.RunOD(scn, h_orbit, SIGMA, SIGMA, seed=1234 + rank, filter_offset=rank * nf)
+            est = kf2.RunOD(scn, h_orbit, SIGMA, SIGMA, seed=1234 + rank, filter_offset=rank * nf, out_buffers=h_out)
         e1.record()
         barrier()
         e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -217,14 +231,14 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
         pin = lambda t: t[:e_steps].cpu().pin_memory().numpy()
         hPhi, hHt, hreal, hcomp = pin(Phi), pin(Ht), pin(real), pin(comp)
         kf3 = make()
-        kf3.RunBatch(flags_np[:e_steps], hPhi, hHt, hreal, hcomp, None, every_step=False, want=("state", "covar"))
+        kf3.RunBatch(flags_np[:e_steps], hPhi, hHt, hreal, hcomp, None, every_step=False, want=("state", "covar"), out_buffers=h_out)
         barrier()
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h0.record()
         n_host = 2
         for _ in range(n_host):
             L.check(lib.gkb_reset(kf3._h))
-            kf3.RunBatch(flags_np[:e_steps], hPhi, hHt, hreal, hcomp, None, every_step=False, want=("state", "covar"))
+            kf3.RunBatch(flags_np[:e_steps], hPhi, hHt, hreal, hcomp, None, every_step=False, want=("state", "covar"), out_buffers=h_out)
         h1.record()
         barrier()
         host_ms = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device=dev)

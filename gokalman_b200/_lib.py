@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libgokalman_b200.so")
 VANILLA, PREDICTOR, INFORMATION, SQRT, HYBRID, SRIF = range(6)
 HOST, DEVICE = 0, 1
 NOISE_PHILOX, NOISE_REPLAY = 0, 1
+REDUCE_NCCL, REDUCE_PEER = 0, 1
 F_MEAS, F_EKF, F_SNC = 1, 2, 4
 
 STATUS_NAMES = {
@@ -76,6 +77,8 @@ SYMBOLS = [
     ("gkb_set_measurement_matrix", _i, [_vp, _i, _vp]),
     ("gkb_set_noise", _i, [_vp, _vp, _i, _vp]),
     ("gkb_set_replay_noise", _i, [_vp, _i, _vp, _vp, _i]),
+    ("gkb_set_philox_noise", _i, [_vp, C.c_uint64, _i64]),
+    ("gkb_awgn_sample", _i, [_i, _i, _vp, _vp, C.c_uint64, _i64, _i, _i, _vp, _vp, _vp]),
     ("gkb_reset", _i, [_vp]),
     ("gkb_set_stream", _i, [_vp, _vp]),
     ("gkb_set_strict", _i, [_vp, _i]),
@@ -92,6 +95,7 @@ SYMBOLS = [
     ("gkb_householder_transf", _i, [_i, _i, _i64, _i, _vp, _i]),
     ("gkb_batch_solve", _i, [_i, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     ("gkb_mc_chisquare", _i, [C.POINTER(McConfig), C.POINTER(McOutputs)]),
+    ("gkb_mc_chisquare_multi", _i, [C.POINTER(McConfig), C.POINTER(_i), _i, _i, C.POINTER(McOutputs)]),
     ("gkb_last_kernel_ms", C.c_float, []),
     ("gkb_last_main_kernel_ms", C.c_float, []),
     ("gkb_last_kernel_launches", _i, []),

@@ -116,19 +116,21 @@ class BatchNoise(ReplayNoise):
 
 
 class AWGN:
-    """noise.go:109-159.  The reference seeds math/rand from the clock (irreproducible by design);
-    here the samples come from the engine's counter-based Philox4x32-10 stream keyed by
-    (seed, trial, step), generated inside the Monte Carlo kernel.  It is the noise of the pure
-    predictor that NewMonteCarloRuns drives."""
+    """noise.go:109-159.  The reference seeds math/rand from the clock (irreproducible by design); here the samples
+    come from the engine's counter-based Philox4x32-10 stream keyed by (seed, filter, step), generated on the device:
+    inside the Monte Carlo kernel for the pure predictor NewMonteCarloRuns drives, and by `gkb_set_philox_noise` for
+    any ordinary filter that carries this noise (vanilla_test.go:29-75, information_test.go, squareroot_test.go).
+    Process(k) / Measurement(k) return, on the host, exactly the samples filter 0 of such a handle consumes at step
+    k (`gkb_awgn_sample`); like the reference's AWGN a second Process(k) call at the same step is a fresh draw."""
 
-    def __init__(self, Q, R, seed=None):
+    def __init__(self, Q, R, seed=None, device=0):
         self.Q, self.R = _mat(Q), _mat(R)
         for name, M in (("process", self.Q), ("measurement", self.R)):
             try:
                 np.linalg.cholesky(M)
             except np.linalg.LinAlgError:
                 raise ValueError("%s noise invalid" % name)  # noise.go:149-156 panics
-        self._seed0 = seed
+        self._seed0, self._device = seed, device
         self.Reset()
 
     def Reset(self):
@@ -137,6 +139,7 @@ class AWGN:
             self.seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
         else:
             self.seed = int(self._seed0)
+        self._last_k, self._calls = None, 0
 
     def ProcessMatrix(self):
         return self.Q
@@ -144,17 +147,31 @@ class AWGN:
     def MeasurementMatrix(self):
         return self.R
 
-    def Process(self, k):
-        raise NotImplementedError("AWGN samples are generated on the device by the Monte Carlo kernel")
+    def _sample(self, k, filter_index=0):
+        n, m = self.Q.shape[0], self.R.shape[0]
+        w, v, w2 = np.zeros(n), np.zeros(m), np.zeros(n)
+        _lib.check(_lib.load().gkb_awgn_sample(n, m, _ptr(self.Q), _ptr(self.R), self.seed, filter_index, int(k), self._device,
+                                               _ptr(w), _ptr(v), _ptr(w2)))
+        return w, v, w2
 
-    Measurement = Process
+    def Process(self, k, filter_index=0):
+        """noise.go:127-131.  The first call at step k returns the draw of vanilla.go:146, a second consecutive call at
+        the same k the (different) draw of vanilla.go:195."""
+        self._calls = self._calls + 1 if self._last_k == k else 1
+        self._last_k = k
+        w, _, w2 = self._sample(k, filter_index)
+        return w if self._calls % 2 == 1 else w2
+
+    def Measurement(self, k, filter_index=0):
+        """noise.go:133-137"""
+        return self._sample(k, filter_index)[1]
 
     def __str__(self):
         return "AWGN{\nQ=%s\nR=%s}\n" % (self.Q, self.R)
 
 
-def NewAWGN(Q, R, seed=None):
-    return AWGN(Q, R, seed)
+def NewAWGN(Q, R, seed=None, device=0):
+    return AWGN(Q, R, seed, device)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -251,14 +268,27 @@ class _Filter:
     def n_filters(self):
         return self._nf
 
-    def _alloc_out(self, steps, every_step, want, innov_len):
+    def _alloc_out(self, steps, every_step, want, innov_len, buffers=None):
+        """buffers: optional dict of caller-owned C-contiguous float64 arrays (e.g. pinned host memory) to receive the
+        fields named by their keys (+ "status": int32 [n_filters]); anything missing is allocated here."""
         n, m, nf = self._n, self._m, self._nf
         rows = steps if every_step else 1
         sizes = {"state": n, "meas": m, "innov": innov_len, "covar": n * n, "pred_covar": n * n, "gain": n * m,
                  "obs_dev": m}
         shape = (lambda c: (rows, nf, c)) if self._fm else (lambda c: (rows, c, nf))
-        fields = {k: np.zeros(shape(sizes[k])) for k in _OUT_FIELDS if k in want and sizes[k] > 0}
-        status = np.zeros(nf, dtype=np.int32)
+        buffers = buffers or {}
+
+        def field(k):
+            b = buffers.get(k)
+            if b is None:
+                return np.zeros(shape(sizes[k]))
+            if b.dtype != np.float64 or not b.flags["C_CONTIGUOUS"] or b.size != int(np.prod(shape(sizes[k]))):
+                raise GkbError(-10, "output buffer %r must be a C-contiguous float64 array of %d elements" % (k, int(np.prod(shape(sizes[k])))))
+            return b.reshape(shape(sizes[k]))
+        fields = {k: field(k) for k in _OUT_FIELDS if k in want and sizes[k] > 0}
+        status = buffers.get("status")
+        if status is None:
+            status = np.zeros(nf, dtype=np.int32)
         out = _lib.Outputs()
         out.mem, out.every_step = _lib.HOST, int(every_step)
         for k, a in fields.items():
@@ -353,10 +383,8 @@ class _LDKF(_Filter):
 
     def _apply_noise(self, noise, set_matrices=True):
         lib = _lib.load()
-        if isinstance(noise, AWGN):
-            if self._kind != _lib.PREDICTOR:
-                raise NotImplementedError("AWGN drives the Monte Carlo pure predictor; give a tested filter "
-                                          "Noiseless(Q, R) or ReplayNoise (examples/robot/main.go:32-33)")
+        if isinstance(noise, AWGN) and self._fm:
+            raise NotImplementedError("large-state handles carry Noiseless noise only")
         if set_matrices:
             Q, R = _mat(noise.ProcessMatrix()), _mat(noise.MeasurementMatrix())
             _lib.check(lib.gkb_set_noise(self._h, _ptr(Q), R.shape[0], _ptr(R)))
@@ -372,6 +400,8 @@ class _LDKF(_Filter):
                 return np.ascontiguousarray(a.reshape(steps, comps, self._nf))
             w, v = soa(w, self._n), soa(v, self._m)
             _lib.check(lib.gkb_set_replay_noise(self._h, steps, _ptr(w), _ptr(v), _lib.HOST))
+        if isinstance(noise, AWGN):  # samples drawn on the device, keyed by (seed, filter, step)
+            _lib.check(lib.gkb_set_philox_noise(self._h, noise.seed, 0))
         self.Noise = noise
 
     def SetNoise(self, n):
@@ -380,6 +410,8 @@ class _LDKF(_Filter):
     def Reset(self):
         _lib.check(_lib.load().gkb_reset(self._h))
         self.Noise.Reset()
+        if isinstance(self.Noise, AWGN):  # Reset() re-seeds an AWGN (noise.go:145-159): re-arm the handle with the new stream
+            _lib.check(_lib.load().gkb_set_philox_noise(self._h, self.Noise.seed, 0))
 
     def __str__(self):
         return "F=%s\nG=%s\nH=%s\n%s" % (self.F, self.G, self.H, self.Noise)
@@ -536,7 +568,7 @@ class _NLDKF(_Filter):
     def Predict(self):
         return self._one(False, None, None)
 
-    def RunBatch(self, flags, Phi, Htilde, real_obs, computed_obs, Gamma=None, every_step=True, want=None):
+    def RunBatch(self, flags, Phi, Htilde, real_obs, computed_obs, Gamma=None, every_step=True, want=None, out_buffers=None):
         """Batched entry point: `steps` epochs of Prepare + Update/Predict in one kernel launch.
         Phi: [steps, n, n] (shared) or [steps, n*n, n_filters]; Htilde likewise; observations
         [steps, m] or [steps, m, n_filters]; flags uint8[steps]; Gamma [steps, n, q] (shared)."""
@@ -564,7 +596,7 @@ class _NLDKF(_Filter):
         real_obs, computed_obs = obs(real_obs), obs(computed_obs)
         if Gamma is not None:
             Gamma = np.ascontiguousarray(_arr(Gamma).reshape(steps, -1))
-        out, fields, status = self._alloc_out(steps, every_step, want or self._want, self._innov_len())
+        out, fields, status = self._alloc_out(steps, every_step, want or self._want, self._innov_len(), out_buffers)
         _lib.check(lib.gkb_nl_run(self._h, steps, _ptr(flags), _ptr(Phi), phi_shared, _ptr(Htilde), h_shared,
                                   _ptr(real_obs), _ptr(computed_obs), _ptr(Gamma), _lib.HOST, C.byref(out)))
         self._raise_status(status)
@@ -632,7 +664,8 @@ class HybridKF(_NLDKF):
         dense Joseph form -- the validation twin of the production kernels."""
         _lib.check(_lib.load().gkb_set_strict(self._h, int(bool(on))))
 
-    def RunOD(self, scenario, orbit0, sigma_range, sigma_rate, seed, flags=None, every_step=False, filter_offset=0):
+    def RunOD(self, scenario, orbit0, sigma_range, sigma_rate, seed, flags=None, every_step=False, filter_offset=0,
+              out_buffers=None):
         """The fused OD run (gkb_od_run): per epoch the reference orbit / STM / range + range-rate partials /
         observations of every filter are computed on the device (gokalman_b200.od.Scenario holds the per-epoch
         station and truth tables) and consumed by Prepare + Update / Predict in the same kernel.  orbit0:
@@ -641,7 +674,7 @@ class HybridKF(_NLDKF):
         steps = scenario.steps
         flags = scenario.flags if flags is None else np.ascontiguousarray(np.asarray(flags, dtype=np.uint8))
         cfg = scenario.config(orbit0, sigma_range, sigma_rate, seed, filter_offset)
-        out, fields, status = self._alloc_out(steps, every_step, ("state", "covar"), self._m)
+        out, fields, status = self._alloc_out(steps, every_step, ("state", "covar"), self._m, out_buffers)
         _lib.check(_lib.load().gkb_od_run(self._h, C.byref(cfg), steps, flags.ctypes.data, C.byref(out)))
         self._raise_status(status)
         return Estimate(self._n, self._m, fields, status)
@@ -730,9 +763,13 @@ class MonteCarloRuns:
     recipe (model, noise seed, controls) that the fused kernel regenerates on demand -- Philox is
     counter-based, so NewChiSquare sees exactly the trajectories Mean/StdDev/Truth describe."""
 
-    def __init__(self, samples, steps, rowsH, controls, kf, trial_offset=0):
+    def __init__(self, samples, steps, rowsH, controls, kf, trial_offset=0, devices=None, reduce="nccl"):
         self.runs, self.steps, self.rowsH = samples, steps, rowsH
         self.kf, self.controls, self.trial_offset = kf, controls, trial_offset
+        # devices: the runs are sharded over these GPUs of this process (gkb_mc_chisquare_multi: contiguous trial
+        # ranges, one collective -- NCCL all-reduce or the rank-ordered peer-memory sum -- inside the C-ABI)
+        self.devices = None if devices is None else [int(d) for d in devices]
+        self.reduce = {"nccl": _lib.REDUCE_NCCL, "peer": _lib.REDUCE_PEER}[reduce]
         self.noise = kf.Noise
         self._stats = None
 
@@ -801,7 +838,11 @@ class MonteCarloRuns:
         if want_status:
             res["status"] = np.zeros(runs, dtype=np.int32)
             out.status = res["status"].ctypes.data
-        _lib.check(_lib.load().gkb_mc_chisquare(C.byref(cfg), C.byref(out)))
+        if self.devices is not None:
+            devs = (C.c_int * len(self.devices))(*self.devices)
+            _lib.check(_lib.load().gkb_mc_chisquare_multi(C.byref(cfg), devs, len(self.devices), self.reduce, C.byref(out)))
+        else:
+            _lib.check(_lib.load().gkb_mc_chisquare(C.byref(cfg), C.byref(out)))
         return res
 
     def _get_stats(self):
@@ -856,11 +897,12 @@ def _controls(controls, steps):
     return np.stack(controls)
 
 
-def NewMonteCarloRuns(samples, steps, rowsH, controls, kf, trial_offset=0):
-    """montecarlo.go:92-119.  `kf` must be a pure predictor whose noise is AWGN (or ReplayNoise)."""
+def NewMonteCarloRuns(samples, steps, rowsH, controls, kf, trial_offset=0, devices=None, reduce="nccl"):
+    """montecarlo.go:92-119.  `kf` must be a pure predictor whose noise is AWGN (or ReplayNoise).  devices: shard the
+    runs over several GPUs of this process (Mean / StdDev / NewChiSquare then reduce across them inside the C-ABI)."""
     if not getattr(kf, "predictionOnly", False):
         raise ValueError("the Kalman filter needed for the Monte Carlo runs must be a pure predictor")
-    return MonteCarloRuns(samples, steps, rowsH, _controls(controls, steps), kf, trial_offset)
+    return MonteCarloRuns(samples, steps, rowsH, _controls(controls, steps), kf, trial_offset, devices, reduce)
 
 
 _KIND_OF = {Vanilla: _lib.VANILLA, Information: _lib.INFORMATION, SquareRoot: _lib.SQRT}

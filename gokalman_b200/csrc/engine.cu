@@ -6,6 +6,7 @@
 // work on the handle's stream (the legacy default stream unless gkb_set_stream is used), so a
 // caller can bracket them with its own CUDA events.  There is no CPU path anywhere in this file.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -170,9 +171,13 @@ struct gkb_filter {
   bool ekf = false;
   bool strict = false;  // gkb_set_strict: reference-order arithmetic (hybrid)
   DevBuf vec, mat, vec0, mat0, status;
-  DevBuf replay_w, replay_v;
+  DevBuf replay_w, replay_v, replay_w2;
   int replay_steps = 0;
   bool has_w = false, has_v = false;
+  // AWGN on this handle (gkb_set_philox_noise): the samples of each call are generated into the replay arrays
+  bool philox = false;
+  unsigned long long philox_seed = 0;
+  long long philox_offset = 0;
   DevBuf in_y, in_u, in_gu, in_a, in_b, in_c, in_d, in_e, in_f;  // staging for host inputs
   DevBuf o_state, o_meas, o_innov, o_covar, o_pred, o_gain, o_obsdev;
   // large-state handles (kernels_tile.cu): filter-major arrays, model kept on the device
@@ -264,7 +269,7 @@ static void destroy_filter(gkb_filter* f) {
     for (int b = 0; b < 2; ++b) { cudaEventDestroy(f->ev_h2d[b]); cudaEventDestroy(f->ev_done[b]); }
   }
   DevBuf* bufs[] = {&f->st_phi[0], &f->st_phi[1], &f->st_h[0], &f->st_h[1], &f->st_r[0], &f->st_r[1], &f->st_c[0], &f->st_c[1],
-                    &f->orbit, &f->od_tab, &f->sched, &f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
+                    &f->replay_w2, &f->orbit, &f->od_tab, &f->sched, &f->tile_model, &f->vec, &f->mat, &f->vec0, &f->mat0, &f->status, &f->replay_w, &f->replay_v, &f->in_y, &f->in_u, &f->in_gu,
                     &f->in_a, &f->in_b, &f->in_c, &f->in_d, &f->in_e, &f->in_f, &f->o_state, &f->o_meas, &f->o_innov,
                     &f->o_covar, &f->o_pred, &f->o_gain, &f->o_obsdev};
   for (DevBuf* b : bufs) b->release();
@@ -563,6 +568,69 @@ int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R) {
   // GKB_INFORMATION: inv(Q), inv(R) deliberately left stale (information.go:136-138)
   f->has_w = f->has_v = false;
   f->replay_steps = 0;
+  f->philox = false;  // SetNoise replaces the Noise object: an AWGN one is re-armed by gkb_set_philox_noise
+  return 0;
+}
+
+int gkb_set_philox_noise(gkb_filter* f, uint64_t seed, int64_t filter_offset) {
+  if (!f) return fail(GKB_ERR_ARG, "NULL handle");
+  if (f->tile) return fail(GKB_ERR_UNSUPPORTED, "large-state handles (n=%d) carry Noiseless noise only", f->hm.n);
+  if (f->hm.kind == GKB_HYBRID || f->hm.kind == GKB_SRIF)
+    return fail(GKB_ERR_UNSUPPORTED, "the NLDKF kinds never draw noise samples (hybrid.go / srif.go call neither Process nor Measurement)");
+  f->philox = true;
+  f->philox_seed = seed;
+  f->philox_offset = filter_offset;
+  f->has_w = f->has_v = false;
+  f->replay_steps = 0;
+  return 0;
+}
+
+namespace {
+// chol(Q), chol(R) of a model for the AWGN colouring (distmv.NewNormal, noise.go:146-153); GKB_ERR_ARG when either is
+// not positive definite (NewAWGN panics there, noise.go:149-156).
+int awgn_factors(const HostModel& hm, double* LQ, double* LR, cudaStream_t s) {
+  HostModel t = hm;
+  t.m = hm.m_r;
+  int rc = launch_model_setup(t, kOpSqrtQ | kOpSqrtR, nullptr, nullptr, s);
+  if (rc) return fail(rc, "noise factorisation failed (%d)", rc);
+  for (int i = 0; i < hm.n * hm.n; ++i) {
+    if (!std::isfinite(t.sqrtQ[i])) return fail(GKB_ERR_ARG, "process noise invalid: Q is not positive definite (noise.go:149-151)");
+    LQ[i] = t.sqrtQ[i];
+  }
+  for (int i = 0; i < hm.m_r * hm.m_r; ++i) {
+    if (!std::isfinite(t.sqrtR[i])) return fail(GKB_ERR_ARG, "measurement noise invalid: R is not positive definite (noise.go:154-156)");
+    LR[i] = t.sqrtR[i];
+  }
+  return 0;
+}
+}  // namespace
+
+int gkb_awgn_sample(int n, int m, const double* Q, const double* R, uint64_t seed, int64_t filter, int step, int device,
+                    double* w, double* v, double* w2) {
+  if (!Q || !R) return fail(GKB_ERR_ARG, "NULL argument");
+  if (n < 1 || n > GKB_MAX_N || m < 1 || m > GKB_MAX_M) return fail(GKB_ERR_UNSUPPORTED, "n=%d m=%d outside 1..%d / 1..%d", n, m, GKB_MAX_N, GKB_MAX_M);
+  if (!gkb_shape_supported(GKB_VANILLA, n, m)) return fail(GKB_ERR_UNSUPPORTED, "no compiled setup kernel for n=%d m=%d", n, m);
+  int rc = check_device(device);
+  if (rc) return rc;
+  cudaStream_t s = cudaStreamLegacy;
+  HostModel hm;
+  memset(&hm, 0, sizeof hm);
+  hm.n = n; hm.m = m; hm.m_r = m;
+  sym_from_upper(hm.Q, Q, n);
+  sym_from_upper(hm.R, R, m);
+  double LQ[GKB_MAX_N * GKB_MAX_N], LR[GKB_MAX_M * GKB_MAX_M];
+  if ((rc = awgn_factors(hm, LQ, LR, s))) return rc;
+  DevBuf d;
+  if ((rc = d.ensure(sizeof(double) * (size_t)(2 * n + m)))) return rc;
+  double* dw = d.as<double>();
+  launch_awgn_fill(n, m, LQ, LR, seed, filter, 1, 1, step, dw, dw + n, dw + n + m, s);
+  double h[2 * GKB_MAX_N + GKB_MAX_M];
+  cudaError_t e = cudaMemcpy(h, dw, sizeof(double) * (size_t)(2 * n + m), cudaMemcpyDeviceToHost);
+  d.release();
+  if (e != cudaSuccess) return fail(GKB_ERR_CUDA, "AWGN sample failed: %s", cudaGetErrorString(e));
+  if (w) memcpy(w, h, sizeof(double) * n);
+  if (v) memcpy(v, h + n, sizeof(double) * m);
+  if (w2) memcpy(w2, h + n + m, sizeof(double) * n);
   return 0;
 }
 
@@ -574,6 +642,7 @@ int gkb_set_replay_noise(gkb_filter* f, int steps, const double* w, const double
   const cudaMemcpyKind kind = mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   int rc;
   f->has_w = f->has_v = false;
+  f->philox = false;
   if (w) {
     const size_t bytes = sizeof(double) * (size_t)steps * f->hm.n * f->nf;
     if ((rc = f->replay_w.ensure(bytes))) return rc;
@@ -779,6 +848,22 @@ int gkb_update(gkb_filter* f, int steps, const double* y, int y_shared, const do
   io.w = f->has_w ? f->replay_w.as<double>() : nullptr;
   io.v = f->has_v ? f->replay_v.as<double>() : nullptr;
   io.replay_steps = f->replay_steps;
+  if (f->philox) {
+    // AWGN: this call's Process / Measurement samples, keyed by (filter, absolute step), into the replay arrays
+    if (hm.m_r != m) return fail(GKB_ERR_DIMS, "dimensions must agree: H has %d rows but R is %dx%d", m, hm.m_r, hm.m_r);
+    double LQ[GKB_MAX_N * GKB_MAX_N], LR[GKB_MAX_M * GKB_MAX_M];
+    if ((rc = awgn_factors(hm, LQ, LR, f->stream))) return rc;
+    const size_t wb = sizeof(double) * (size_t)steps * n * f->nf, vb = sizeof(double) * (size_t)steps * m * f->nf;
+    if ((rc = f->replay_w.ensure(wb)) || (rc = f->replay_v.ensure(vb)) || (rc = f->replay_w2.ensure(wb))) return rc;
+    const bool second = hm.kind == GKB_VANILLA;  // only Vanilla.Update calls Process(k) twice (vanilla.go:146,195)
+    launch_awgn_fill(n, m, LQ, LR, f->philox_seed, f->philox_offset, f->nf, steps, f->step, f->replay_w.as<double>(),
+                     f->replay_v.as<double>(), second ? f->replay_w2.as<double>() : nullptr, f->stream);
+    io.w = f->replay_w.as<double>();
+    io.v = f->replay_v.as<double>();
+    io.w2 = second ? f->replay_w2.as<double>() : nullptr;
+    io.step0 = 0;
+    io.replay_steps = steps;
+  }
   const int innov_len = (hm.kind == GKB_INFORMATION) ? n : m;
   OutPlan pl;
   if ((rc = plan_outputs(f, out, steps, innov_len, pl))) return rc;
@@ -1222,11 +1307,26 @@ struct McScratch {
   DevBuf partial, out, u, gu, gu_f, w, v, err;
   McSetupCache setup_truth, setup_filter;
   int device = -1;
+  cudaEvent_t done = nullptr;  // multi-device runs: "this shard's sums are in `out`"
+  void release() {  // the buffers live on `device`
+    if (device >= 0) cudaSetDevice(device);
+    DevBuf* bufs[] = {&partial, &out, &u, &gu, &gu_f, &w, &v, &err};
+    for (DevBuf* b : bufs) b->release();
+    if (done) cudaEventDestroy(done);
+    done = nullptr;
+    setup_truth.valid = setup_filter.valid = false;
+    device = -1;
+  }
 };
-thread_local McScratch g_mc;
+constexpr int kMcMaxShards = 16;
+// slot 0 serves gkb_mc_chisquare; gkb_mc_chisquare_multi uses one slot per shard (two shards may share a device)
+thread_local McScratch g_mc_slots[kMcMaxShards];
 }  // namespace
 
-int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
+// The body of gkb_mc_chisquare on one scratch slot.  raw_xstats < 0: the normal call (outputs copied to `out`);
+// raw_xstats = 0 / 1: a shard of a multi-device run -- the per-step SUMS (and, with 1, the Mean / StdDev columns) are
+// left in g_mc.out [cols][steps] on the device, the error word in g_mc.err, nothing is copied out, no host sync.
+static int mc_run(const gkb_mc_config* cfg, const gkb_mc_outputs* out, McScratch& g_mc, int raw_xstats) {
   if (!cfg || !out) return fail(GKB_ERR_ARG, "NULL argument");
   if (!cfg->with_nees && !cfg->with_nis)
     return fail(GKB_ERR_ARG, "Chi Square requires either NEES or NIS or both");  // chisquare.go:17-19
@@ -1246,7 +1346,8 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   if (rc) return rc;
   cudaStream_t s = cudaStreamLegacy;
   if (g_mc.device != cfg->device) {
-    g_mc = McScratch();
+    g_mc.release();
+    cudaSetDevice(cfg->device);
     g_mc.device = cfg->device;
   }
   // tm: the truth generator (the pure predictor of NewMonteCarloRuns, montecarlo.go:92, with its AWGN's Q, R);
@@ -1300,7 +1401,7 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   io.seed = cfg->seed;
   io.with_nees = cfg->with_nees;
   io.with_nis = cfg->with_nis;
-  io.want_xstats = (out->sum_d || out->sum_dd || out->x_ref) ? 1 : 0;
+  io.want_xstats = raw_xstats >= 0 ? raw_xstats : ((out->sum_d || out->sum_dd || out->x_ref) ? 1 : 0);
   const int cols = mc_cols(n, io.want_xstats);
   if (cfg->controls && c > 0 && (tm.need_ctrl || hm.need_ctrl)) {
     // montecarlo.go:98-104 replaces a single control vector by zeros: an all-zero control stream adds
@@ -1380,10 +1481,11 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
   rc = launch_mc(tm, hm, io, cfg->device, &grid, s);
   timer.main_end();
   if (rc) return fail(rc, "no Monte Carlo kernel for kind=%d n=%d m=%d", hm.kind, n, m);
-  const double scale = out->sums_only ? 1.0 : 1.0 / (double)cfg->trials;  // stat.Mean, chisquare.go:85-92
+  const double scale = (out->sums_only || raw_xstats >= 0) ? 1.0 : 1.0 / (double)cfg->trials;  // stat.Mean, chisquare.go:85-92
   launch_mc_finish(io.partial, grid, steps, cols, scale, g_mc.out.as<double>(), s);
   timer.stop(2, sync);
   GKB_CUDA(cudaGetLastError());
+  if (raw_xstats >= 0) return 0;  // a shard of gkb_mc_chisquare_multi: the caller reduces g_mc.out across devices
   const cudaMemcpyKind back = out->mem == GKB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   const double* o = g_mc.out.as<double>();
   const size_t sb = sizeof(double) * (size_t)steps;
@@ -1413,6 +1515,179 @@ int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) {
     GKB_CUDA(cudaStreamSynchronize(s));
   }
   d_tx.release(); d_ty.release(); d_nw.release(); d_nv.release(); d_st.release();
+  return 0;
+}
+
+int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out) { return mc_run(cfg, out, g_mc_slots[0], -1); }
+
+// ---- the same over several GPUs of this process, with the collective inside the ABI -----------------------
+namespace {
+// NCCL is bound at run time (dlopen): the library has no link-time dependency on it, a Python process that imported
+// torch already carries torch's bundled libnccl, and a cgo caller gets the system one.
+struct NcclApi {
+  void* lib = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api = []() {
+    NcclApi a;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (a.lib) break;
+    }
+    if (!a.lib) return a;
+    a.CommInitAll = reinterpret_cast<int (*)(void**, int, const int*)>(dlsym(a.lib, "ncclCommInitAll"));
+    a.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(a.lib, "ncclCommDestroy"));
+    a.GroupStart = reinterpret_cast<int (*)()>(dlsym(a.lib, "ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<int (*)()>(dlsym(a.lib, "ncclGroupEnd"));
+    a.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(a.lib, "ncclAllReduce"));
+    a.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(a.lib, "ncclGetErrorString"));
+    a.ok = a.CommInitAll && a.CommDestroy && a.GroupStart && a.GroupEnd && a.AllReduce;
+    return a;
+  }();
+  return api;
+}
+// one communicator set per device list, kept for the life of the process (ncclCommInitAll costs ~100 ms)
+struct NcclComms {
+  std::vector<int> devices;
+  std::vector<void*> comms;
+};
+NcclComms* nccl_comms_for(const int* devices, int n) {
+  static std::vector<NcclComms*> cache;
+  for (NcclComms* c : cache)
+    if ((int)c->devices.size() == n && std::equal(devices, devices + n, c->devices.begin())) return c;
+  NcclApi& api = nccl_api();
+  if (!api.ok) return nullptr;
+  NcclComms* c = new NcclComms();
+  c->devices.assign(devices, devices + n);
+  c->comms.assign(n, nullptr);
+  if (api.CommInitAll(c->comms.data(), n, devices) != 0) {
+    delete c;
+    return nullptr;
+  }
+  cache.push_back(c);
+  return c;
+}
+
+// out0[j] += sum_i peer[i][j] (i = 1 .. n-1, in shard order: a fixed, rank-ordered sum) for j < count, through
+// peer-memory loads (NVLink / NVSwitch P2P) -- the whole "collective" of this path is 2 x steps doubles.
+struct PeerPtrs { const double* p[kMcMaxShards]; int n; };
+__global__ void mc_peer_reduce_kernel(double* __restrict__ out0, const __grid_constant__ PeerPtrs peers, int count) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  double s = out0[j];
+  for (int i = 1; i < peers.n; ++i) s += peers.p[i][j];
+  out0[j] = s;
+}
+}  // namespace
+
+int gkb_mc_chisquare_multi(const gkb_mc_config* cfg, const int* devices, int n_devices, int reduce, const gkb_mc_outputs* out) {
+  if (!cfg || !out || !devices) return fail(GKB_ERR_ARG, "NULL argument");
+  if (n_devices < 1 || n_devices > kMcMaxShards) return fail(GKB_ERR_ARG, "n_devices %d outside 1..%d", n_devices, kMcMaxShards);
+  if (reduce != GKB_REDUCE_NCCL && reduce != GKB_REDUCE_PEER) return fail(GKB_ERR_ARG, "unknown reduction mode %d", reduce);
+  if (out->mem != GKB_HOST) return fail(GKB_ERR_UNSUPPORTED, "gkb_mc_chisquare_multi writes host outputs");
+  if (out->truth_x || out->truth_y || out->noise_w || out->noise_v || out->status)
+    return fail(GKB_ERR_UNSUPPORTED, "per-trial dumps are single-device outputs (gkb_mc_chisquare)");
+  if (cfg->noise_mode != GKB_NOISE_PHILOX) return fail(GKB_ERR_UNSUPPORTED, "multi-device runs draw their noise from Philox (keyed by the global trial index)");
+  if (cfg->trials < n_devices) return fail(GKB_ERR_ARG, "fewer trials (%lld) than devices (%d)", (long long)cfg->trials, n_devices);
+  if (reduce == GKB_REDUCE_NCCL)
+    for (int i = 0; i < n_devices; ++i)
+      for (int j = 0; j < i; ++j)
+        if (devices[i] == devices[j]) return fail(GKB_ERR_ARG, "NCCL needs distinct devices (device %d is listed twice)", devices[i]);
+  const int n = cfg->n, steps = cfg->steps;
+  const int xstats = (out->sum_d || out->sum_dd || out->x_ref) ? 1 : 0;
+  const int cols = mc_cols(n, xstats);
+  const int sum_count = (kMcBaseCols + (xstats ? 2 * n : 0)) * steps;  // the x_ref columns are identical on every device: not summed
+  int rc;
+  // 1. every device runs its contiguous trial range; nothing here waits for a kernel
+  gkb_mc_outputs raw;
+  memset(&raw, 0, sizeof raw);
+  raw.mem = GKB_DEVICE;
+  raw.sums_only = 1;
+  const int64_t base = cfg->trials / n_devices, rem = cfg->trials % n_devices;
+  for (int i = 0; i < n_devices; ++i) {
+    gkb_mc_config ci = *cfg;
+    const int64_t lo = (int64_t)i * base + std::min<int64_t>(i, rem);
+    ci.device = devices[i];
+    ci.trials = base + (i < rem ? 1 : 0);
+    ci.trial_offset = cfg->trial_offset + lo;
+    McScratch& sc = g_mc_slots[i];
+    if ((rc = mc_run(&ci, &raw, sc, xstats))) return rc;
+    if (!sc.done) GKB_CUDA(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
+    GKB_CUDA(cudaEventRecord(sc.done, cudaStreamLegacy));
+  }
+  // 2. the one collective of the path: the per-step sums
+  McScratch& s0 = g_mc_slots[0];
+  if (n_devices > 1 && reduce == GKB_REDUCE_NCCL) {
+    NcclApi& api = nccl_api();
+    NcclComms* cm = nccl_comms_for(devices, n_devices);
+    if (!api.ok || !cm) return fail(GKB_ERR_CUDA, "NCCL is not available in this process (dlopen libnccl.so.2 / ncclCommInitAll failed): use GKB_REDUCE_PEER");
+    int nrc = api.GroupStart();
+    for (int i = 0; i < n_devices && nrc == 0; ++i) {
+      cudaSetDevice(devices[i]);
+      double* b = g_mc_slots[i].out.as<double>();
+      nrc = api.AllReduce(b, b, (size_t)sum_count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, cm->comms[i], cudaStreamLegacy);
+    }
+    const int erc = api.GroupEnd();
+    if (nrc != 0 || erc != 0) return fail(GKB_ERR_CUDA, "ncclAllReduce failed: %s", api.GetErrorString ? api.GetErrorString(nrc ? nrc : erc) : "?");
+  } else if (n_devices > 1) {
+    GKB_CUDA(cudaSetDevice(devices[0]));
+    PeerPtrs pp;
+    pp.n = n_devices;
+    DevBuf staged[kMcMaxShards];
+    for (int i = 1; i < n_devices; ++i) {
+      GKB_CUDA(cudaStreamWaitEvent(cudaStreamLegacy, g_mc_slots[i].done, 0));
+      int can = devices[i] == devices[0] ? 1 : 0;
+      if (!can) {
+        cudaDeviceCanAccessPeer(&can, devices[0], devices[i]);
+        if (can) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(devices[i], 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+          else if (e != cudaSuccess) { can = 0; (void)cudaGetLastError(); }
+        }
+      }
+      if (can) {
+        pp.p[i] = g_mc_slots[i].out.as<double>();
+      } else {  // no P2P mapping between the two devices: bring the 16 KB over with a peer copy
+        if ((rc = staged[i].ensure(sizeof(double) * (size_t)sum_count))) return rc;
+        GKB_CUDA(cudaMemcpyPeerAsync(staged[i].p, devices[0], g_mc_slots[i].out.p, devices[i], sizeof(double) * (size_t)sum_count, cudaStreamLegacy));
+        pp.p[i] = staged[i].as<double>();
+      }
+    }
+    pp.p[0] = s0.out.as<double>();
+    mc_peer_reduce_kernel<<<(sum_count + 255) / 256, 256, 0, cudaStreamLegacy>>>(s0.out.as<double>(), pp, sum_count);
+    GKB_CUDA(cudaGetLastError());
+    GKB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    for (int i = 1; i < n_devices; ++i) staged[i].release();
+  }
+  // 3. results from device 0; the error words from every device
+  GKB_CUDA(cudaSetDevice(devices[0]));
+  std::vector<double> h((size_t)cols * steps);
+  GKB_CUDA(cudaMemcpy(h.data(), s0.out.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+  int32_t first = 0;
+  for (int i = 0; i < n_devices; ++i) {
+    GKB_CUDA(cudaSetDevice(devices[i]));
+    int32_t e = 0;
+    GKB_CUDA(cudaMemcpy(&e, g_mc_slots[i].err.p, sizeof e, cudaMemcpyDeviceToHost));  // also waits for device i
+    if (e != 0 && first == 0) first = e;
+  }
+  const double scale = out->sums_only ? 1.0 : 1.0 / (double)cfg->trials;  // stat.Mean over ALL trials, chisquare.go:85-92
+  for (int k = 0; k < steps; ++k) {
+    if (out->nis) out->nis[k] = h[k] * scale;
+    if (out->nees) out->nees[k] = h[(size_t)steps + k] * scale;
+    for (int i = 0; i < n && xstats; ++i) {
+      if (out->sum_d) out->sum_d[(size_t)k * n + i] = h[(size_t)(kMcBaseCols + i) * steps + k];
+      if (out->sum_dd) out->sum_dd[(size_t)k * n + i] = h[(size_t)(kMcBaseCols + n + i) * steps + k];
+      if (out->x_ref) out->x_ref[(size_t)k * n + i] = h[(size_t)(kMcBaseCols + 2 * n + i) * steps + k];
+    }
+  }
+  if (out->first_error) *out->first_error = first;
   return 0;
 }
 

@@ -49,6 +49,7 @@ struct LtiIo {
   const double* gu;  // [steps][n]: G u per step (gu_kernel), nullptr = no control term
   const double* w;  // replay noise [replay_steps][n][nf] or nullptr
   const double* v;  // [replay_steps][m_v][nf] or nullptr
+  const double* w2; // Vanilla only: what the SECOND Process(k) call returns (AWGN draws afresh), nullptr = w again
   int replay_steps;
   int every_step;
   double *o_state, *o_meas, *o_innov, *o_covar, *o_pred, *o_gain, *o_obsdev;
@@ -169,6 +170,11 @@ int launch_od_synth(const OdParams& c, int64_t nf, int steps, double* orbit, con
 // The fused run: synthesis + hybrid CKF / EKF step per epoch, no streams in HBM (n = 6, m = 2 only).
 int launch_od_run(const HostModel& hm, const OdParams& c, const NlIo& io, double* orbit, const double* station,
                   const double* tobs, cudaStream_t s);
+// AWGN samples on the device (kernels_noise.cu): for filters [0, nf) and steps [step0, step0 + steps), the coloured
+// draws w = LQ z[0:n], v = LR z[n:n+m], w2 = LQ z[n+m:2n+m] of z = Philox normals of (seed, filter_offset + filter, step),
+// written SoA [steps][component][nf].  LQ [n*n], LR [m*m] are host arrays (lower Cholesky factors).
+int launch_awgn_fill(int n, int m, const double* LQ, const double* LR, unsigned long long seed, long long filter_offset,
+                     int64_t nf, int steps, int step0, double* w, double* v, double* w2, cudaStream_t s);
 // Large-state Vanilla (kernels_tile.cu): n in {16, 24, 32}, m <= 8.
 int tile_shape_supported(int n, int m);
 int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s);

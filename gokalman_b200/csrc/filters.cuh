@@ -77,10 +77,12 @@ struct StepOut {
 // gu = G u (formed once per step for all filters by gu_kernel).  NOISY = false compiles out the
 // "+ Process(k)" / "+ Measurement(k)" additions for a Noiseless filter (they would add +0.0);
 // CHECK = false drops the engine's own non-finite guard (the reference has none).
+// w is what the first Process(k) call returns (vanilla.go:146), w2 what the second one returns (vanilla.go:195):
+// the same vector for BatchNoise-style replay (noise.go:73-78), two different draws for AWGN (noise.go:127-131).
 template <int N, int M, bool PREDICTOR, bool NOISY = true, bool CHECK = true>
 GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&P)[N * (N + 1) / 2],
                          const double (&y)[M], const double (&gu)[N], const double (&w)[N],
-                         const double (&v)[M], StepOut<N, M>& o) {
+                         const double (&v)[M], StepOut<N, M>& o, const double (&w2)[N]) {
   constexpr int SN = N * (N + 1) / 2;
   // 138-146: x- = F x + G u + Process(k)
   double xm[N];
@@ -181,7 +183,7 @@ GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&
       double s = o.K[i * M] * o.innov[0];
 #pragma unroll
       for (int a = 1; a < M; ++a) s = fma(o.K[i * M + a], o.innov[a], s);
-      xp[i] = NOISY ? ((xm[i] + s) + w[i]) : (xm[i] + s);
+      xp[i] = NOISY ? ((xm[i] + s) + w2[i]) : (xm[i] + s);
     }
     // 197-205: Joseph form, restructured (see header)
     double Pp[SN];
@@ -225,6 +227,14 @@ GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&
     for (int i = 0; i < SN; ++i) P[i] = Pp[i];
     return 0;
   }
+}
+
+// BatchNoise / Noiseless form: both Process(k) calls see the same vector.
+template <int N, int M, bool PREDICTOR, bool NOISY = true, bool CHECK = true>
+GKB_DEV int vanilla_step(const VanillaModel<N, M>& md, double (&x)[N], double (&P)[N * (N + 1) / 2],
+                         const double (&y)[M], const double (&gu)[N], const double (&w)[N],
+                         const double (&v)[M], StepOut<N, M>& o) {
+  return vanilla_step<N, M, PREDICTOR, NOISY, CHECK>(md, x, P, y, gu, w, v, o, w);
 }
 
 }  // namespace gkb

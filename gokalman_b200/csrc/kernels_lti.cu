@@ -76,7 +76,13 @@ vanilla_update_kernel(const __grid_constant__ VanillaModel<N, M> md, const __gri
       for (int i = 0; i < N; ++i) gu[i] = __ldg(io.gu + (int64_t)k * N + i);
     }
     StepOut<N, M> o;
-    if (err == 0) err = vanilla_step<N, M, PREDICTOR>(md, x, P, y, gu, w, v, o);
+    if (io.w2 != nullptr) {  // AWGN: the second Process(k) call of the step draws afresh (noise.go:127-131)
+      double w2[N];
+      load_soa<N>(w2, io.w2 + (int64_t)(io.step0 + k) * N * io.nf, io.nf, tid);
+      if (err == 0) err = vanilla_step<N, M, PREDICTOR>(md, x, P, y, gu, w, v, o, w2);
+    } else if (err == 0) {
+      err = vanilla_step<N, M, PREDICTOR>(md, x, P, y, gu, w, v, o);
+    }
     if (err != 0) {
       if (status == 0) status = err;
       continue;  // like the reference, a failed Update leaves the previous estimate in place

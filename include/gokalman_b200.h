@@ -108,6 +108,19 @@ int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R);
  * [steps][n][n_filters], v is [steps][m][n_filters] (either may be NULL = zeros), `mem` says
  * where they live; they are copied.  Cleared by gkb_set_noise. */
 int gkb_set_replay_noise(gkb_filter* f, int steps, const double* w, const double* v, int mem);
+/* AWGN noise (noise.go:109-159) on an ordinary LDKF handle: from now on Noise.Process(k) / Noise.Measurement(k) are
+ * drawn on the device from Philox4x32-10 keyed by (seed, filter_offset + filter, step k) and coloured with chol(Q),
+ * chol(R) of the handle's current noise matrices -- normals [0, n) for the first Process(k) call of a step,
+ * [n, n + m) for Measurement(k), [n + m, 2n + m) for Vanilla.Update's second Process(k) call (vanilla.go:195; the
+ * reference's AWGN also draws afresh there).  It is the stream gkb_mc_chisquare uses for (trial, step): a pure
+ * predictor with this noise reproduces NewMonteCarloRuns' truth sample for sample.  GKB_ERR_ARG at the next
+ * gkb_update when Q or R is not positive definite (NewAWGN panics, noise.go:149-156).  Cleared by gkb_set_noise
+ * and gkb_set_replay_noise. */
+int gkb_set_philox_noise(gkb_filter* f, uint64_t seed, int64_t filter_offset);
+/* The same samples on the host (AWGN.Process(k) / AWGN.Measurement(k) of the Go interface, noise.go:127-137), for ONE
+ * (filter, step): w [n] first Process draw, v [m] Measurement draw, w2 [n] second Process draw; any may be NULL. */
+int gkb_awgn_sample(int n, int m, const double* Q, const double* R, uint64_t seed, int64_t filter, int step, int device,
+                    double* w, double* v, double* w2);
 /* Reset() (vanilla.go:121-125): state <- initial estimate, step <- 0. */
 int gkb_reset(gkb_filter* f);
 /* Stream the handle's kernels and copies are enqueued on (a cudaStream_t; NULL = the legacy
@@ -292,6 +305,20 @@ typedef struct gkb_mc_outputs {
 } gkb_mc_outputs;
 
 int gkb_mc_chisquare(const gkb_mc_config* cfg, const gkb_mc_outputs* out);
+
+/* ---- the same run sharded over several GPUs of THIS process, collective included: device
+ *      devices[i] runs the contiguous trial range i of cfg->trials (TOTAL trials; Philox is keyed by the global trial
+ *      index cfg->trial_offset + trial, so the trajectories do not depend on the device count), then the per-step
+ *      NEES / NIS sums -- and the Mean / StdDev sums when out->sum_d / sum_dd are given -- are reduced:
+ *        GKB_REDUCE_NCCL  one ncclAllReduce (SUM, double, 2 x steps [+ 2 n steps]) over a communicator set created with
+ *                         ncclCommInitAll and cached per device list (libnccl.so.2 is bound with dlopen at first use);
+ *        GKB_REDUCE_PEER  one kernel on devices[0] that adds the peers' sums through NVLink peer-memory loads in
+ *                         shard order -- a fixed, rank-ordered sum: bit-reproducible for a given device list, and the
+ *                         only mode that accepts the same device twice.
+ *      cfg->device is ignored; outputs are host arrays (nis / nees means or sums, sum_d / sum_dd / x_ref, first_error);
+ *      per-trial dumps and replay noise are single-device features.  n_devices = 1 is gkb_mc_chisquare. */
+typedef enum gkb_reduce { GKB_REDUCE_NCCL = 0, GKB_REDUCE_PEER = 1 } gkb_reduce;
+int gkb_mc_chisquare_multi(const gkb_mc_config* cfg, const int* devices, int n_devices, int reduce, const gkb_mc_outputs* out);
 
 /* Device time (ms, CUDA events on the launch stream) of the kernels launched by the last
  * gkb_update / gkb_nl_run / gkb_mc_chisquare call on this thread, and how many kernels that was. */

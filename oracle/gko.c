@@ -43,6 +43,8 @@ struct gko_filter {
   /* replay noise (BatchNoise-style index by k, noise.go:73-86) */
   int replay_steps, replay_mv;
   double *replay_w, *replay_v;
+  double* replay_w2; /* optional: the vector the SECOND Process(k) call of Vanilla.Update returns (vanilla.go:195) --
+                        AWGN draws a fresh sample on every call (noise.go:127-131), BatchNoise repeats vector k */
   /* NLDKF */
   double *Phi, *Htilde, *Gamma;
   int has_htilde, ekf, locked, snc;
@@ -107,7 +109,7 @@ void gko_free(gko_filter* f) {
   free(f->F); free(f->G); free(f->H); free(f->Q); free(f->R);
   free(f->Finv); free(f->Qinv); free(f->Rinv); free(f->sqrtQ); free(f->sqrtR);
   free(f->x); free(f->A); free(f->x_init); free(f->A_init);
-  free(f->replay_w); free(f->replay_v);
+  free(f->replay_w); free(f->replay_v); free(f->replay_w2);
   free(f->Phi); free(f->Htilde); free(f->Gamma); free(f->sqrt_inv_noise);
   free(f->ws);
   free(f);
@@ -140,6 +142,15 @@ static int noise_process(const gko_filter* f, int k, double* w) {
   return 0;
 }
 
+static int noise_process_again(const gko_filter* f, int k, double* w) {
+  if (f->replay_w2) {
+    if (k >= f->replay_steps) return GKO_ERR_NOISE_RANGE;
+    dcopy(w, f->replay_w2 + (size_t)k * f->n, f->n);
+    return 0;
+  }
+  return noise_process(f, k, w);
+}
+
 static int noise_measurement(const gko_filter* f, int k, double* v) {
   int m = f->m;
   if (f->replay_v) {
@@ -151,9 +162,20 @@ static int noise_measurement(const gko_filter* f, int k, double* v) {
   return 0;
 }
 
+void gko_set_replay_second_draw(gko_filter* f, const double* w2) { /* after gko_set_replay: [replay_steps][n] */
+  free(f->replay_w2);
+  f->replay_w2 = NULL;
+  if (w2) {
+    f->replay_w2 = dalloc((size_t)f->replay_steps * f->n);
+    dcopy(f->replay_w2, w2, (size_t)f->replay_steps * f->n);
+  }
+}
+
 void gko_set_replay(gko_filter* f, int steps, const double* w, const double* v, int m_v) {
   free(f->replay_w);
   free(f->replay_v);
+  free(f->replay_w2);
+  f->replay_w2 = NULL;
   f->replay_w = f->replay_v = NULL;
   f->replay_steps = steps;
   f->replay_mv = m_v;
@@ -311,7 +333,8 @@ void gko_set_noise(gko_filter* f, const double* Q, int m_r, const double* R) {
   /* GKO_INFORMATION: Qinv/Rinv deliberately left stale (information.go:136-138) */
   free(f->replay_w);
   free(f->replay_v);
-  f->replay_w = f->replay_v = NULL;
+  free(f->replay_w2);
+  f->replay_w = f->replay_v = f->replay_w2 = NULL;
 }
 
 void gko_reset(gko_filter* f) { /* vanilla.go:121-125, information.go:146-150, squareroot.go:122-126 */
@@ -483,7 +506,7 @@ static int vanilla_update(gko_filter* f, const double* y, const double* u, gko_e
     gko_mulvec(xp, K, innov, n, m);
   }
   for (int i = 0; i < n; ++i) xp[i] = xm[i] + xp[i];
-  if ((ierr = noise_process(f, f->step, wk)) != 0) return ierr; /* second Process(k) call, 195 */
+  if ((ierr = noise_process_again(f, f->step, wk)) != 0) return ierr; /* second Process(k) call, 195 */
   for (int i = 0; i < n; ++i) xp[i] = xp[i] + wk[i];
   /* 197-205: Joseph form */
   gko_mul(KH, K, f->H, n, m, n);

@@ -93,6 +93,9 @@ void gko_set_noise(gko_filter* f, const double* Q, int m_r, const double* R);
 /* Replay noise: like noise.go BatchNoise (index by k) but carrying Q and R.  w is [steps][n],
  * v is [steps][m]; either may be NULL (zeros).  The arrays are copied. */
 void gko_set_replay(gko_filter* f, int steps, const double* w, const double* v, int m_v);
+/* AWGN semantics (noise.go:127-131: a fresh draw on every call): w2 [steps][n] is what the SECOND Process(k) call of
+ * Vanilla.Update (vanilla.go:195) returns; NULL = BatchNoise semantics (the same vector k twice). */
+void gko_set_replay_second_draw(gko_filter* f, const double* w2);
 void gko_reset(gko_filter* f);
 void gko_initial_estimate(const gko_filter* f, gko_estimate* est);
 

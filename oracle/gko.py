@@ -203,11 +203,17 @@ class Filter:
         R = np.atleast_2d(_a(R))
         lib().gko_set_noise(self.h, _p(_a(Q)), R.shape[0], _p(R))
 
-    def SetReplayNoise(self, w, v):
+    def SetReplayNoise(self, w, v, w2=None):
+        """w2: what the second Process(k) call of Vanilla.Update returns (AWGN draws afresh); None = w again."""
         w, v = _a(w), _a(v)
         steps = (w if w is not None else v).shape[0]
         mv = v.shape[1] if v is not None else self.m
         lib().gko_set_replay(self.h, steps, _p(w), _p(v), mv)
+        if w2 is not None:
+            L = lib()
+            L.gko_set_replay_second_draw.argtypes = [C.c_void_p, C.c_void_p]
+            L.gko_set_replay_second_draw.restype = None
+            L.gko_set_replay_second_draw(self.h, _p(_a(w2)))
 
     def Reset(self):
         lib().gko_reset(self.h)
