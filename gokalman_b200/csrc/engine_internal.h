@@ -120,7 +120,7 @@ struct McIo {
 };
 // columns of McIo::partial per step: NIS, NEES, then sum d_i (n), sum d_i^2 (n), xref_i (n), d = x - xref
 constexpr int kMcBaseCols = 2;
-constexpr int kMcChunk = 256;  // steps accumulated in shared memory between flushes to McIo::partial
+constexpr int kMcChunk = 64;   // steps accumulated in shared memory between flushes to McIo::partial (4 KB per CTA at 2 columns)
 inline int mc_cols(int n, int want_xstats) { return kMcBaseCols + (want_xstats ? 3 * n : 0); }
 
 // ---- launchers (each returns a gkb_status; GKB_ERR_UNSUPPORTED when the shape is not compiled) ----

@@ -15,6 +15,10 @@
 // resident CTAs per SM the register allocator must leave room for (measured on B200 for n = 3:
 // 5 CTAs of 128 threads = 96 registers is the fastest point, see DESIGN.md "tuning log")
 #define GKB_MC_MIN_CTAS(n, m, lean) (!(lean) ? 1 : ((n) <= 3 && (m) == 1) ? 5 : (n) <= 3 ? 4 : (n) == 4 ? 3 : 2)
+// The vanilla tested filter at n <= 3, m = 1 fits 72 registers without spills: 7 CTAs per SM run as fast as 5 on a full
+// GPU (18.95 ms for 10^6 x 1000) and keep a 125 000-trial shard (one eighth of 10^6: strong scaling on
+// 8 GPUs = 977 CTAs) resident in ONE wave of 148 x 7 = 1036 CTAs instead of 1.32 waves of 740.
+#define GKB_MC_MIN_CTAS_VANILLA(n, m, lean) (((lean) && (n) <= 3 && (m) == 1) ? 7 : GKB_MC_MIN_CTAS(n, m, lean))
 #endif
 #ifndef GKB_MC_HOIST_MODEL
 #define GKB_MC_HOIST_MODEL 0
@@ -73,6 +77,7 @@ GKB_DEV double warp_sum(double v) {
 template <int N, int M>
 struct VanillaTested {
   using Model = VanillaModel<N, M>;
+  static constexpr int min_ctas(bool lean) { return GKB_MC_MIN_CTAS_VANILLA(N, M, lean); }
   double x[N];
   double P[N * (N + 1) / 2];
   GKB_DEV void init(const McModel<N, M>& mm) {
@@ -123,6 +128,7 @@ struct VanillaTested {
 template <int N, int M>
 struct InfoTested {
   using Model = InfoModel<N, M>;
+  static constexpr int min_ctas(bool lean) { return GKB_MC_MIN_CTAS(N, M, lean); }
   double iv[N];
   double I[N * (N + 1) / 2];
   GKB_DEV void init(const McModel<N, M>& mm) {
@@ -189,6 +195,7 @@ struct InfoTested {
 template <int N, int M>
 struct SqrtTested {
   using Model = SqrtModel<N, M>;
+  static constexpr int min_ctas(bool lean) { return GKB_MC_MIN_CTAS(N, M, lean); }
   double x[N];
   double S[N * N];
   GKB_DEV void init(const McModel<N, M>& mm) {
@@ -267,7 +274,7 @@ struct SqrtTested {
 // NOCTRL (LEAN only) = the run has no control term (io.gu == nullptr: no G, or all-zero controls as in
 // montecarlo.go:98-104): the per-step control loads and selects are compiled out.
 template <int N, int M, class Tested, bool LEAN, bool NOCTRL = false>
-__global__ void __launch_bounds__(kThreads, GKB_MC_MIN_CTAS(N, M, LEAN))
+__global__ void __launch_bounds__(kThreads, Tested::min_ctas(LEAN))
 mc_chisquare_kernel(const __grid_constant__ McModel<N, M> mm_c, const __grid_constant__ typename Tested::Model md_c,
                     const __grid_constant__ McIo io) {
 #if GKB_MC_HOIST_MODEL
