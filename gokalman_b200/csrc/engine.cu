@@ -224,8 +224,8 @@ int gkb_shape_supported(int kind, int n, int m) {
   if (kind == GKB_VANILLA && tile_shape_supported(n, m)) return 1;
 #define GKB_CASE(NN, MM) \
   if (n == NN && m == MM) return 1;
-  if (kind == GKB_HYBRID || kind == GKB_SRIF) {
-    GKB_FOR_EACH_SHAPE(GKB_CASE)
+  if (kind == GKB_HYBRID || kind == GKB_SRIF) {  // n = 7, 8: general kernels only (kernels_nl_big.cu)
+    GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)
   } else {  // the LDKF kinds also have n = 7, 8 (batched Update kernels; the Monte Carlo harness stops at n = 6)
     GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)
   }

@@ -13,7 +13,8 @@ namespace gkb {
 
 // LDKF kinds (Vanilla / pure predictor / Information / Square root) also get n = 7 and 8 (the north star's "n <= 8"): slower
 // (the 8 x 8 intermediates no longer fit the registers: ptxas reports local memory) but correct, same parity bar.
-#define GKB_FOR_EACH_LTI_SHAPE(X) GKB_FOR_EACH_SHAPE(X) X(7, 1) X(7, 2) X(7, 3) X(8, 1) X(8, 2) X(8, 3)
+#define GKB_FOR_EACH_BIG_SHAPE(X) X(7, 1) X(7, 2) X(7, 3) X(8, 1) X(8, 2) X(8, 3)
+#define GKB_FOR_EACH_LTI_SHAPE(X) GKB_FOR_EACH_SHAPE(X) GKB_FOR_EACH_BIG_SHAPE(X)
 
 constexpr int kThreads = 128;  // threads per CTA for the register kernels
 
@@ -142,6 +143,7 @@ int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStrea
 int launch_gu(const double* G_host, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s);
 int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s);
 int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s);
+int launch_nl_run_big(const HostModel& hm, const NlIo& io, cudaStream_t s);  // kernels_nl_big.cu: n = 7, 8
 // kernels_nl_tma.cu: the TMA production path of the NLDKF kinds.  0 = launched, 1 = not applicable to this call.
 int launch_nl_tma(const HostModel& hm, const NlIo& io, cudaStream_t s);
 // SmoothAll (hybrid.go:209-238, srif.go:165-192) over stored [steps][C][nf] histories, in place.

@@ -55,7 +55,7 @@ def _check(est, refs, fields, tag):
             assert err <= TOL, (tag, fld, f, err)
 
 
-@pytest.mark.parametrize("n,m,q", [(6, 2, 3), (4, 2, 2), (3, 1, 0), (6, 3, 3)])
+@pytest.mark.parametrize("n,m,q", [(6, 2, 3), (4, 2, 2), (3, 1, 0), (6, 3, 3), (8, 3, 3), (7, 2, 2), (8, 1, 0)])
 def test_hybrid_ckf_ekf_snc_matches_oracle(oracle, n, m, q):
     """hybrid.go:104-204: Predict / CKF update / EKF update / SNC epochs mixed in one batched run
     with per-filter Phi, Htilde and observations (BASELINE config 4 shape is n=6, m=2, q=3)."""
@@ -277,7 +277,7 @@ def test_srif_tma_speculative_epoch_falls_back(oracle, n, m, nf):
         assert fx.scaled_err(vec[:, f], rv) <= TOL and fx.scaled_err(mat[:, :, f], np.asarray(rm).reshape(n, n)) <= TOL
 
 
-@pytest.mark.parametrize("n,m", [(6, 2), (4, 2), (3, 1)])
+@pytest.mark.parametrize("n,m", [(6, 2), (4, 2), (3, 1), (8, 2), (7, 3)])
 def test_srif_matches_oracle(oracle, n, m):
     """srif.go:101-160 with per-filter Phi / Htilde; State(), Covariance(), PredCovariance() read-outs."""
     gk = _gpu()
