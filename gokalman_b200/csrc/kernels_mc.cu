@@ -5,7 +5,17 @@
 namespace gkb {
 
 #ifndef GKB_MC_PART
-#error "compile with -DGKB_MC_PART=0..3 (see Makefile): 0 = dispatch + finish kernel, 1/2/3 = vanilla / information / sqrt kernels"
+#error "compile with -DGKB_MC_PART=0..6 (see Makefile): 0 = dispatch + finish kernel, 1/2/3 = vanilla / information / sqrt kernels for n <= 6, 4/5/6 = the same for n = 7, 8"
+#endif
+// parts 4-6 instantiate the n = 7, 8 shapes (the north star's "n <= 8"; spilled, slower, same parity bar) under *_big names
+#if GKB_MC_PART >= 4
+#define GKB_MC_SHAPES(X) GKB_FOR_EACH_BIG_SHAPE(X)
+#define GKB_MC_NAME(base) base##_big
+#define GKB_MC_KIND (GKB_MC_PART - 3)
+#else
+#define GKB_MC_SHAPES(X) GKB_FOR_EACH_SHAPE(X)
+#define GKB_MC_NAME(base) base
+#define GKB_MC_KIND GKB_MC_PART
 #endif
 #if GKB_MC_PART == 0
 // out[col][k] = scale * sum_b partial[b][k][col].  A CTA is 32 result slots x 8 row groups: thread (x, y) adds the CTA
@@ -76,7 +86,7 @@ static int pick_grid(Kern kern, size_t smem, int64_t trials, int device) {
   return (int)(g < 1 ? 1 : g);
 }
 
-#if GKB_MC_PART == 1
+#if GKB_MC_KIND == 1
 template <int N, int M>
 static int launch_mc_shape_vanilla(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
@@ -109,16 +119,16 @@ static int launch_mc_shape_vanilla(const HostModel& tm, const HostModel& hm, con
       }
 }
 
-int launch_mc_vanilla(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+int GKB_MC_NAME(launch_mc_vanilla)(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
   if (hm.n == NN && hm.m == MM) return launch_mc_shape_vanilla<NN, MM>(tm, hm, io, device, grid_out, s);
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_MC_SHAPES(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
 }
 #endif
 
-#if GKB_MC_PART == 2
+#if GKB_MC_KIND == 2
 template <int N, int M>
 static int launch_mc_shape_info(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
@@ -149,16 +159,16 @@ static int launch_mc_shape_info(const HostModel& tm, const HostModel& hm, const 
       }
 }
 
-int launch_mc_info(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+int GKB_MC_NAME(launch_mc_info)(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
   if (hm.n == NN && hm.m == MM) return launch_mc_shape_info<NN, MM>(tm, hm, io, device, grid_out, s);
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_MC_SHAPES(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
 }
 #endif
 
-#if GKB_MC_PART == 3
+#if GKB_MC_KIND == 3
 template <int N, int M>
 static int launch_mc_shape_sqrt(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
   const int cols = mc_cols(N, io.want_xstats);
@@ -187,10 +197,10 @@ static int launch_mc_shape_sqrt(const HostModel& tm, const HostModel& hm, const 
       }
 }
 
-int launch_mc_sqrt(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+int GKB_MC_NAME(launch_mc_sqrt)(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
   if (hm.n == NN && hm.m == MM) return launch_mc_shape_sqrt<NN, MM>(tm, hm, io, device, grid_out, s);
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_MC_SHAPES(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
 }
@@ -206,12 +216,16 @@ int mc_max_grid(int device) {
 int launch_mc_vanilla(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
 int launch_mc_info(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
 int launch_mc_sqrt(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_vanilla_big(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_info_big(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+int launch_mc_sqrt_big(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
 
 int launch_mc(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
+  const bool big = hm.n > 6;
   switch (hm.kind) {
-    case GKB_VANILLA: return launch_mc_vanilla(tm, hm, io, device, grid_out, s);
-    case GKB_INFORMATION: return launch_mc_info(tm, hm, io, device, grid_out, s);
-    case GKB_SQRT: return launch_mc_sqrt(tm, hm, io, device, grid_out, s);
+    case GKB_VANILLA: return big ? launch_mc_vanilla_big(tm, hm, io, device, grid_out, s) : launch_mc_vanilla(tm, hm, io, device, grid_out, s);
+    case GKB_INFORMATION: return big ? launch_mc_info_big(tm, hm, io, device, grid_out, s) : launch_mc_info(tm, hm, io, device, grid_out, s);
+    case GKB_SQRT: return big ? launch_mc_sqrt_big(tm, hm, io, device, grid_out, s) : launch_mc_sqrt(tm, hm, io, device, grid_out, s);
     default: return GKB_ERR_UNSUPPORTED;
   }
 }
@@ -220,7 +234,7 @@ int mc_shape_supported(int kind, int n, int m) {
   if (kind != GKB_VANILLA && kind != GKB_INFORMATION && kind != GKB_SQRT) return 0;
 #define GKB_CASE(NN, MM) \
   if (n == NN && m == MM) return 1;
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)  // n <= 6 (parts 1-3) and n = 7, 8 (parts 4-6)
 #undef GKB_CASE
   return 0;
 }

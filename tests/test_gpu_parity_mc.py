@@ -272,3 +272,26 @@ def test_chisquare_failed_update_is_reported():
     with pytest.raises(gk.GkbError) as ei:
         gk.NewChiSquare(bad, runs, [np.zeros(1)], True, True)
     assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("kind", ["vanilla", "information", "sqrt"])
+@pytest.mark.parametrize("n,m", [(8, 3), (7, 2)])
+def test_mc_chisquare_n7_n8_matches_oracle(oracle, kind, n, m):
+    """The north star's n <= 8: the fused Monte Carlo + chi-square kernels at n = 7 and 8 (kernels_mc.cu parts 4-6),
+    a seeded random model with a control, all three tested filter kinds, against the oracle on the dumped noise."""
+    gk = _gpu()
+    rng = np.random.default_rng(100 * n + m)
+    A = rng.standard_normal((n, n))
+    B = rng.standard_normal((m, m))
+    f = dict(F=np.eye(n) + 0.05 * rng.standard_normal((n, n)), G=rng.standard_normal((n, 1)), H=rng.standard_normal((m, n)),
+             Q=1e-3 * (A @ A.T + n * np.eye(n)), R=1e-1 * (B @ B.T + m * np.eye(m)), x0=rng.standard_normal(n),
+             P0=np.diag(rng.uniform(0.5, 2.0, n)))
+    f["x0_truth"] = f["x0"] + 0.1 * rng.standard_normal(n)
+    steps, trials = 40, 70
+    controls = [np.array([0.2 * np.cos(0.1 * k)]) for k in range(steps)]
+    r = _mc_pair(gk, oracle, f, kind, trials, steps, controls)
+    ref = r["ref"]
+    assert fx.scaled_err(r["tx"], ref["truth_x"].transpose(1, 2, 0)) <= TOL
+    assert fx.scaled_err(r["nees"], ref["NEES"]) <= TOL, fx.scaled_err(r["nees"], ref["NEES"])
+    if kind != "information":
+        assert fx.scaled_err(r["nis"], ref["NIS"]) <= TOL, fx.scaled_err(r["nis"], ref["NIS"])
