@@ -9,5 +9,5 @@ from .api import (  # noqa: F401
     AsSymDense, DenseIdentity, HouseholderTransf, Identity, IsNil, ScaledDenseIdentity, ScaledIdentity, Sign,
     AWGN, BatchGroundTruth, BatchKF, BatchNoise, ErrorEstimate, Estimate, HybridKF, NewBatchGroundTruth, NewBatchKF, Information, MonteCarloRuns, NewAWGN, NewChiSquare, NewHybridKF,
     NewInformation, NewInformationFromState, NewMonteCarloRuns, NewNoiseless, NewPurePredictorVanilla, NewSRIF,
-    NewSquareRoot, NewVanilla, Noiseless, ReplayNoise, SRIF, SquareRoot, VanLoan, Vanilla,
+    NewSquareRoot, NewVanilla, Noiseless, ReplayNoise, SRIF, SquareRoot, VanLoan, VanLoanBatch, Vanilla,
 )

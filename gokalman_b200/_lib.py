@@ -89,6 +89,7 @@ SYMBOLS = [
     ("gkb_nl_run", _i, [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(Outputs)]),
     ("gkb_od_synthesize", _i, [C.POINTER(OdConfig), _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     ("gkb_od_run", _i, [_vp, C.POINTER(OdConfig), _i, _vp, C.POINTER(Outputs)]),
+    ("gkb_van_loan", _i, [_i, _i, _i64, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     ("gkb_get_state", _i, [_vp, _vp, _vp]),
     ("gkb_set_state", _i, [_vp, _vp, _vp]),
     ("gkb_smooth_all", _i, [_i, _i, _i64, _i, _vp, _i, _vp, _vp, _i, _vp]),

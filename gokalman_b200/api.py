@@ -1066,6 +1066,25 @@ def VanLoan(A, Gamma, W, dt):
     return F, Q, err
 
 
+def VanLoanBatch(A, Gamma, W, dt, device=0):
+    """c2d.go:13-75 for a batch of systems on the device (`gkb_van_loan`): A [n, n] (shared) or [n, n, N]; Gamma [n, q]
+    or [n, q, N]; W [q, q]; dt a scalar or [N].  Returns F [n, n, N], Q [n, n, N], status [N].  The Nyquist warning is
+    the single-system host wrapper's (VanLoan above); the batch call never fails on it, like the reference still
+    returns F and Q."""
+    lib = _lib.load()
+    A, Gamma, W = _arr(A), _arr(Gamma), _mat(W)
+    n, q = A.shape[0], W.shape[0]
+    dt = np.ascontiguousarray(np.atleast_1d(np.asarray(dt, dtype=np.float64)))
+    a_shared, g_shared, dt_shared = int(A.ndim == 2), int(Gamma.reshape(n, q, -1).shape[2] == 1), int(dt.size == 1)
+    count = max(1 if a_shared else A.shape[2], 1 if g_shared else Gamma.reshape(n, q, -1).shape[2], dt.size)
+    A = np.ascontiguousarray(A.reshape(n * n) if a_shared else A.reshape(n * n, count))
+    Gamma = np.ascontiguousarray(Gamma.reshape(n * q) if g_shared else Gamma.reshape(n * q, count))
+    F, Q, status = np.zeros((n * n, count)), np.zeros((n * n, count)), np.zeros(count, dtype=np.int32)
+    _lib.check(lib.gkb_van_loan(n, q, count, device, _ptr(A), a_shared, _ptr(Gamma), g_shared, _ptr(W), _ptr(dt), dt_shared,
+                                _lib.HOST, _ptr(F), _ptr(Q), status.ctypes.data))
+    return F.reshape(n, n, count), Q.reshape(n, n, count), status
+
+
 # --------------------------------------------------------------------------------------------------
 # helper.go: exported helpers
 # --------------------------------------------------------------------------------------------------

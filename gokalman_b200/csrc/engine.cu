@@ -1225,6 +1225,43 @@ int gkb_householder_transf(int n, int m, int64_t count, int device, double* A, i
   return 0;
 }
 
+// ---- VanLoan (c2d.go) --------------------------------------------------------------------------------------
+int gkb_van_loan(int n, int q, int64_t count, int device, const double* A, int a_shared, const double* Gamma, int g_shared,
+                 const double* W, const double* dt, int dt_shared, int mem, double* F, double* Q, int32_t* status) {
+  if (!A || !Gamma || !W || !dt || !F || !Q) return fail(GKB_ERR_ARG, "NULL argument");
+  if (n < 1 || n > GKB_MAX_N || q < 1 || q > GKB_MAX_N) return fail(GKB_ERR_UNSUPPORTED, "n=%d q=%d outside 1..%d", n, q, GKB_MAX_N);
+  if (count < 1) return fail(GKB_ERR_ARG, "count must be >= 1");
+  int rc = check_device(device);
+  if (rc) return rc;
+  cudaStream_t s = cudaStreamLegacy;
+  if (mem == GKB_DEVICE) {
+    rc = launch_van_loan(n, q, count, A, a_shared, Gamma, g_shared, W, dt, dt_shared, F, Q, status, s);
+    GKB_CUDA(cudaGetLastError());
+    return rc ? fail(rc, "no Van Loan kernel for n=%d q=%d", n, q) : 0;
+  }
+  const size_t ab = sizeof(double) * n * n * (a_shared ? 1 : (size_t)count), gb = sizeof(double) * n * q * (g_shared ? 1 : (size_t)count);
+  const size_t wb = sizeof(double) * q * q, tb = sizeof(double) * (dt_shared ? 1 : (size_t)count);
+  const size_t ob = sizeof(double) * n * n * (size_t)count, sb = sizeof(int32_t) * (size_t)count;
+  DevBuf dA, dG, dW, dT, dF, dQ, dS;
+  auto cleanup = [&]() { dA.release(); dG.release(); dW.release(); dT.release(); dF.release(); dQ.release(); dS.release(); };
+  if ((rc = dA.ensure(ab)) || (rc = dG.ensure(gb)) || (rc = dW.ensure(wb)) || (rc = dT.ensure(tb)) || (rc = dF.ensure(ob)) ||
+      (rc = dQ.ensure(ob)) || (rc = dS.ensure(sb))) { cleanup(); return rc; }
+  cudaMemcpyAsync(dA.p, A, ab, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dG.p, Gamma, gb, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dW.p, W, wb, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dT.p, dt, tb, cudaMemcpyHostToDevice, s);
+  rc = launch_van_loan(n, q, count, dA.as<double>(), a_shared, dG.as<double>(), g_shared, dW.as<double>(), dT.as<double>(),
+                       dt_shared, dF.as<double>(), dQ.as<double>(), dS.as<int32_t>(), s);
+  cudaMemcpyAsync(F, dF.p, ob, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(Q, dQ.p, ob, cudaMemcpyDeviceToHost, s);
+  if (status) cudaMemcpyAsync(status, dS.p, sb, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cleanup();
+  if (rc) return fail(rc, "no Van Loan kernel for n=%d q=%d", n, q);
+  if (e != cudaSuccess) return fail(GKB_ERR_CUDA, "VanLoan failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---- BatchKF -------------------------------------------------------------------------------------------
 int gkb_batch_solve(int n, int m, int steps, int64_t n_filters, int device, const double* R, const double* H, int h_shared,
                     const double* real_obs, const double* computed_obs, int mem, double* xhat0, double* P0,

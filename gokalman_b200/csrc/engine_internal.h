@@ -177,6 +177,9 @@ int launch_od_run(const HostModel& hm, const OdParams& c, const NlIo& io, double
 // written SoA [steps][component][nf].  LQ [n*n], LR [m*m] are host arrays (lower Cholesky factors).
 int launch_awgn_fill(int n, int m, const double* LQ, const double* LR, unsigned long long seed, long long filter_offset,
                      int64_t nf, int steps, int step0, double* w, double* v, double* w2, cudaStream_t s);
+// Van Loan c2d (c2d.go:13-75) for `count` systems, one thread each (kernels_c2d.cu).  Device pointers.
+int launch_van_loan(int n, int q, int64_t count, const double* A, int a_shared, const double* Gamma, int g_shared,
+                    const double* W, const double* dt, int dt_shared, double* F, double* Q, int32_t* status, cudaStream_t s);
 // Large-state Vanilla (kernels_tile.cu): n in {16, 24, 32}, m <= 8.
 int tile_shape_supported(int n, int m);
 int launch_tile_update(const TileIo& io, int n, int device, cudaStream_t s);

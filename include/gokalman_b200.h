@@ -240,6 +240,15 @@ int gkb_batch_solve(int n, int m, int steps, int64_t n_filters, int device, cons
                     int h_shared, const double* real_obs, const double* computed_obs, int mem, double* xhat0,
                     double* P0, int32_t* status);
 
+/* ---- VanLoan (c2d.go:13-75) for a batch of continuous-time systems: per system M = [[-A dt, Gamma W Gamma^T dt],
+ *      [0, A^T dt]], E = expm(M) (Higham's scaling and squaring, Pade 3/5/7/9/13: the algorithm of mat64.Dense.Exp),
+ *      F = (E_22)^T, Q = AsSymDense(F E_12).  A [n*n][count] (or [n*n] when a_shared), Gamma [n*q][count] (or shared),
+ *      W [q*q] shared, dt [count] (or one value when dt_shared); outputs F, Q [n*n][count]; status [count] optional.
+ *      `mem` says where all arrays live.  n, q <= 8.  The Nyquist warning of c2d.go:15-28 (eigenvalues of A) is the
+ *      host wrapper's job: this call never fails on it, like the reference still returns F and Q. */
+int gkb_van_loan(int n, int q, int64_t count, int device, const double* A, int a_shared, const double* Gamma, int g_shared,
+                 const double* W, const double* dt, int dt_shared, int mem, double* F, double* Q, int32_t* status);
+
 /* Raw filter state: x-like vector [n][N] and matrix [n*n][N] (vanilla/hybrid: x, P; information:
  * i, I; sqrt: x, S; SRIF: b, R).  Host pointers. */
 int gkb_get_state(const gkb_filter* f, double* vec, double* mat);

@@ -179,6 +179,10 @@ int gko_od_synth(double mu, double j2, double re, double dt, int64_t nf, int ste
                  const double* station, const double* truth_obs, double sigma_range, double sigma_rate, uint64_t seed,
                  int64_t filter_offset, double* Phi, double* Ht, double* real_obs, double* comp_obs, double* orbit_out);
 
+/* gko_c2d.c: c2d.go:13-75 VanLoan (without the Nyquist warning) and the Higham-2005 matrix exponential it rests on. */
+int gko_expm(double* E, const double* A, int d);
+int gko_van_loan(int n, int q, const double* A, const double* Gamma, const double* W, double dt, double* F, double* Q);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,7 +81,7 @@ class McConfig(C.Structure):
 
 def build(force=False):
     """Compile oracle/_build/libgko.so with the committed Makefile (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("gko.c", "gko_linalg.c", "gko_od.c", "gko.h", "gko_linalg.h", "Makefile",
+    srcs = [os.path.join(_HERE, f) for f in ("gko.c", "gko_linalg.c", "gko_od.c", "gko_c2d.c", "gko.h", "gko_linalg.h", "Makefile",
                                                os.path.join("..", "include", "gokalman_b200_icdf.inc"))]
     if (not force and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
@@ -480,3 +480,29 @@ def od_synth(mu, j2, re, dt, orbit0, station, truth_obs, sigma_range, sigma_rate
     if rc != 0:
         raise OracleError(rc)
     return Phi, Ht, real, comp, orb
+
+
+def van_loan(A, Gamma, W, dt):
+    """gko_c2d.c: c2d.go:13-75 (F, Q) of one system."""
+    A, Gamma, W = np.atleast_2d(_a(A)), np.atleast_2d(_a(Gamma)), np.atleast_2d(_a(W))
+    n, q = A.shape[0], W.shape[0]
+    Gamma = np.ascontiguousarray(Gamma.reshape(n, q))
+    F, Q = np.zeros((n, n)), np.zeros((n, n))
+    L = lib()
+    L.gko_van_loan.restype = C.c_int
+    L.gko_van_loan.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    rc = L.gko_van_loan(n, q, _p(A), _p(Gamma), _p(W), float(dt), _p(F), _p(Q))
+    if rc != 0:
+        raise OracleError(rc)
+    return F, Q
+
+
+def expm(A):
+    A = np.atleast_2d(_a(A))
+    E = np.zeros_like(A)
+    L = lib()
+    L.gko_expm.restype = C.c_int
+    L.gko_expm.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    if L.gko_expm(_p(E), _p(A), A.shape[0]) != 0:
+        raise OracleError(-1)
+    return E
