@@ -220,3 +220,81 @@ func HouseholderTransf(A *mat64.Dense, n, m int) error {
 // FilterMajor reports the array layout of a handle: large-state Vanilla handles (n = 16, 24, ... 64) take and
 // return filter-major arrays [N][C] instead of [C][N] (see gkb_filter_major in the header).
 func (kf *Vanilla) FilterMajor() bool { return C.gkb_filter_major(kf.h) != 0 }
+
+// ---- round 2 entry points (same caveat: source only, never compiled here) --------------------------------
+
+// TestedModel is the tested filter's OWN model for ChiSquareWith (chisquare.go:16 takes any LDKF: its F / G / H and
+// its Noise's Q / R); nil slices mean "the truth generator's matrix".
+type TestedModel struct{ F, G, H, Q, R []float64 }
+
+// ChiSquareWith is ChiSquare with a tested filter that carries its own model, on one or several GPUs of this
+// process.  devices == nil: one GPU (cfg.device); otherwise the trials are sharded over `devices` and the per-step
+// sums are reduced inside the C-ABI (peer = the rank-ordered NVLink peer-memory sum, else one ncclAllReduce).
+func ChiSquareWith(cfg *C.gkb_mc_config, tested *TestedModel, devices []int32, peer bool, steps int) (nis, nees []float64, err error) {
+	if tested != nil {
+		cfg.filter_F, cfg.filter_G, cfg.filter_H, cfg.filter_Q, cfg.filter_R = ptr(tested.F), ptr(tested.G), ptr(tested.H), ptr(tested.Q), ptr(tested.R)
+	}
+	nis, nees = make([]float64, steps), make([]float64, steps)
+	var first C.int32_t
+	out := C.gkb_mc_outputs{mem: C.GKB_HOST, nis: ptr(nis), nees: ptr(nees), first_error: &first}
+	var rc C.int
+	if devices == nil {
+		rc = C.gkb_mc_chisquare(cfg, &out)
+	} else {
+		mode := C.int(C.GKB_REDUCE_NCCL)
+		if peer {
+			mode = C.GKB_REDUCE_PEER
+		}
+		rc = C.gkb_mc_chisquare_multi(cfg, (*C.int)(unsafe.Pointer(&devices[0])), C.int(len(devices)), mode, &out)
+	}
+	if rc != 0 {
+		return nil, nil, lastErr(rc)
+	}
+	if first != 0 {
+		panic("a trial's Update failed") // chisquare.go:40-42 panics
+	}
+	return nis, nees, nil
+}
+
+// SetAWGN arms the handle with AWGN noise (noise.go:109-159) drawn on the device: Process(k) / Measurement(k) of
+// filter f at step k are Philox(seed, filterOffset + f, k) normals coloured with chol(Q), chol(R).
+func (kf *Vanilla) SetAWGN(Q, R mat64.Symmetric, seed uint64, filterOffset int64) error {
+	mr, _ := R.Dims()
+	if rc := C.gkb_set_noise(kf.h, ptr(raw(Q)), C.int(mr), ptr(raw(R))); rc != 0 {
+		return lastErr(rc)
+	}
+	return lastErr(C.gkb_set_philox_noise(kf.h, C.uint64_t(seed), C.int64_t(filterOffset)))
+}
+
+// VanLoanBatch is c2d.go:13-75 for `count` systems (A [n*n][count] or shared, dt [count] or one value).
+func VanLoanBatch(n, q int, count int64, device int, A []float64, aShared bool, Gamma []float64, gShared bool, W, dt []float64,
+	dtShared bool) (F, Q []float64, err error) {
+	F, Q = make([]float64, int64(n*n)*count), make([]float64, int64(n*n)*count)
+	b := func(v bool) C.int {
+		if v {
+			return 1
+		}
+		return 0
+	}
+	rc := C.gkb_van_loan(C.int(n), C.int(q), C.int64_t(count), C.int(device), ptr(A), b(aShared), ptr(Gamma), b(gShared), ptr(W),
+		ptr(dt), b(dtShared), C.GKB_HOST, ptr(F), ptr(Q), nil)
+	return F, Q, lastErr(rc)
+}
+
+// HybridHandle is the NLDKF handle of NewHybridKF (gkb_create_hybrid); only what round 2 added is sketched here.
+type HybridHandle struct{ h *C.gkb_filter }
+
+// SetStrict selects the reference-order arithmetic (bit-identical to the CPU restatement of hybrid.go:104-204).
+func (kf *HybridHandle) SetStrict(on bool) error {
+	v := C.int(0)
+	if on {
+		v = 1
+	}
+	return lastErr(C.gkb_set_strict(kf.h, v))
+}
+
+// RunOD is the fused OD run: the step the reference's callers do with the smd propagator before every
+// Prepare(Phi, Htilde) + Update(real, computed) (hybrid_test.go:159-294) happens on the device, per filter.
+func (kf *HybridHandle) RunOD(cfg *C.gkb_od_config, steps int, flags []uint8, out *C.gkb_outputs) error {
+	return lastErr(C.gkb_od_run(kf.h, cfg, C.int(steps), (*C.uint8_t)(unsafe.Pointer(&flags[0])), out))
+}

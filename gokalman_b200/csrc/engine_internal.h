@@ -8,12 +8,16 @@
 namespace gkb {
 
 // (n, m) shapes with compiled one-filter-per-thread kernels.
-#define GKB_FOR_EACH_SHAPE(X) \
-  X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 3) X(5, 1) X(5, 2) X(6, 1) X(6, 2) X(6, 3)
+// (in four groups, so that the heaviest templates -- the fused Monte Carlo kernels -- compile as parallel parts)
+#define GKB_FOR_EACH_SHAPE_G0(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 3)
+#define GKB_FOR_EACH_SHAPE_G1(X) X(5, 1) X(5, 2) X(6, 1) X(6, 2) X(6, 3)
+#define GKB_FOR_EACH_SHAPE_G2(X) X(7, 1) X(7, 2) X(7, 3)
+#define GKB_FOR_EACH_SHAPE_G3(X) X(8, 1) X(8, 2) X(8, 3)
+#define GKB_FOR_EACH_SHAPE(X) GKB_FOR_EACH_SHAPE_G0(X) GKB_FOR_EACH_SHAPE_G1(X)
 
 // LDKF kinds (Vanilla / pure predictor / Information / Square root) also get n = 7 and 8 (the north star's "n <= 8"): slower
 // (the 8 x 8 intermediates no longer fit the registers: ptxas reports local memory) but correct, same parity bar.
-#define GKB_FOR_EACH_BIG_SHAPE(X) X(7, 1) X(7, 2) X(7, 3) X(8, 1) X(8, 2) X(8, 3)
+#define GKB_FOR_EACH_BIG_SHAPE(X) GKB_FOR_EACH_SHAPE_G2(X) GKB_FOR_EACH_SHAPE_G3(X)
 #define GKB_FOR_EACH_LTI_SHAPE(X) GKB_FOR_EACH_SHAPE(X) GKB_FOR_EACH_BIG_SHAPE(X)
 
 constexpr int kThreads = 128;  // threads per CTA for the register kernels
@@ -142,6 +146,7 @@ int launch_model_setup(HostModel& hm, int ops, double* x0, double* A0, cudaStrea
 // gu[k][i] = sum_j G[i][j] u[k][j]: the control term, identical for every filter of a batch.
 int launch_gu(const double* G_host, int n, int c, const double* u_dev, int steps, double* gu_dev, cudaStream_t s);
 int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s);
+int launch_lti_update_big(const HostModel& hm, const LtiIo& io, cudaStream_t s);  // kernels_lti.cu part 1: n = 7, 8
 int launch_nl_run(const HostModel& hm, const NlIo& io, cudaStream_t s);
 int launch_nl_run_big(const HostModel& hm, const NlIo& io, cudaStream_t s);  // kernels_nl_big.cu: n = 7, 8
 // kernels_nl_tma.cu: the TMA production path of the NLDKF kinds.  0 = launched, 1 = not applicable to this call.

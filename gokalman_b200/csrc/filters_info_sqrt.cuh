@@ -138,16 +138,20 @@ GKB_DEV int info_step(const InfoModel<N, M>& md, double (&iv)[N], double (&I)[N 
         HTR[i * M + a] = s;
       }
   }
-  // 205-212
+  // 205-212 (nothing is committed before the non-finite check: a failed Update leaves the previous estimate in place)
   bool finite = true;
+  double ivn[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     double s = HTR[i * M] * y[0];
 #pragma unroll
     for (int a = 1; a < M; ++a) s = fma(HTR[i * M + a], y[a], s);
-    iv[i] = s + im[i];
-    finite = finite && isfinite(iv[i]);
+    ivn[i] = s + im[i];
+    finite = finite && isfinite(ivn[i]);
   }
+  if (!finite) return GKB_ERR_NONFINITE;
+#pragma unroll
+  for (int i = 0; i < N; ++i) iv[i] = ivn[i];
 #pragma unroll
   for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -158,7 +162,7 @@ GKB_DEV int info_step(const InfoModel<N, M>& md, double (&iv)[N], double (&I)[N 
       I[sym_idx<N>(i, j)] = o.Ipred[sym_idx<N>(i, j)] + s;
     }
   (void)SN;
-  return finite ? 0 : GKB_ERR_NONFINITE;
+  return 0;
 }
 
 template <int N, int M>

@@ -389,15 +389,17 @@ GKB_DEV int srif_step(const NlModel<N, M>& md, double (&b)[N], double (&R)[N * N
     A[(N + a) * COLS + N] = yw[a];
   }
   householder_transf<N, M>(A);
-  bool finite = true;
+  bool finite = true;  // checked before R / b are committed: a failed Update leaves the previous estimate in place
+#pragma unroll
+  for (int i = 0; i < N; ++i) finite = finite && isfinite(A[i * COLS + N]);
+  if (!finite) return GKB_ERR_NONFINITE;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
 #pragma unroll
     for (int j = 0; j < N; ++j) R[i * N + j] = A[i * COLS + j];
     b[i] = A[i * COLS + N];
-    finite = finite && isfinite(b[i]);
   }
-  return finite ? 0 : GKB_ERR_NONFINITE;
+  return 0;
 }
 
 // ---- the SRIF epoch for the usual case, as straight-line code ----------------------------------------------

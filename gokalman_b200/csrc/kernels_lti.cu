@@ -28,6 +28,28 @@ GKB_DEV void write_out(double* base, int k, int every_step, const double (&src)[
   store_soa<C>(dst, src, nf, tid);
 }
 
+// A failed Update returns (nil, err) in the reference: the rows of that (filter, step) in the caller's output arrays
+// are filled with NaN (never left holding data of an earlier call), the filter keeps its previous estimate and the
+// first error goes to the status array.
+template <int C>
+GKB_DEV void write_nan(double* base, int k, int every_step, int64_t nf, int64_t tid) {
+  if (base == nullptr) return;
+  double* dst = base + (every_step ? (int64_t)k * C * nf : 0);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+  for (int i = 0; i < C; ++i) dst[(int64_t)i * nf + tid] = qnan;
+}
+template <int N, int M, int INNOV>
+GKB_DEV void fail_outputs(const LtiIo& io, int k, int64_t tid) {
+  if (!(io.every_step || k == io.steps - 1)) return;
+  write_nan<N>(io.o_state, k, io.every_step, io.nf, tid);
+  write_nan<M>(io.o_meas, k, io.every_step, io.nf, tid);
+  write_nan<INNOV>(io.o_innov, k, io.every_step, io.nf, tid);
+  write_nan<N * M>(io.o_gain, k, io.every_step, io.nf, tid);
+  write_nan<N * N>(io.o_covar, k, io.every_step, io.nf, tid);
+  write_nan<N * N>(io.o_pred, k, io.every_step, io.nf, tid);
+}
+
 template <int N, int M>
 GKB_DEV void load_inputs(const LtiIo& io, int k, int64_t tid, double (&y)[M], double (&w)[N], double (&v)[M],
                          int& err) {
@@ -85,6 +107,7 @@ vanilla_update_kernel(const __grid_constant__ VanillaModel<N, M> md, const __gri
     }
     if (err != 0) {
       if (status == 0) status = err;
+      fail_outputs<N, M, M>(io, k, tid);
       continue;  // like the reference, a failed Update leaves the previous estimate in place
     }
     if (io.every_step || k == io.steps - 1) {
@@ -144,6 +167,7 @@ info_update_kernel(const __grid_constant__ InfoModel<N, M> md, const __grid_cons
     if (err == 0) err = info_step<N, M>(md, iv, I, y, gu, v, o);
     if (err != 0) {
       if (status == 0) status = err;
+      fail_outputs<N, M, N>(io, k, tid);
       continue;
     }
     if (io.every_step || k == io.steps - 1) {
@@ -202,6 +226,7 @@ sqrt_update_kernel(const __grid_constant__ SqrtModel<N, M> md, const __grid_cons
     if (err == 0) err = sqrt_step<N, M>(md, x, S, y, gu, w, v, o);
     if (err != 0) {
       if (status == 0) status = err;
+      fail_outputs<N, M, M>(io, k, tid);
       continue;
     }
     if (io.every_step || k == io.steps - 1) {
@@ -227,6 +252,7 @@ sqrt_update_kernel(const __grid_constant__ SqrtModel<N, M> md, const __grid_cons
 }
 
 // ---- control term: gu[k][i] = sum_j G[i][j] u[k][j], once per step for the whole batch ----------------
+#if GKB_LTI_PART == 0
 struct GuParams { double G[GKB_MAX_N * GKB_MAX_C]; };
 __global__ void gu_kernel_p(const __grid_constant__ GuParams p, int n, int c, const double* __restrict__ u, int steps,
                             double* __restrict__ gu) {
@@ -246,6 +272,7 @@ int launch_gu(const double* G_host, int n, int c, const double* u_dev, int steps
   gu_kernel_p<<<(total + 127) / 128, 128, 0, s>>>(p, n, c, u_dev, steps, gu_dev);
   return 0;
 }
+#endif
 
 // ---- model marshalling + dispatch -------------------------------------------------------------------
 template <int N, int M>
@@ -299,12 +326,25 @@ static int launch_shape(const HostModel& hm, const LtiIo& io, cudaStream_t s) {
   }
 }
 
+#ifndef GKB_LTI_PART
+#error "compile with -DGKB_LTI_PART=0 (n <= 6 + the control-term kernels) or 1 (n = 7, 8): see Makefile"
+#endif
+#if GKB_LTI_PART == 0
 int launch_lti_update(const HostModel& hm, const LtiIo& io, cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
   if (hm.n == NN && hm.m == MM) return launch_shape<NN, MM>(hm, io, s);
-  GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)
+  GKB_FOR_EACH_SHAPE(GKB_CASE)
+#undef GKB_CASE
+  return launch_lti_update_big(hm, io, s);
+}
+#else
+int launch_lti_update_big(const HostModel& hm, const LtiIo& io, cudaStream_t s) {
+#define GKB_CASE(NN, MM) \
+  if (hm.n == NN && hm.m == MM) return launch_shape<NN, MM>(hm, io, s);
+  GKB_FOR_EACH_BIG_SHAPE(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
 }
+#endif
 
 }  // namespace gkb

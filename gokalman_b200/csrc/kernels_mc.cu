@@ -5,17 +5,28 @@
 namespace gkb {
 
 #ifndef GKB_MC_PART
-#error "compile with -DGKB_MC_PART=0..6 (see Makefile): 0 = dispatch + finish kernel, 1/2/3 = vanilla / information / sqrt kernels for n <= 6, 4/5/6 = the same for n = 7, 8"
+#error "compile with -DGKB_MC_PART=0..12 (see Makefile): 0 = dispatch + finish kernel; 1 + 3 g + (kind - 1) = the kernels of tested kind 1 / 2 / 3 (vanilla / information / sqrt) for shape group g = 0 (n <= 4), 1 (n = 5, 6), 2 (n = 7), 3 (n = 8)"
 #endif
-// parts 4-6 instantiate the n = 7, 8 shapes (the north star's "n <= 8"; spilled, slower, same parity bar) under *_big names
-#if GKB_MC_PART >= 4
-#define GKB_MC_SHAPES(X) GKB_FOR_EACH_BIG_SHAPE(X)
-#define GKB_MC_NAME(base) base##_big
-#define GKB_MC_KIND (GKB_MC_PART - 3)
+// The fused kernels are the heaviest templates of the library (the n = 8 information filter alone takes minutes):
+// twelve parts build in parallel.  Groups 2 and 3 are the north star's "n <= 8": spilled, slower, same parity bar.
+#if GKB_MC_PART > 0
+#define GKB_MC_KIND ((GKB_MC_PART - 1) % 3 + 1)
+#define GKB_MC_GROUP ((GKB_MC_PART - 1) / 3)
+#if GKB_MC_GROUP == 0
+#define GKB_MC_SHAPES(X) GKB_FOR_EACH_SHAPE_G0(X)
+#define GKB_MC_NAME(base) base##_g0
+#elif GKB_MC_GROUP == 1
+#define GKB_MC_SHAPES(X) GKB_FOR_EACH_SHAPE_G1(X)
+#define GKB_MC_NAME(base) base##_g1
+#elif GKB_MC_GROUP == 2
+#define GKB_MC_SHAPES(X) GKB_FOR_EACH_SHAPE_G2(X)
+#define GKB_MC_NAME(base) base##_g2
 #else
-#define GKB_MC_SHAPES(X) GKB_FOR_EACH_SHAPE(X)
-#define GKB_MC_NAME(base) base
-#define GKB_MC_KIND GKB_MC_PART
+#define GKB_MC_SHAPES(X) GKB_FOR_EACH_SHAPE_G3(X)
+#define GKB_MC_NAME(base) base##_g3
+#endif
+#else
+#define GKB_MC_KIND 0
 #endif
 #if GKB_MC_PART == 0
 // out[col][k] = scale * sum_b partial[b][k][col].  A CTA is 32 result slots x 8 row groups: thread (x, y) adds the CTA
@@ -213,21 +224,25 @@ int mc_max_grid(int device) {
   return sms * kMcMaxCtasPerSm;
 }
 
-int launch_mc_vanilla(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
-int launch_mc_info(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
-int launch_mc_sqrt(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
-int launch_mc_vanilla_big(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
-int launch_mc_info_big(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
-int launch_mc_sqrt_big(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+#define GKB_MC_DECL(g) \
+  int launch_mc_vanilla_g##g(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s); \
+  int launch_mc_info_g##g(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);    \
+  int launch_mc_sqrt_g##g(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s);
+GKB_MC_DECL(0) GKB_MC_DECL(1) GKB_MC_DECL(2) GKB_MC_DECL(3)
+#undef GKB_MC_DECL
 
 int launch_mc(const HostModel& tm, const HostModel& hm, const McIo& io, int device, int* grid_out, cudaStream_t s) {
-  const bool big = hm.n > 6;
+  const int g = hm.n <= 4 ? 0 : hm.n <= 6 ? 1 : hm.n == 7 ? 2 : 3;
+#define GKB_MC_CALL(fn) \
+  (g == 0 ? fn##_g0(tm, hm, io, device, grid_out, s) : g == 1 ? fn##_g1(tm, hm, io, device, grid_out, s) : \
+   g == 2 ? fn##_g2(tm, hm, io, device, grid_out, s) : fn##_g3(tm, hm, io, device, grid_out, s))
   switch (hm.kind) {
-    case GKB_VANILLA: return big ? launch_mc_vanilla_big(tm, hm, io, device, grid_out, s) : launch_mc_vanilla(tm, hm, io, device, grid_out, s);
-    case GKB_INFORMATION: return big ? launch_mc_info_big(tm, hm, io, device, grid_out, s) : launch_mc_info(tm, hm, io, device, grid_out, s);
-    case GKB_SQRT: return big ? launch_mc_sqrt_big(tm, hm, io, device, grid_out, s) : launch_mc_sqrt(tm, hm, io, device, grid_out, s);
+    case GKB_VANILLA: return GKB_MC_CALL(launch_mc_vanilla);
+    case GKB_INFORMATION: return GKB_MC_CALL(launch_mc_info);
+    case GKB_SQRT: return GKB_MC_CALL(launch_mc_sqrt);
     default: return GKB_ERR_UNSUPPORTED;
   }
+#undef GKB_MC_CALL
 }
 
 int mc_shape_supported(int kind, int n, int m) {

@@ -28,6 +28,20 @@ GKB_DEV void nl_out(double* base, int k, int every_step, const double (&src)[C],
   for (int i = 0; i < C; ++i) __stcs(dst + (int64_t)i * nf, src[i]);
 }
 
+// A failed epoch (the reference returns (nil, err)): NaN rows in the caller's output arrays, never stale data.
+template <int N, int M, int INNOV>
+GKB_DEV void nl_fail_outputs(const NlIo& io, int k, int64_t tid) {
+  if (!(io.every_step || k == io.steps - 1)) return;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  auto fill = [&](double* base, int comps) {
+    if (base == nullptr) return;
+    double* dst = base + (io.every_step ? (int64_t)k * comps * io.nf : 0) + tid;
+    for (int i = 0; i < comps; ++i) dst[(int64_t)i * io.nf] = qnan;
+  };
+  fill(io.o_state, N); fill(io.o_meas, M); fill(io.o_innov, INNOV); fill(io.o_obsdev, M); fill(io.o_gain, N * M);
+  fill(io.o_covar, N * N); fill(io.o_pred, N * N);
+}
+
 template <int N, int M>
 __global__ void __launch_bounds__(kThreads)
 hybrid_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant__ NlIo io) {
@@ -62,6 +76,7 @@ hybrid_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constan
     int err = hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, Gk, has_meas, ekf, snc, o);
     if (err != 0) {
       if (status == 0) status = err;
+      nl_fail_outputs<N, M, M>(io, k, tid);
       continue;
     }
     if (io.every_step || k == io.steps - 1) {
@@ -128,6 +143,7 @@ hybrid_run_strict_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_
     int err = strict::hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, Gk, has_meas, ekf, snc, Ppred, K, innov, obsdev);
     if (err != 0) {
       if (status == 0) status = err;
+      nl_fail_outputs<N, M, M>(io, k, tid);
       continue;
     }
     if (io.every_step || k == io.steps - 1) {
@@ -177,6 +193,7 @@ srif_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant_
     int err = srif_step<N, M>(md, b, R, Phi, Ht, ro, co, has_meas, o);
     if (err != 0) {
       if (status == 0) status = err;
+      nl_fail_outputs<N, M, N>(io, k, tid);
       continue;
     }
     if (io.every_step || k == io.steps - 1) {

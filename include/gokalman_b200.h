@@ -154,7 +154,12 @@ typedef struct gkb_outputs {
   double* obs_dev;    /* ObservationDev() (hybrid, SRIF) [m]                                   */
   int32_t* status;    /* [n_filters]: 0 or the first gkb_status the filter hit                  */
 } gkb_outputs;
-/* innov has n components for GKB_INFORMATION (returns i+, information.go:272-274) and GKB_SRIF
+/* A filter whose Update / Predict fails at some step (the reference returns (nil, err): singular S, singular Phi,
+ * a non-finite estimate) keeps its PREVIOUS estimate, records the first error in status[filter], and the rows of
+ * the failed (filter, step) in every requested output array are filled with NaN -- never left holding data of an
+ * earlier call.  (Large-state handles: the failing filter stops at that step and is restored to its state at the
+ * start of the call; its output rows from the failing step on are not written.)
+ * innov has n components for GKB_INFORMATION (returns i+, information.go:272-274) and GKB_SRIF
  * (returns b, srif.go:238-240). */
 
 /* ---- LDKF.Update(measurement, control), `steps` times (vanilla.go:128-220,

@@ -16,9 +16,13 @@
  * PARITY PINNING: vanilla/information/sqrt are pinned by the reference's golden CSVs
  * (examples/jerkcar/{vanilla,information,sqrt}.csv, 6 decimals); HouseholderTransf and the SRIF
  * measurement update by the reference's known-answer tests (helper_test.go:108-117,
- * srif_test.go:15-56).  HybridKF, Monte Carlo and chi-square numerics have NO runnable reference
- * pin (their reference tests need the absent `smd` package / are time-seeded): for those this
- * oracle is "parity unpinned" and is cross-checked algebraically instead (tests/test_oracle_*.py).
+ * srif_test.go:15-56), VanLoan by c2d_test.go:9-33.  HybridKF, SmoothAll, BatchKF, Monte Carlo and chi-square
+ * numerics have NO runnable reference pin (their reference tests need the absent `smd` package / are time-seeded):
+ * for those this oracle is "parity unpinned" by reference vectors and is pinned INDEPENDENTLY instead
+ * (tests/test_oracle_crosscheck.py): hybrid CKF == the golden-pinned vanilla on an LTI model, the SmoothAll identity,
+ * BatchKF against numpy's normal equations, and the Monte Carlo + chi-square means against the exact moments of an
+ * analytic linear-Gaussian recursion (tests/chi2_moments.py).  The OD-input synthesis (gko_od.c) restates the engine's
+ * own documented algorithm (the reference's callers use the external `smd` propagator): parity unpinned.
  * The reference itself (Go + gonum) cannot be built here: no Go toolchain, no gonum sources.
  */
 #ifndef GKO_H

@@ -47,10 +47,10 @@ def test_shape_table_and_version():
         assert lib.gkb_shape_supported(0, n, 8) == 1 and lib.gkb_shape_supported(0, n, 1) == 1
         assert lib.gkb_shape_supported(2, n, 8) == 0 and lib.gkb_shape_supported(0, n, 9) == 0
     assert lib.gkb_shape_supported(0, 44, 8) == 0 and lib.gkb_shape_supported(0, 72, 8) == 0 and lib.gkb_shape_supported(0, 128, 8) == 0
-    for kind in range(4):  # the LDKF kinds reach the north star's n <= 8; the NLDKF kinds stop at n = 6
+    for kind in range(6):  # every kind reaches the north star's n <= 8
         assert lib.gkb_shape_supported(kind, 8, 3) == 1 and lib.gkb_shape_supported(kind, 7, 1) == 1
         assert lib.gkb_shape_supported(kind, 9, 1) == 0
-    assert lib.gkb_shape_supported(4, 8, 2) == 0 and lib.gkb_shape_supported(5, 7, 2) == 0
+    assert lib.gkb_shape_supported(4, 8, 2) == 1 and lib.gkb_shape_supported(5, 7, 2) == 1 and lib.gkb_shape_supported(4, 9, 2) == 0
 
 
 def _has_gpu():

@@ -439,3 +439,35 @@ def test_host_stream_pipeline_is_bit_identical(kind, monkeypatch):
             x, P, (vec, mat) = run(every)
             assert np.array_equal(x, ref[every][0]) and np.array_equal(P, ref[every][1]), (chunk, every)
             assert np.array_equal(vec, ref[every][2][0]) and np.array_equal(mat, ref[every][2][1])
+
+
+def test_failed_epoch_writes_nan_rows_and_keeps_previous_estimate(oracle):
+    """A filter whose epoch fails (here: a singular Phi for one filter at one epoch of an SRIF run, srif.go:112-114
+    returns an error) keeps its previous estimate, reports the error in status, and its output rows of that epoch
+    are NaN -- not stale data from an earlier call; the other filters and the later epochs are unaffected."""
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS, F_EKF, F_SNC
+    rng = np.random.default_rng(5)
+    n, m, nf, steps = 6, 2, 9, 12
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    Phi[5, :, :, 2] = 0.0
+    P0, R = np.diag([50, 50, 50, 1, 1, 1.0]), np.diag([1e-2, 1e-2])
+    flags = np.full(steps, F_MEAS, dtype=np.uint8)
+    kf, _ = gk.NewSRIF(np.zeros(n), P0, m, False, gk.NewNoiseless(np.zeros((n, n)), R), n_filters=nf)
+    kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=True)      # an earlier call fills the staging buffers
+    kf.Reset()
+    est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=True)
+    assert est.status[2] == -5 and np.all(np.delete(est.status, 2) == 0)
+    xs, Ps = est.State(), est.Covariance()
+    assert np.all(np.isnan(xs[5, :, 2])) and np.all(np.isnan(Ps[5, :, :, 2]))
+    assert np.all(np.isfinite(np.delete(xs, 2, axis=2))) and np.all(np.isfinite(xs[[0, 4, 6, 11], :, 2]))
+    # the oracle's filter also keeps its previous estimate through the failed call and carries on
+    o = oracle.NewSRIF(np.zeros(n), P0, m, False, R)
+    for k in range(steps):
+        o.Prepare(Phi[k, :, :, 2], Ht[k, :, :, 2])
+        try:
+            e = o.UpdateNL(real[k, :, 2], comp[k, :, 2])
+        except Exception:
+            assert k == 5
+            continue
+        assert fx.scaled_err(xs[k, :, 2], e.State()) <= TOL, k
