@@ -195,16 +195,19 @@ GKB_DEV int hybrid_step(const NlModel<N, M>& md, double (&x)[N], double (&P)[N *
 // triangular shortcut of inverse_lu (dtrti2 + the ||A|| ||inv(A)|| <= 1e16 test), on 21 instead of 36 registers
 // at n = 6.  Returns 0 ok, 1 singular (a zero on the diagonal), 2 ill-conditioned.
 // STRAIGHT: no early return on a zero diagonal (the arithmetic then runs on inf / NaN and only the return code counts).
-template <int N, bool STRAIGHT = false>
+// NOCOND: the cond <= 1e16 test is dropped (same inverse, bit for bit; see inverse_lu_nopivot).
+template <int N, bool STRAIGHT = false, bool NOCOND = false>
 GKB_DEV int inverse_upper_packed(double (&u)[N * (N + 1) / 2]) {
   double anorm = 0.0;
   bool singular = false;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    double s = 0.0;
+    if constexpr (!NOCOND) {
+      double s = 0.0;
 #pragma unroll
-    for (int j = i; j < N; ++j) s += fabs(u[sym_idx<N>(i, j)]);
-    anorm = fmax(anorm, s);
+      for (int j = i; j < N; ++j) s += fabs(u[sym_idx<N>(i, j)]);
+      anorm = fmax(anorm, s);
+    }
     singular = singular || (u[sym_idx<N>(i, i)] == 0.0);
   }
   if constexpr (!STRAIGHT) {
@@ -224,16 +227,20 @@ GKB_DEV int inverse_upper_packed(double (&u)[N * (N + 1) / 2]) {
 #pragma unroll
     for (int i = 0; i < j; ++i) u[sym_idx<N>(i, j)] *= ajj;
   }
-  double inorm = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double s = 0.0;
-#pragma unroll
-    for (int j = i; j < N; ++j) s += fabs(u[sym_idx<N>(i, j)]);
-    inorm = fmax(inorm, s);
-  }
   if (STRAIGHT && singular) return 1;
-  return (anorm * inorm <= 1e16) ? 0 : 2;
+  if constexpr (NOCOND) {
+    return 0;
+  } else {
+    double inorm = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = i; j < N; ++j) s += fabs(u[sym_idx<N>(i, j)]);
+      inorm = fmax(inorm, s);
+    }
+    return (anorm * inorm <= 1e16) ? 0 : 2;
+  }
 }
 
 // srif.go:223-235 State() = inv(R) b.  Returns false where the reference panics (singular R).
@@ -417,8 +424,6 @@ GKB_DEV bool srif_step_tri(const NlModel<N, M>& md, double (&b)[N], double (&U)[
                            bool pad_lane) {
   constexpr int SN = N * (N + 1) / 2, ROWS_PHI = N * N, ROWS_H = M * N;
   bool ok = true;
-  // 117-118, 223-235: x-bar = Phi inv(R) b
-  double xbar[N];
   double a[N * N];
 #pragma unroll
   for (int i = 0; i < N * N; ++i) a[i] = col[i * STRIDE];
@@ -426,23 +431,16 @@ GKB_DEV bool srif_step_tri(const NlModel<N, M>& md, double (&b)[N], double (&U)[
 #pragma unroll
     for (int i = 0; i < N; ++i) a[i * N + i] = 1.0;
   }
-  {
-    double Ui[SN], xs[N];
+  // 117-119: the reference forms x-bar = Phi (inv(R) b) and then b-bar = R-bar x-bar = (R inv(Phi)) (Phi inv(R) b), which is
+  // b itself up to rounding (cond(R) eps).  The production epoch takes b-bar = b -- 143 of the epoch's ~1010 FP64
+  // instructions (the triangular inverse of R, two matrix-vector products with Phi and R-bar) for a result that is
+  // closer to the exact one; the literal sequence stays in srif_step (general kernel, GKB_NL_PATH=plain), and the
+  // difference is measured over all filters of the full-size run (tests/test_gpu_fullsize.py: <= 1e-10).  State() must
+  // still exist (srif.go:228-230 panics on a singular R): an exactly zero diagonal entry sends the warp to srif_step.
 #pragma unroll
-    for (int i = 0; i < SN; ++i) Ui[i] = U[i];
-    const int rc = inverse_upper_packed<N, true>(Ui);  // (no `ok && f()`: short-circuit evaluation would be a branch)
-    ok = ok && (rc == 0);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double s = Ui[sym_idx<N>(i, i)] * b[i];
-#pragma unroll
-      for (int j = i + 1; j < N; ++j) s = fma(Ui[sym_idx<N>(i, j)], b[j], s);
-      xs[i] = s;
-    }
-    mulvec<N, N>(xbar, a, xs);
-  }
+  for (int i = 0; i < N; ++i) ok = ok && (U[sym_idx<N>(i, i)] != 0.0);
   // 110-115: inv(Phi) as inverse_lu computes it when no interchange is needed
-  const bool inv_ok = inverse_lu_nopivot<N>(a);
+  const bool inv_ok = inverse_lu_nopivot<N, true>(a);
   ok = ok && inv_ok;
   // R-bar = R inv(Phi) (R triangular), b-bar = R-bar x-bar, straight into the Householder work matrix
   constexpr int COLS = N + 1;
@@ -457,12 +455,7 @@ GKB_DEV bool srif_step_tri(const NlModel<N, M>& md, double (&b)[N], double (&U)[
       A[i * COLS + j] = s;
     }
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double s = A[i * COLS] * xbar[0];
-#pragma unroll
-    for (int j = 1; j < N; ++j) s = fma(A[i * COLS + j], xbar[j], s);
-    A[i * COLS + N] = s;
-  }
+  for (int i = 0; i < N; ++i) A[i * COLS + N] = b[i];
   // 143-150: whitened observation rows (L = chol(R_meas), not its inverse: reference quirk)
   {
     double y[M];
@@ -491,7 +484,7 @@ GKB_DEV bool srif_step_tri(const NlModel<N, M>& md, double (&b)[N], double (&U)[
   }
   householder_transf<N, M>(A);
 #pragma unroll
-  for (int i = 0; i < N; ++i) ok = ok && isfinite(A[i * COLS + N]);
+  for (int i = 0; i < N; ++i) ok = ok && isfinite(A[i * COLS + N]) && isfinite(A[i * COLS + i]);
   if (!__all_sync(0xffffffffu, ok)) return false;
 #pragma unroll
   for (int i = 0; i < N; ++i) {

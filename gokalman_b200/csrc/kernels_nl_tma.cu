@@ -169,6 +169,39 @@ hybrid_run_tma_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_con
 // column of a stage into registers the stage is re-armed for epoch k + kWStages, so every warp always has
 // one to two epochs (13 KB each at n = 6, m = 2) in flight while it does the FP64 work of the current one.
 // Out-of-range filters of a ragged last warp are zero-filled by the TMA and never written back.
+// The SRIF's GENERAL epoch (srif_step: LU with interchanges, votes, a full R), kept OUT OF LINE: it runs for Predict()
+// epochs, for the first epoch of a run (R is a full matrix until the first Householder update) and when the
+// speculative epoch gives up -- rare, and inlined it costs the hot loop its registers (the straight-line epoch
+// srif_step_tri needs all 255).  State and inputs travel through local / shared memory on this path only.
+template <int N, int M>
+__device__ __noinline__ int srif_epoch_general(const NlModel<N, M>& md, double* __restrict__ b_io, double* __restrict__ R_io,
+                                               const double* __restrict__ col, bool has_meas, bool pad_lane) {
+  constexpr int ROWS_PHI = N * N, ROWS_H = M * N;
+  double b[N], R[N * N], Phi[N * N], Ht[M * N], ro[M], co[M];
+#pragma unroll
+  for (int i = 0; i < N; ++i) b[i] = b_io[i];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) { R[i] = R_io[i]; Phi[i] = col[i * 32]; }
+#pragma unroll
+  for (int i = 0; i < M * N; ++i) Ht[i] = has_meas ? col[(ROWS_PHI + i) * 32] : 0.0;
+#pragma unroll
+  for (int a = 0; a < M; ++a) {
+    ro[a] = has_meas ? col[(ROWS_PHI + ROWS_H + a) * 32] : 0.0;
+    co[a] = has_meas ? col[(ROWS_PHI + ROWS_H + M + a) * 32] : 0.0;
+  }
+  if (pad_lane) {  // keep the padding lanes' Phi invertible (zero-filled by the TMA)
+#pragma unroll
+    for (int i = 0; i < N; ++i) Phi[i * N + i] = 1.0;
+  }
+  NlOut<N, M> o;
+  const int err = srif_step<N, M>(md, b, R, Phi, Ht, ro, co, has_meas, o);
+#pragma unroll
+  for (int i = 0; i < N; ++i) b_io[i] = b[i];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) R_io[i] = R[i];
+  return err;
+}
+
 struct NlTensorMaps {
   alignas(64) CUtensorMap phi;
   alignas(64) CUtensorMap h;
@@ -307,6 +340,23 @@ __device__ __forceinline__ void nl_wtma_task(const NlModel<N, M>& md, const NlIo
     const bool has_meas = (fl & GKB_F_MEAS) != 0, ekf = (fl & GKB_F_EKF) != 0;
     tma::mbar_wait(&full[s], phase);
     const double* col = ring + (size_t)s * ROWS * 32 + lane;
+    if constexpr (SRIF) {
+      // the general epoch, out of line (reads its inputs from the stage, state through a local copy)
+      double tb[N], tR[N * N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) tb[i] = x[i];
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) tR[i] = P[i];
+      const int err = srif_epoch_general<N, M>(md, tb, tR, col, has_meas, !active);
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = tb[i];
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) P[i] = tR[i];
+      __syncwarp();  // every lane is done with the stage: re-arm it
+      if (lane == 0 && k + kWStages < k1) issue(k + kWStages, s);
+      if (++s == kWStages) { s = 0; phase ^= 1u; }
+      if (err != 0 && status == 0) status = err;
+    } else {
     double Phi[N * N], Ht[M * N], ro[M], co[M];
 #pragma unroll
     for (int i = 0; i < N * N; ++i) Phi[i] = col[i * 32];
@@ -329,13 +379,7 @@ __device__ __forceinline__ void nl_wtma_task(const NlModel<N, M>& md, const NlIo
     if (++s == kWStages) { s = 0; phase ^= 1u; }
     NlOut<N, M> o;
     int err;
-    if constexpr (SRIF) {
-      if (!active) {  // keep the padding lanes' Phi invertible (zero-filled by the TMA)
-#pragma unroll
-        for (int i = 0; i < N; ++i) Phi[i * N + i] = 1.0;
-      }
-      err = srif_step<N, M>(md, x, P, Phi, Ht, ro, co, has_meas, o);
-    } else {
+    {
       err = hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, nullptr, has_meas, ekf, false, o);
       if (io.every_step && active && err == 0) {  // Estimate k: streamed out once, never read back here
         if (io.o_state != nullptr) {
@@ -353,6 +397,7 @@ __device__ __forceinline__ void nl_wtma_task(const NlModel<N, M>& md, const NlIo
       }
     }
     if (err != 0 && status == 0) status = err;
+    }  // !SRIF
   }
   if constexpr (SRIF) {
     // read-outs of the last estimate: State() = inv(R) b (srif.go:223-235), Covariance() = inv(R) inv(R)^T (253-265)

@@ -20,7 +20,8 @@ def test_van_loan_device_kat_and_batch(oracle):
         G = rng.standard_normal((n, q))
         Bq = rng.standard_normal((q, q))
         W = Bq @ Bq.T + np.eye(q)
-        dt = np.exp(rng.uniform(np.log(1e-3), np.log(20.0), count))  # 1-norms of M from ~1e-2 to ~1e2: every Pade degree
+        dt = np.exp(rng.uniform(np.log(1e-3), np.log(1.5), count))  # 1-norms of M from ~1e-2 to ~15: every Pade degree + scaling
+        # (larger |A| dt makes Van Loan's F E_12 product cancel e^{+|A| dt} against e^{-|A| dt}: ill-posed for any implementation)
         F, Q, st = gk.VanLoanBatch(A, G, W, dt)
         assert np.all(st == 0)
         for i in range(count):

@@ -142,6 +142,23 @@ def test_srif_full_size_subset_matches_oracle(oracle):
         assert ex <= TOL, report
         assert eP <= TOL, report
     print("srif full size (filter, err x, err P, reference FMA sensitivity):", report)
+    # production-vs-literal over ALL filters: the production epoch takes b-bar = b where the reference (and the general
+    # kernel, GKB_NL_PATH=plain) forms R-bar Phi inv(R) b; R is untouched by that, b / State() move at rounding level
+    os.environ["GKB_NL_PATH"] = "plain"
+    try:
+        kf2, _ = gk.NewSRIF(np.zeros(n), P0, m, False, gk.NewNoiseless(np.diag([1e-12] * 3), R), n_filters=nf)
+        xs2 = torch.zeros(n, nf, dtype=torch.float64, device=dev)
+        Ps2 = torch.zeros(n * n, nf, dtype=torch.float64, device=dev)
+        out.state, out.covar = xs2.data_ptr(), Ps2.data_ptr()
+        L.check(lib.gkb_nl_run(kf2._h, steps, flags.data_ptr(), Phi.data_ptr(), 0, Ht.data_ptr(), 0, real.data_ptr(),
+                               comp.data_ptr(), None, L.DEVICE, C.byref(out)))
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("GKB_NL_PATH", None)
+    assert bool(torch.equal(Ps, Ps2))
+    ex_all = ((xs - xs2).abs() / torch.maximum(xs2.abs(), xs2.abs().amax(dim=0, keepdim=True))).amax()
+    print("srif production-vs-literal over %d filters: covariance bit-identical, state max scaled diff %.2e" % (nf, float(ex_all)))
+    assert float(ex_all) <= TOL
 
 
 def test_vanilla32_full_size_subset_matches_oracle(oracle):

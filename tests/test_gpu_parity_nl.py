@@ -177,8 +177,9 @@ def test_hybrid_tma_staged_path_matches_oracle(oracle, n, m, nf):
 def test_srif_tma_staged_path_matches_oracle(oracle, n, m, nf):
     """SRIF on the production path (final read-outs only, per-filter streams): the warp-private TMA
     kernel, with Predict epochs (dense R afterwards: the general LU inverse) and Update epochs
-    (upper-triangular R: the triangular shortcut of inverse_lu).  Equal to the plain-load kernel bit
-    for bit and to the oracle to 1e-10: State(), Covariance(), raw b and R."""
+    (upper-triangular R: the straight-line production epoch, which takes b-bar = b instead of forming
+    R-bar Phi inv(R) b).  Equal to the literal plain-load kernel to rounding (1e-12: the b-bar shortcut), bit for bit
+    across its own scheduling variants, and to the oracle to 1e-10: State(), Covariance(), raw b and R."""
     import os
     gk = _gpu()
     from gokalman_b200._lib import F_MEAS, F_EKF, F_SNC
@@ -202,8 +203,8 @@ def test_srif_tma_staged_path_matches_oracle(oracle, n, m, nf):
     est, vec, mat = run(None)
     assert np.all(est.status == 0)
     est2, vec2, mat2 = run("plain")
-    assert np.array_equal(vec, vec2) and np.array_equal(mat, mat2)
-    assert np.array_equal(np.asarray(est.State()), np.asarray(est2.State()))
+    assert np.array_equal(mat, mat2)  # R never sees the shortcut
+    assert fx.scaled_err(vec, vec2) <= 1e-12 and fx.scaled_err(np.asarray(est.State()), np.asarray(est2.State())) <= 1e-12
     assert np.array_equal(np.asarray(est.Covariance()), np.asarray(est2.Covariance()))
     os.environ["GKB_NL_CHUNKS"] = "4"  # chunked persistent scheduling, forced
     try:
@@ -228,7 +229,8 @@ def test_srif_tma_speculative_epoch_falls_back(oracle, n, m, nf):
     """The production SRIF kernel runs measurement epochs speculatively without row interchanges in the LU of Phi
     (srif_step_tri) and must hand the epoch to the general step, from the untouched shared-memory stage, when some
     lane needs one.  Here a few filters get a Phi with two rows exchanged at some epochs (partial pivoting has to
-    swap), one filter gets a singular Phi (srif.go:112-114 error).  Bit-equal to the plain-load kernel, 1e-10 to the
+    swap), one filter gets a singular Phi (srif.go:112-114 error).  Equal to the literal plain-load kernel to rounding
+    (b: 1e-12, the production epoch's b-bar = b; R: bit for bit), bit-equal across scheduling variants, 1e-10 to the
     oracle, and the singular filter reports the error without disturbing its neighbours."""
     import os
     gk = _gpu()
@@ -261,10 +263,13 @@ def test_srif_tma_speculative_epoch_falls_back(oracle, n, m, nf):
     est, vec, mat = run(None)
     good = np.array([f for f in range(nf) if f != bad])
     assert np.all(est.status[good] == 0) and est.status[bad] != 0
-    for other in (run("plain"), run(None, "3")):
+    for literal, other in ((True, run("plain")), (False, run(None, "3"))):
         est2, vec2, mat2 = other
         assert np.array_equal(est.status, est2.status)
-        assert np.array_equal(vec[:, good], vec2[:, good]) and np.array_equal(mat[:, :, good], mat2[:, :, good])
+        # b: rounding level.  (After a fallback a warp runs the literal epoch for the rest of its TASK; with forced
+        # chunking the tasks are shorter, so a few more epochs take the production epoch's b-bar = b.)
+        assert fx.scaled_err(vec[:, good], vec2[:, good]) <= 1e-12, literal
+        assert np.array_equal(mat[:, :, good], mat2[:, :, good])
         assert np.array_equal(np.asarray(est.Covariance())[..., good], np.asarray(est2.Covariance())[..., good])
     for f in sorted(set([0, 1, 2, 32, 33, 34, 36, nf - 1])):
         o = oracle.NewSRIF(0.2 * np.ones(n), P0, m, False, R)
@@ -437,8 +442,13 @@ def test_host_stream_pipeline_is_bit_identical(kind, monkeypatch):
         monkeypatch.setenv("GKB_NL_H2D_CHUNK", chunk)
         for every in (False, True):
             x, P, (vec, mat) = run(every)
-            assert np.array_equal(x, ref[every][0]) and np.array_equal(P, ref[every][1]), (chunk, every)
-            assert np.array_equal(vec, ref[every][2][0]) and np.array_equal(mat, ref[every][2][1])
+            if kind == "srif":
+                # a 1-epoch tail launch (22 = 3 x 7 + 1) runs the literal general epoch, the others the production
+                # epoch with b-bar = b: equal to rounding in b / State(), bit for bit in R / Covariance()
+                assert fx.scaled_err(x, ref[every][0]) <= 1e-12 and fx.scaled_err(vec, ref[every][2][0]) <= 1e-12
+            else:
+                assert np.array_equal(x, ref[every][0]) and np.array_equal(vec, ref[every][2][0]), (chunk, every)
+            assert np.array_equal(P, ref[every][1]) and np.array_equal(mat, ref[every][2][1]), (chunk, every)
 
 
 def test_failed_epoch_writes_nan_rows_and_keeps_previous_estimate(oracle):
@@ -455,7 +465,8 @@ def test_failed_epoch_writes_nan_rows_and_keeps_previous_estimate(oracle):
     flags = np.full(steps, F_MEAS, dtype=np.uint8)
     kf, _ = gk.NewSRIF(np.zeros(n), P0, m, False, gk.NewNoiseless(np.zeros((n, n)), R), n_filters=nf)
     kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=True)      # an earlier call fills the staging buffers
-    kf.Reset()
+    from gokalman_b200 import _lib
+    _lib.check(_lib.load().gkb_reset(kf._h))
     est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=True)
     assert est.status[2] == -5 and np.all(np.delete(est.status, 2) == 0)
     xs, Ps = est.State(), est.Covariance()
