@@ -478,7 +478,8 @@ int gkb_set_stream(gkb_filter* f, void* stream) {
 
 int gkb_set_strict(gkb_filter* f, int on) {
   if (!f) return fail(GKB_ERR_ARG, "NULL handle");
-  if (f->hm.kind != GKB_HYBRID) return fail(GKB_ERR_UNSUPPORTED, "strict (reference-order) arithmetic is built for GKB_HYBRID handles");
+  if (f->hm.kind != GKB_HYBRID && f->hm.kind != GKB_SRIF)
+    return fail(GKB_ERR_UNSUPPORTED, "strict (reference-order) arithmetic is built for GKB_HYBRID and GKB_SRIF handles");
   f->strict = on != 0;
   return 0;
 }

@@ -245,7 +245,8 @@ template <int N, int M>
 static int launch_nl_shape(const HostModel& hm, const NlIo& io, cudaStream_t s) {
   if (hm.kind != GKB_HYBRID && hm.kind != GKB_SRIF) return GKB_ERR_UNSUPPORTED;
   // production configuration (per-filter streams, final outputs only): the TMA kernels of kernels_nl_tma.cu
-  if (!(io.strict && hm.kind == GKB_HYBRID) && launch_nl_tma(hm, io, s) == 0) return 0;
+  // (gkb_set_strict: the hybrid's reference-order kernel / the SRIF's literal general epoch instead)
+  if (!io.strict && launch_nl_tma(hm, io, s) == 0) return 0;
   return launch_nl_general<N, M>(hm, io, s);
 }
 

@@ -131,7 +131,10 @@ int gkb_set_stream(gkb_filter* f, void* stream);
  * dense Joseph form and AsSymDense (GKB_ERR_ASYMMETRIC can be raised in this mode) -- the arithmetic the
  * reference itself executes, at a fraction of the production kernels' speed.  For validation: the fast kernels
  * restructure the Joseph update and use FMAs, which moves ill-conditioned runs (statOD: R = 1e-6 against
- * P0 = 10) by more than 1e-10.  on = 0 (default) selects the production kernels. */
+ * P0 = 10) by more than 1e-10.  On a GKB_SRIF handle it selects the literal epoch of srif.go:101-160 (the general
+ * kernel: x-bar = Phi inv(R) b, b-bar = R-bar x-bar formed explicitly, full mat64.Inverse tests) instead of the
+ * production epoch, which takes b-bar = b and differs from it at rounding level (1.5e-13 on the full-size run).
+ * on = 0 (default) selects the production kernels. */
 int gkb_set_strict(gkb_filter* f, int on);
 int64_t gkb_n_filters(const gkb_filter* f);
 /* 1 when the handle's per-filter arrays are filter-major [N][C] (large-state handles), 0 for SoA [C][N]. */

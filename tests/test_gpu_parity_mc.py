@@ -295,3 +295,31 @@ def test_mc_chisquare_n7_n8_matches_oracle(oracle, kind, n, m):
     assert fx.scaled_err(r["nees"], ref["NEES"]) <= TOL, fx.scaled_err(r["nees"], ref["NEES"])
     if kind != "information":
         assert fx.scaled_err(r["nis"], ref["NIS"]) <= TOL, fx.scaled_err(r["nis"], ref["NIS"])
+
+
+def test_statod5044_example_monte_carlo_and_csv(oracle):
+    """examples/statOD5044/main.go:36-116: the 4-state / 2-control / 2-measurement statOD model -- truth from a pure
+    predictor with AWGN on the closed-loop F - G T (zero control matrix there: here G with zero controls, the
+    `len(controls) == 1` rule of montecarlo.go:98-104), NEES / NIS of a Vanilla filter on the same model, and
+    MonteCarloRuns.AsCSV (montecarlo.go:62-89) against Mean / StdDev / the dumped truth."""
+    gk = _gpu()
+    f = fx.statod4()
+    steps, trials = 108, 15  # numMC = 15 (main.go:74); samples shortened from 1086
+    fm = dict(F=f["Fcl"], G=f["G"], H=f["H"], Q=f["Q"], R=f["R"], x0=f["x0"], P0=f["P0"], x0_truth=f["x0"])
+    r = _mc_pair(gk, oracle, fm, "vanilla", trials, steps, [np.zeros(2)])
+    ref = r["ref"]
+    assert fx.scaled_err(r["tx"], ref["truth_x"].transpose(1, 2, 0)) <= TOL
+    assert fx.scaled_err(r["nees"], ref["NEES"]) <= TOL and fx.scaled_err(r["nis"], ref["NIS"]) <= TOL
+    headers = ["dr", "dr_dot", "dtheta", "dtheta_dot"]  # main.go:77
+    csvs = r["runs"].AsCSV(headers)
+    assert len(csvs) == 4
+    for i, text in enumerate(csvs):
+        lines = text.split("\n")
+        assert lines[0] == "".join("%s-%d," % (headers[i], k) for k in range(trials)) + headers[i] + "-mean," + headers[i] + "-stddev"
+        assert len(lines) == steps + 1
+        for k in (0, steps // 2, steps - 1):
+            vals = [float(v) for v in lines[1 + k].split(",")]
+            assert len(vals) == trials + 2
+            assert np.allclose(vals[:trials], r["tx"][k, i, :], atol=5e-7)            # %f: six decimals
+            assert abs(vals[trials] - ref["mean"][k, i]) <= 5e-7 + 1e-9 * abs(ref["mean"][k, i])
+            assert abs(vals[trials + 1] - ref["std"][k, i]) <= 5e-7 + 1e-6 * abs(ref["std"][k, i])
