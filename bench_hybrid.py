@@ -104,7 +104,7 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
     import torch.distributed as dist
     import gokalman_b200 as gk
     from gokalman_b200 import _lib as L
-    from bench import ClockSampler, hbm_peak, measured_traffic, when_fp64_peak_known
+    from bench import ClockSampler, hbm_peak, measured_traffic, settle_clocks, when_fp64_peak_known
 
     workload = workload or args.workload
     lib = gk.load()
@@ -162,6 +162,8 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
     n_steps = args.steps
     for _ in range(args.warmup if not sub else 3):
         step_device()
+    barrier()
+    settle_clocks(step_device, torch.cuda.synchronize)  # untimed: clocks out of idle, sustained regime
     barrier()
     if sub:  # long enough a timed region for the clock sampler: >= 0.15 s
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -26,7 +26,7 @@ def run_ours_tile(args, rank, world, local, sub=False):
     import torch.distributed as dist
     import gokalman_b200 as gk
     from gokalman_b200 import _lib as L
-    from bench import ClockSampler, measured_traffic, when_fp64_peak_known
+    from bench import ClockSampler, measured_traffic, settle_clocks, when_fp64_peak_known
     import fixtures as fx
 
     lib = gk.load()
@@ -61,6 +61,8 @@ def run_ours_tile(args, rank, world, local, sub=False):
     n_steps = args.steps if not sub else max(3, min(args.steps, 10))
     for _ in range(args.warmup if not sub else 3):
         step_device()
+    barrier()
+    settle_clocks(step_device, torch.cuda.synchronize, max_steps=8)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -205,3 +205,41 @@ def test_strict_hybrid_full_size_plain_tolerance(oracle):
     # conventional formulas reaches condition numbers of 1e12 on these streams)
     PRODUCTION_VS_STRICT_MEDIAN, PRODUCTION_VS_STRICT_P99, PRODUCTION_VS_STRICT_MAX = 1e-8, 1e-5, 1e-2
     assert q[0] <= PRODUCTION_VS_STRICT_MEDIAN and q[1] <= PRODUCTION_VS_STRICT_P99 and emax <= PRODUCTION_VS_STRICT_MAX
+
+
+def test_strict_on_srif_selects_the_literal_epoch(oracle):
+    """gkb_set_strict on a GKB_SRIF handle runs the literal epoch of srif.go:101-160 (x-bar = Phi inv(R) b and
+    b-bar = R-bar x-bar formed explicitly): bit-identical to the general kernel, 1e-10 to the oracle; the production
+    epoch (b-bar = b) differs from it at rounding level only."""
+    import os
+    import gokalman_b200 as gk
+    from gokalman_b200 import _lib as L
+    rng = np.random.default_rng(21)
+    n, m, nf, steps = 6, 2, 66, 30
+    Phi = np.eye(n)[None, :, :, None] + 0.02 * rng.standard_normal((steps, n, n, nf))
+    Ht = rng.standard_normal((steps, m, n, nf))
+    real = rng.standard_normal((steps, m, nf))
+    comp = real + 0.05 * rng.standard_normal((steps, m, nf))
+    flags = np.full(steps, L.F_MEAS, dtype=np.uint8)
+    P0, R = np.diag([50, 50, 50, 1, 1, 1.0]), np.diag([1e-2, 1e-2])
+
+    def run(strict, path=None):
+        if path:
+            os.environ["GKB_NL_PATH"] = path
+        try:
+            kf, _ = gk.NewSRIF(0.1 * np.ones(n), P0, m, False, gk.NewNoiseless(np.zeros((n, n)), R), n_filters=nf)
+            _lib_check = L.check(L.load().gkb_set_strict(kf._h, int(strict)))
+            est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=False, want=("state", "covar"))
+            return est, kf.GetState()
+        finally:
+            os.environ.pop("GKB_NL_PATH", None)
+    es, (bs, Rs) = run(True)
+    ep, (bp, Rp) = run(False)
+    el, (bl, Rl) = run(False, "plain")
+    assert np.array_equal(bs, bl) and np.array_equal(Rs, Rl) and np.array_equal(es.State(), el.State())
+    assert np.array_equal(Rs, Rp) and fx.scaled_err(bp, bs) <= 1e-12 and not np.array_equal(bp, bs)
+    o = oracle.NewSRIF(0.1 * np.ones(n), P0, m, False, R)
+    for k in range(steps):
+        o.Prepare(Phi[k, :, :, 7], Ht[k, :, :, 7])
+        eo = o.UpdateNL(real[k, :, 7], comp[k, :, 7])
+    assert fx.scaled_err(es.State()[:, 7], eo.State()) <= TOL and fx.scaled_err(es.Covariance()[:, :, 7], eo.Covariance()) <= TOL
