@@ -178,6 +178,8 @@ struct gkb_filter {
   bool philox = false;
   unsigned long long philox_seed = 0;
   long long philox_offset = 0;
+  bool awgn_valid = false;  // chol(Q), chol(R) of the current noise matrices (recomputed after gkb_set_noise)
+  double awgn_LQ[GKB_MAX_N * GKB_MAX_N], awgn_LR[GKB_MAX_M * GKB_MAX_M];
   DevBuf in_y, in_u, in_gu, in_a, in_b, in_c, in_d, in_e, in_f;  // staging for host inputs
   DevBuf o_state, o_meas, o_innov, o_covar, o_pred, o_gain, o_obsdev;
   // large-state handles (kernels_tile.cu): filter-major arrays, model kept on the device
@@ -570,6 +572,7 @@ int gkb_set_noise(gkb_filter* f, const double* Q, int m_r, const double* R) {
   f->has_w = f->has_v = false;
   f->replay_steps = 0;
   f->philox = false;  // SetNoise replaces the Noise object: an AWGN one is re-armed by gkb_set_philox_noise
+  f->awgn_valid = false;
   return 0;
 }
 
@@ -852,8 +855,11 @@ int gkb_update(gkb_filter* f, int steps, const double* y, int y_shared, const do
   if (f->philox) {
     // AWGN: this call's Process / Measurement samples, keyed by (filter, absolute step), into the replay arrays
     if (hm.m_r != m) return fail(GKB_ERR_DIMS, "dimensions must agree: H has %d rows but R is %dx%d", m, hm.m_r, hm.m_r);
-    double LQ[GKB_MAX_N * GKB_MAX_N], LR[GKB_MAX_M * GKB_MAX_M];
-    if ((rc = awgn_factors(hm, LQ, LR, f->stream))) return rc;
+    if (!f->awgn_valid) {  // one factorisation per SetNoise, not per Update()
+      if ((rc = awgn_factors(hm, f->awgn_LQ, f->awgn_LR, f->stream))) return rc;
+      f->awgn_valid = true;
+    }
+    const double *LQ = f->awgn_LQ, *LR = f->awgn_LR;
     const size_t wb = sizeof(double) * (size_t)steps * n * f->nf, vb = sizeof(double) * (size_t)steps * m * f->nf;
     if ((rc = f->replay_w.ensure(wb)) || (rc = f->replay_v.ensure(vb)) || (rc = f->replay_w2.ensure(wb))) return rc;
     const bool second = hm.kind == GKB_VANILLA;  // only Vanilla.Update calls Process(k) twice (vanilla.go:146,195)

@@ -20,9 +20,10 @@
 //                real observation = the truth's noise-free (rho, rho') of the epoch (table) + sigma * N(0, 1) drawn
 //                from Philox keyed by (seed, global filter index, epoch)  (hybrid_test.go:206: sigma^2 = 1e-6... here a parameter)
 //
-// od_step is deliberately NOT inlined: the stream generator (od_synth_kernel) and the fused filter kernel
-// (od_run_kernel) call the same machine code, so "synthesise, store, run gkb_nl_run on the streams" and "fused run"
-// are bit-identical by construction.
+// od_step is inlined into the stream generator (od_synth_kernel) and into the fused filter kernel (od_run_kernel); it is
+// written with explicit fma() for every multiply-add and plain single operations otherwise, so that no contraction
+// choice is left to the compiler and the two kernels agree bit for bit ("synthesise, store, run gkb_nl_run on the
+// streams" == "fused run": asserted in tests/test_gpu_od.py and in every bench run).
 #pragma once
 #include "engine_internal.h"
 #include "philox.cuh"
@@ -50,9 +51,11 @@ GKB_DEV void accel_grad(const OdParams& c, double x, double y, double z, double 
   const double q2 = fma(35.0 * z2, ir9, -15.0 * ir7);
   const double q3 = fma(35.0 * z2, ir9, -25.0 * ir7);
   const double m5 = 3.0 * c.mu * ir5, m3 = c.mu * ir3;
-  G.xx = fma(m5, x * x, -m3) - c.kj2 * fma(x * x, q1, f);
-  G.yy = fma(m5, y * y, -m3) - c.kj2 * fma(y * y, q1, f);
-  G.zz = fma(m5, z * z, -m3) - c.kj2 * fma(z * z, q3, g);
+  // (every a*b+c below is an explicit fma: the result must not depend on how a compiler contracts the expression,
+  // because od_step is inlined into two different kernels that have to agree bit for bit)
+  G.xx = fma(-c.kj2, fma(x * x, q1, f), fma(m5, x * x, -m3));
+  G.yy = fma(-c.kj2, fma(y * y, q1, f), fma(m5, y * y, -m3));
+  G.zz = fma(-c.kj2, fma(z * z, q3, g), fma(m5, z * z, -m3));
   G.xy = (x * y) * fma(-c.kj2, q1, m5);
   G.xz = (x * z) * fma(-c.kj2, q2, m5);
   G.yz = (y * z) * fma(-c.kj2, q2, m5);
@@ -69,7 +72,7 @@ GKB_DEV void grad_full(double (&M)[9], const Grad& G) {
 // One epoch of one filter.  X[6]: reference orbit (r, v) at t_k in, at t_{k+1} out.  st[6]: station position /
 // velocity (ECI) at t_{k+1}; tobs[2]: the truth's noise-free (range, range-rate) at t_{k+1}; z[2]: this filter's
 // standard-normal draws for the epoch.  out[52]: Phi (36, row-major), Htilde (12), real (2), computed (2).
-__device__ __noinline__ void od_step(const OdParams& c, double* __restrict__ X, const double* __restrict__ st,
+__device__ __forceinline__ void od_step(const OdParams& c, double* __restrict__ X, const double* __restrict__ st,
                                      const double* __restrict__ tobs, double z0, double z1, double* __restrict__ out) {
   const double h = c.h, hh = 0.5 * h;
   const double r0[3] = {X[0], X[1], X[2]}, v0[3] = {X[3], X[4], X[5]};
@@ -90,8 +93,8 @@ __device__ __noinline__ void od_step(const OdParams& c, double* __restrict__ X, 
   double rn[3], vn[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    rn[i] = fma(h6, (v0[i] + v3[i]) + 2.0 * (v1[i] + v2[i]), r0[i]);
-    vn[i] = fma(h6, (a0[i] + a3[i]) + 2.0 * (a1[i] + a2[i]), v0[i]);
+    rn[i] = fma(h6, fma(2.0, v1[i] + v2[i], v0[i] + v3[i]), r0[i]);
+    vn[i] = fma(h6, fma(2.0, a1[i] + a2[i], a0[i] + a3[i]), v0[i]);
     X[i] = rn[i];
     X[3 + i] = vn[i];
   }
@@ -109,7 +112,7 @@ __device__ __noinline__ void od_step(const OdParams& c, double* __restrict__ X, 
       const int e = i * 3 + j;
       out[kOdPhi + i * 6 + j] = fma(h4_24, P20[e], fma(h2_6, (M0[e] + M1[e]) + M2[e], id));             // Phi_rr
       out[kOdPhi + i * 6 + 3 + j] = fma(h3_12, M1[e] + M2[e], id * h);                                      // Phi_rv
-      out[kOdPhi + (3 + i) * 6 + j] = fma(h3_12, P20[e] + P31[e], h6 * ((M0[e] + M3[e]) + 2.0 * (M1[e] + M2[e])));  // Phi_vr
+      out[kOdPhi + (3 + i) * 6 + j] = fma(h3_12, P20[e] + P31[e], h6 * fma(2.0, M1[e] + M2[e], M0[e] + M3[e]));  // Phi_vr
       out[kOdPhi + (3 + i) * 6 + 3 + j] = fma(h4_24, P31[e], fma(h2_6, (M1[e] + M2[e]) + M3[e], id));   // Phi_vv
     }
   // range / range-rate to the epoch's station, their partials, the observations
