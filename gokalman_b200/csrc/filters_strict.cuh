@@ -194,12 +194,26 @@ GKB_DEV int hybrid_step(const NlModel<N, M>& md, double (&x)[N], double (&P)[N *
                         const double (&Ht)[M * N], const double (&real_obs)[M], const double (&computed_obs)[M],
                         const double* __restrict__ Gamma, bool has_meas, bool ekf, bool snc, double (&Ppred)[N * N],
                         double (&K)[N * M], double (&innov)[M], double (&obsdev)[M]) {
-  // 114-117
+  // 114-117: P-bar = (Phi P) Phi^T.  Row i of Phi P is formed and consumed at once (the entries, and the order of every
+  // sum, are those of the two full products: only the live range of the intermediate shrinks from N*N to N values)
   double Pbar[N * N];
-  {
-    double PhiP[N * N];
-    mul<N, N, N>(PhiP, Phi, P);
-    mul_nt<N, N, N>(Pbar, PhiP, Phi);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double row[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < N; ++l) s = add2(s, mul2(Phi[i * N + l], P[l * N + j]));
+      row[j] = s;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < N; ++l) s = add2(s, mul2(row[l], Phi[j * N + l]));
+      Pbar[i * N + j] = s;
+    }
   }
   if (snc && Gamma != nullptr) {  // 118-123: P-bar + (Gamma Q) Gamma^T
     const int q = md.q;
@@ -278,20 +292,35 @@ GKB_DEV int hybrid_step(const NlModel<N, M>& md, double (&x)[N], double (&P)[N *
     for (int i = 0; i < N; ++i)
 #pragma unroll
       for (int j = 0; j < N; ++j) KH[i * N + j] = add2(i == j ? 1.0 : 0.0, -KH[i * N + j]);
-    double T1[N * N];
-    mul<N, N, N>(T1, KH, Pbar);
-    mul_nt<N, N, N>(Pn, T1, KH);
-    double KR[N * M];
-    mul<N, M, M>(KR, Kn, md.R);
+    // ((I - K H) P-bar) (I - K H)^T + (K R) K^T, row by row (same entries and summation orders as the full products)
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+    for (int i = 0; i < N; ++i) {
+      double t1[N], kr[M];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < M; ++a) s = add2(s, mul2(KR[i * M + a], Kn[j * M + a]));
-        Pn[i * N + j] = add2(Pn[i * N + j], s);
+        for (int l = 0; l < N; ++l) s = add2(s, mul2(KH[i * N + l], Pbar[l * N + j]));
+        t1[j] = s;
       }
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < M; ++b) s = add2(s, mul2(Kn[i * M + b], md.R[b * M + a]));
+        kr[a] = s;
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < N; ++l) s = add2(s, mul2(t1[l], KH[j * N + l]));
+        double r = 0.0;
+#pragma unroll
+        for (int a = 0; a < M; ++a) r = add2(r, mul2(kr[a], Kn[j * M + a]));
+        Pn[i * N + j] = add2(s, r);
+      }
+    }
   }
   // 184-192
   if (!as_sym<N>(Pbar)) return GKB_ERR_ASYMMETRIC;
