@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1603,6 +1604,8 @@ struct NcclComms {
   std::vector<void*> comms;
 };
 NcclComms* nccl_comms_for(const int* devices, int n) {
+  static std::mutex mu;  // handles are per-thread, this cache is per-process
+  std::lock_guard<std::mutex> lock(mu);
   static std::vector<NcclComms*> cache;
   for (NcclComms* c : cache)
     if ((int)c->devices.size() == n && std::equal(devices, devices + n, c->devices.begin())) return c;
