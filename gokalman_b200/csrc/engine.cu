@@ -1172,7 +1172,7 @@ int gkb_od_run(gkb_filter* f, const gkb_od_config* cfg, int steps, const uint8_t
 int gkb_smooth_all(int n, int steps, int64_t n_filters, int device, const double* Phi, int phi_shared, double* state,
                    double* covar, int mem, int32_t* status) {
   if (!Phi || !state || !covar) return fail(GKB_ERR_ARG, "NULL argument");
-  if (n < 1 || n > 6) return fail(GKB_ERR_UNSUPPORTED, "no compiled smoothing kernel for n=%d", n);
+  if (n < 1 || n > GKB_MAX_N) return fail(GKB_ERR_UNSUPPORTED, "no compiled smoothing kernel for n=%d", n);
   if (steps < 1 || n_filters < 1) return fail(GKB_ERR_ARG, "steps and n_filters must be >= 1");
   int rc = check_device(device);
   if (rc) return rc;

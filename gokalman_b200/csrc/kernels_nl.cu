@@ -106,7 +106,7 @@ int launch_smooth_all(int n, int64_t nf, int steps, const double* Phi, int phi_s
   const unsigned grid = (unsigned)((nf + kThreads - 1) / kThreads);
   switch (n) {
 #define GKB_SM(NN) case NN: smooth_all_kernel<NN><<<grid, kThreads, 0, s>>>(nf, steps, Phi, phi_shared, xs, Ps, status); return 0;
-    GKB_SM(1) GKB_SM(2) GKB_SM(3) GKB_SM(4) GKB_SM(5) GKB_SM(6)
+    GKB_SM(1) GKB_SM(2) GKB_SM(3) GKB_SM(4) GKB_SM(5) GKB_SM(6) GKB_SM(7) GKB_SM(8)
 #undef GKB_SM
     default: return GKB_ERR_UNSUPPORTED;
   }
@@ -132,7 +132,7 @@ int launch_householder(int n, int m, int64_t count, double* A, cudaStream_t s) {
   const unsigned grid = (unsigned)((count + kThreads - 1) / kThreads);
 #define GKB_CASE(NN, MM) \
   if (n == NN && m == MM) { householder_kernel<NN, MM><<<grid, kThreads, 0, s>>>(count, A); return 0; }
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)
   GKB_CASE(2, 3)  // srif_test.go:31-56 (the reference's measurementSRIFUpdate known-answer test)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
@@ -236,7 +236,7 @@ int launch_batch_solve(int n, int m, const double* R_host, int64_t nf, int steps
                        cudaStream_t s) {
 #define GKB_CASE(NN, MM) \
   if (n == NN && m == MM) return launch_batch_shape<NN, MM>(R_host, nf, steps, H, h_shared, real_obs, computed_obs, xhat0, P0, status, s);
-  GKB_FOR_EACH_SHAPE(GKB_CASE)
+  GKB_FOR_EACH_LTI_SHAPE(GKB_CASE)
 #undef GKB_CASE
   return GKB_ERR_UNSUPPORTED;
 }

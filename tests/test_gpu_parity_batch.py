@@ -14,7 +14,7 @@ def _gpu():
     return gk
 
 
-@pytest.mark.parametrize("n,m,nf,shared", [(6, 2, 133, False), (4, 2, 7, True), (3, 1, 40, False)])
+@pytest.mark.parametrize("n,m,nf,shared", [(6, 2, 133, False), (4, 2, 7, True), (3, 1, 40, False), (8, 3, 20, False), (7, 1, 9, True)])
 def test_batch_solve_matches_oracle(oracle, n, m, nf, shared):
     gk = _gpu()
     rng = np.random.default_rng(31 + n + nf)

@@ -356,7 +356,8 @@ def test_hybrid_basic_lock_and_toggle(oracle):
     assert eg.IsWithinNσ(1e6)
 
 
-@pytest.mark.parametrize("kind,n,m,nf,shared", [("hybrid", 6, 2, 37, False), ("hybrid", 4, 2, 5, True), ("srif", 6, 2, 9, False)])
+@pytest.mark.parametrize("kind,n,m,nf,shared", [("hybrid", 6, 2, 37, False), ("hybrid", 4, 2, 5, True), ("srif", 6, 2, 9, False),
+                                                 ("hybrid", 8, 2, 11, False), ("srif", 7, 2, 6, False)])
 def test_smooth_all_matches_oracle(oracle, kind, n, m, nf, shared):
     """SmoothAll (hybrid.go:209-238, srif.go:165-192): backward sweep over the stored estimates of a
     batched run, every smoothed state / covariance of every step against the oracle's restatement."""
