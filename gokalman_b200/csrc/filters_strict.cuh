@@ -336,5 +336,315 @@ GKB_DEV int hybrid_step(const NlModel<N, M>& md, double (&x)[N], double (&P)[N *
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same step with the N x N matrices in lane-private SHARED-MEMORY columns and ROLLED loops (round 2).
+//
+// The fully unrolled register version above is ~56 KB of SASS per epoch at n = 6 (it streams through the
+// instruction cache: `no_instruction` 0.47 stalls per issue) and spills (255 registers + 732 B).  Here a thread's
+// matrices live at sm[e * kStrictThreads + threadIdx.x] (entry-major over the CTA: consecutive lanes, consecutive banks, no
+// conflicts) and each of the four dense products is a loop of N iterations -- one column (or row) of the stored
+// operand per iteration against a matrix held in registers with static indices:
+//     T = Phi P        by columns of P   (Ps -> Ws)
+//     P-bar = T Phi^T  by rows of T      (Ws, in place: row i of T is dead once row i of P-bar is formed)
+//     X = A P-bar      by columns        (Ws, in place),  A = I - K H in the registers Phi occupied
+//     P+ = X A^T + (K R) K^T  by rows    (Ws, in place)
+// Every entry is the same sequence of individually rounded multiplications and additions, in the same order, as in
+// the full products of the reference -- only WHERE the operands wait changes.  One deliberate difference: the
+// reference's (and gonum's) sums start from 0; `0 + a*b` is elided here.  That is exact for every value except
+// that (-0) would become +0: only the sign of an exactly-zero entry can differ, which no later operation of the step
+// turns into a different number (zeros are only multiplied, added and compared; pivots are tested `!= 0` first).
+//
+// Ps holds the previous covariance as the PACKED upper triangle (what AsSymDense keeps: the reference reads P[i][j], i > j,
+// from the upper half) and is NOT modified by the step: on success the new covariance is in Ws and the caller copies its
+// upper triangle into Ps (hybrid_sm_commit); on an error nothing of the previous estimate has been touched (hybrid.go
+// returns (nil, err)).  Per thread: N(N+1)/2 + N*N + (N*M + 2M) doubles + N*N for the kernel's Phi stage: 872 B at n = 6,
+// m = 2, i.e. 109 KB per CTA of 128 threads, two CTAs per SM.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStrictThreads = 128;  // threads per CTA of the shared-memory strict kernel (measured: 2 CTAs of 128 at ~250
+constexpr int kStrictMinBlocks = 2;  // registers beat 3 x 96 and 2 x 160 at 168 registers, which spill)
+#define GKB_SM(p, e) (p)[(e) * kStrictThreads]
+
+// dst = Mr * src, column by column (Mr: registers, row-major); src == dst allowed
+template <int N>
+GKB_DEV void sm_left_mul(const double (&Mr)[N * N], const double* src, double* dst) {
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    double p[N], o[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) p[l] = GKB_SM(src, l * N + j);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = mul2(Mr[i * N], p[0]);
+#pragma unroll
+      for (int l = 1; l < N; ++l) s = add2(s, mul2(Mr[i * N + l], p[l]));
+      o[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) GKB_SM(dst, i * N + j) = o[i];
+  }
+}
+
+// dst = Mr * S, S symmetric, stored as its packed upper triangle (static addresses: fully unrolled)
+template <int N>
+GKB_DEV void sm_left_mul_sym(const double (&Mr)[N * N], const double* src, double* dst) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double p[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) p[l] = GKB_SM(src, sym_idx<N>(l, j));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = mul2(Mr[i * N], p[0]);
+#pragma unroll
+      for (int l = 1; l < N; ++l) s = add2(s, mul2(Mr[i * N + l], p[l]));
+      GKB_SM(dst, i * N + j) = s;
+    }
+  }
+}
+
+// P := AsSymDense(W): the upper triangle of the (already tested) work matrix becomes the packed covariance
+template <int N>
+GKB_DEV void hybrid_sm_commit(double* Ps, const double* Ws) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i; j < N; ++j) GKB_SM(Ps, sym_idx<N>(i, j)) = GKB_SM(Ws, i * N + j);
+}
+
+// AsSymDense on a shared-memory matrix (helper.go:65-84): false when an off-diagonal pair differs by more than 1e-6
+// absolute AND more than 1e-2 relative; MIRROR copies the upper triangle down (mat64.SymDense reads only the upper one).
+// One straight-line pass decides the common case (every pair within 1e-6) and mirrors the pairs it has accepted; only
+// when a pair fails that test does the exact predicate run, on the pairs as they still stand.
+template <int N, bool MIRROR>
+GKB_DEV bool sm_as_sym(double* A) {
+  bool fast = true;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      const double a = GKB_SM(A, j * N + i), b = GKB_SM(A, i * N + j);
+      const bool pass = fabs(a - b) <= 1e-6;
+      fast = fast && pass;
+      if (MIRROR && pass) GKB_SM(A, i * N + j) = a;
+    }
+  if (fast) return true;
+  bool ok = true;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i)
+#pragma unroll 1
+    for (int j = 0; j < i; ++j) {
+      const double a = GKB_SM(A, j * N + i), b = GKB_SM(A, i * N + j);
+      const double d = fabs(a - b);
+      ok = ok && ((a == b) || (d <= 1e-6) || (d / fmax(fabs(a), fabs(b)) <= 1e-2));
+    }
+  if (!ok) return false;
+  if (MIRROR) {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i)
+#pragma unroll 1
+      for (int j = 0; j < i; ++j) GKB_SM(A, i * N + j) = GKB_SM(A, j * N + i);
+  }
+  return true;
+}
+
+// Phase A (hybrid.go:114-123 and the x-bar of 126 / 163): Ws = P-bar, xbar = Phi x.  Phi is dead afterwards.
+template <int N, int M>
+GKB_DEV void hybrid_sm_predict(const NlModel<N, M>& md, const double (&x)[N], const double* Ps, double* Ws,
+                               const double (&Phi)[N * N], const double* __restrict__ Gamma, bool snc, double (&xbar)[N]) {
+  sm_left_mul_sym<N>(Phi, Ps, Ws);  // T = Phi P
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {  // P-bar = T Phi^T, row i in place
+    double t[N], o[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) t[l] = GKB_SM(Ws, i * N + l);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = mul2(t[0], Phi[j * N]);
+#pragma unroll
+      for (int l = 1; l < N; ++l) s = add2(s, mul2(t[l], Phi[j * N + l]));
+      o[j] = s;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) GKB_SM(Ws, i * N + j) = o[j];
+  }
+  if (snc && Gamma != nullptr) {  // 118-123: P-bar + (Gamma Q) Gamma^T  (rare: sums from 0 as written)
+    const int q = md.q;
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+      double gq[GKB_MAX_Q];
+#pragma unroll
+      for (int a = 0; a < GKB_MAX_Q; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < GKB_MAX_Q; ++b)
+          if (a < q && b < q) s = add2(s, mul2(__ldg(Gamma + i * q + b), md.Q[b * q + a]));
+        gq[a] = s;
+      }
+#pragma unroll 1
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < GKB_MAX_Q; ++a)
+          if (a < q) s = add2(s, mul2(gq[a], __ldg(Gamma + j * q + a)));
+        GKB_SM(Ws, i * N + j) = add2(GKB_SM(Ws, i * N + j), s);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = mul2(Phi[i * N], x[0]);
+#pragma unroll
+    for (int j = 1; j < N; ++j) s = add2(s, mul2(Phi[i * N + j], x[j]));
+    xbar[i] = s;
+  }
+}
+
+// Phase B (hybrid.go:125-204).  Ws: P-bar in, the new covariance out.  pred_out (global, this filter's column, or
+// nullptr) receives AsSymDense(P-bar) -- the caller overwrites it with NaN if the step fails after that point.
+template <int N, int M>
+GKB_DEV int hybrid_sm_update(const NlModel<N, M>& md, double (&x)[N], double* Ws, double* KRs, const double (&xbar)[N],
+                             const double (&Ht)[M * N], const double (&real_obs)[M], const double (&computed_obs)[M],
+                             bool has_meas, bool ekf, double* __restrict__ pred_out, int64_t nf, double (&K)[N * M],
+                             double (&innov)[M], double (&obsdev)[M]) {
+  auto write_pred = [&]() {
+    if (pred_out == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) __stcs(pred_out + (int64_t)(i * N + j) * nf, GKB_SM(Ws, (i <= j) ? (i * N + j) : (j * N + i)));
+  };
+  if (!has_meas) {  // Predict(): 125-143
+    if (!sm_as_sym<N, false>(Ws)) return GKB_ERR_ASYMMETRIC;
+    write_pred();
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = ekf ? 0.0 : xbar[i];
+#pragma unroll
+    for (int a = 0; a < M; ++a) { innov[a] = 0.0; obsdev[a] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < N * M; ++i) K[i] = 0.0;
+    return 0;
+  }
+  // 146-153
+  double PHt[N * M];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double row[N];
+#pragma unroll
+    for (int l = 0; l < N; ++l) row[l] = GKB_SM(Ws, i * N + l);
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double s = mul2(row[0], Ht[a * N]);
+#pragma unroll
+      for (int l = 1; l < N; ++l) s = add2(s, mul2(row[l], Ht[a * N + l]));
+      PHt[i * M + a] = s;
+    }
+  }
+  double S[M * M];
+#pragma unroll
+  for (int a = 0; a < M; ++a)
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+      double s = mul2(Ht[a * N], PHt[b]);
+#pragma unroll
+      for (int l = 1; l < N; ++l) s = add2(s, mul2(Ht[a * N + l], PHt[l * M + b]));
+      S[a * M + b] = add2(s, md.R[a * M + b]);
+    }
+  if (inverse<M>(S) != 0) return GKB_ERR_SINGULAR_S;
+  double Kn[N * M];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double s = mul2(PHt[i * M], S[a]);
+#pragma unroll
+      for (int b = 1; b < M; ++b) s = add2(s, mul2(PHt[i * M + b], S[b * M + a]));
+      Kn[i * M + a] = s;
+    }
+  // 156-173
+  double y[M], inn[M], xhat[N];
+#pragma unroll
+  for (int a = 0; a < M; ++a) { y[a] = add2(real_obs[a], -computed_obs[a]); inn[a] = 0.0; }
+  if (ekf) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = mul2(Kn[i * M], y[0]);
+#pragma unroll
+      for (int a = 1; a < M; ++a) s = add2(s, mul2(Kn[i * M + a], y[a]));
+      xhat[i] = s;
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double s = mul2(Ht[a * N], xbar[0]);
+#pragma unroll
+      for (int l = 1; l < N; ++l) s = add2(s, mul2(Ht[a * N + l], xbar[l]));
+      inn[a] = add2(y[a], -s);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = mul2(Kn[i * M], inn[0]);
+#pragma unroll
+      for (int a = 1; a < M; ++a) s = add2(s, mul2(Kn[i * M + a], inn[a]));
+      xhat[i] = add2(xbar[i], s);
+    }
+  }
+  // 184-187 (moved up: P-bar is not modified between 117 and 184, and X below overwrites it)
+  if (!sm_as_sym<N, false>(Ws)) return GKB_ERR_ASYMMETRIC;
+  write_pred();
+  // 174-182: dense Joseph form ((I - K H) P-bar) (I - K H)^T + (K R) K^T
+  {
+    double A[N * N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = mul2(Kn[i * M], Ht[j]);
+#pragma unroll
+        for (int a = 1; a < M; ++a) s = add2(s, mul2(Kn[i * M + a], Ht[a * N + j]));
+        A[i * N + j] = add2(i == j ? 1.0 : 0.0, -s);
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double s = mul2(Kn[i * M], md.R[a]);
+#pragma unroll
+        for (int b = 1; b < M; ++b) s = add2(s, mul2(Kn[i * M + b], md.R[b * M + a]));
+        GKB_SM(KRs, i * M + a) = s;
+      }
+    sm_left_mul<N>(A, Ws, Ws);  // X = (I - K H) P-bar
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {  // P+ row i = X row i (I - K H)^T + (K R) row i K^T
+      double t[N], kr[M], o[N];
+#pragma unroll
+      for (int l = 0; l < N; ++l) t[l] = GKB_SM(Ws, i * N + l);
+#pragma unroll
+      for (int a = 0; a < M; ++a) kr[a] = GKB_SM(KRs, i * M + a);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = mul2(t[0], A[j * N]);
+#pragma unroll
+        for (int l = 1; l < N; ++l) s = add2(s, mul2(t[l], A[j * N + l]));
+        double r = mul2(kr[0], Kn[j * M]);
+#pragma unroll
+        for (int a = 1; a < M; ++a) r = add2(r, mul2(kr[a], Kn[j * M + a]));
+        o[j] = add2(s, r);
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) GKB_SM(Ws, i * N + j) = o[j];
+    }
+  }
+  // 188-192 (the caller keeps the upper triangle: hybrid_sm_commit)
+  if (!sm_as_sym<N, false>(Ws)) return GKB_ERR_ASYMMETRIC;
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = xhat[i];
+#pragma unroll
+  for (int i = 0; i < N * M; ++i) K[i] = Kn[i];
+#pragma unroll
+  for (int a = 0; a < M; ++a) { innov[a] = inn[a]; obsdev[a] = y[a]; }
+  return 0;
+}
+
 }  // namespace strict
 }  // namespace gkb

@@ -66,8 +66,10 @@ typedef enum gkb_mem { GKB_HOST = 0, GKB_DEVICE = 1 } gkb_mem;
 const char* gkb_version(void);
 const char* gkb_last_error(void);
 int gkb_device_count(void);
-/* 1 if a filter of (kind, n, m) can be created: LDKF kinds n <= 8, m <= 3 (n = 5: m <= 2) plus the large-state Vanilla
- * shapes; HYBRID / SRIF n <= 6.  (gkb_mc_chisquare has kernels for n <= 6 and reports GKB_ERR_UNSUPPORTED above.) */
+/* 1 if a filter of (kind, n, m) can be created: every kind n <= 8, m <= 3 (n = 5: m <= 2) plus the large-state Vanilla
+ * shapes.  gkb_mc_chisquare, gkb_smooth_all, gkb_batch_solve and gkb_householder_transf cover the same n <= 8 table.
+ * n = 7, 8 run the same one-filter-per-thread templates with L1-resident spills (correct to the same bar, slower);
+ * the TMA production path of the NLDKF kinds is n <= 6. */
 int gkb_shape_supported(int kind, int n, int m);
 
 /* ---- construction: replaces NewVanilla / NewPurePredictorVanilla / NewInformation /

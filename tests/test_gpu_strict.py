@@ -243,3 +243,37 @@ def test_strict_on_srif_selects_the_literal_epoch(oracle):
         o.Prepare(Phi[k, :, :, 7], Ht[k, :, :, 7])
         eo = o.UpdateNL(real[k, :, 7], comp[k, :, 7])
     assert fx.scaled_err(es.State()[:, 7], eo.State()) <= TOL and fx.scaled_err(es.Covariance()[:, :, 7], eo.Covariance()) <= TOL
+
+
+def test_strict_scheduler_and_register_twin_are_bit_identical():
+    """The shared-memory strict kernel under its (chunk, group) scheduler -- forced onto a small ragged batch with 1, 2
+    and 5 chunks, Predict epochs on chunk boundaries, final and every-step outputs -- returns the bits of the default
+    launch and of the fully unrolled register version (GKB_STRICT_PATH=regs), the first implementation of the same step."""
+    import gokalman_b200 as gk
+    from gokalman_b200 import _lib as L
+    from bench import np_od_streams
+    nf, steps, n, m = 77, 41, 6, 2
+    Phi, Ht, real, comp = np_od_streams(nf, steps, 99)
+    Phi, Ht = Phi.reshape(steps, n, n, nf), Ht.reshape(steps, m, n, nf)
+    flags = np.array([(0 if k in (8, 9, 20) else L.F_MEAS) | (L.F_EKF if k >= 15 else 0) for k in range(steps)], dtype=np.uint8)
+
+    def run(every, env):
+        saved = {k: os.environ.get(k) for k in ("GKB_NL_CHUNKS", "GKB_STRICT_PATH")}
+        os.environ.update(env)
+        try:
+            kf, _ = gk.NewHybridKF(np.zeros(n), P0_APPD, gk.NewNoiseless(Q_APPD, R_APPD), m, n_filters=nf)
+            kf.SetStrict(True)
+            est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=every)
+            assert np.all(est.status == 0)
+            return [np.asarray(getattr(est, g)()) for g in ("State", "Covariance", "PredCovariance", "Gain", "Innovation")]
+        finally:
+            for k, v in saved.items():
+                os.environ.pop(k, None)
+                if v is not None:
+                    os.environ[k] = v
+    for every in (False, True):
+        ref = run(every, {})
+        for env in ({"GKB_NL_CHUNKS": "1"}, {"GKB_NL_CHUNKS": "2"}, {"GKB_NL_CHUNKS": "5"}, {"GKB_STRICT_PATH": "regs"}):
+            got = run(every, env)
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b), (every, env)
