@@ -1155,6 +1155,8 @@ int gkb_od_run(gkb_filter* f, const gkb_od_config* cfg, int steps, const uint8_t
   io.o_state = pl.state;
   io.o_covar = pl.covar;
   io.status = f->status.as<int32_t>();
+  if ((rc = f->sched.ensure(sizeof(int) * (size_t)((f->nf + 31) / 32 + 1)))) return rc;
+  io.sched = f->sched.as<int>();
   const bool sync = !(out && out->mem == GKB_DEVICE);
   Timer tm(f->stream);
   rc = launch_od_run(hm, c, io, f->orbit.as<double>(), dst, dst + 6 * (size_t)steps, f->stream);

@@ -8,6 +8,7 @@
 #include "engine_internal.h"
 #include "filters_nl.cuh"
 #include "filters_strict.cuh"
+#include "sched.cuh"
 
 namespace gkb {
 
@@ -146,19 +147,6 @@ GKB_DEV void nl_cp_async8(double* smem_dst, const double* gsrc) {
 GKB_DEV void nl_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 GKB_DEV void nl_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Spin (lane 0) until the group's flag reaches `value`, then make the state written by the group's previous owner visible.
-GKB_DEV void nl_acquire_group(const int* flag, int value, int lane) {
-  if (lane == 0) {
-    int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-      if (seen < value) __nanosleep(200);
-    } while (seen < value);
-  }
-  __syncwarp();
-  __threadfence();
-}
-
 // Epochs [k0, k1) of filter `tid` (one thread), state from / to the handle's arrays.
 // Shared-memory columns of the thread: Ps (packed covariance), Ws (work matrix), Hs (M*N + 2M: the stage of H-tilde and the
 // two observations between the end of one epoch and the update of the next, and K R during the Joseph products -- the two
@@ -290,23 +278,13 @@ hybrid_run_strict_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_
     return;
   }
   const int n_tasks = groups * io.chunks;
-  int* next_task = io.sched;  // [0]: task counter;  [1 + g]: chunks of group g already written back
-  int* done = io.sched + 1;
-  for (;;) {
-    int task = 0;
-    if (lane == 0) task = atomicAdd(next_task, 1);
-    task = __shfl_sync(0xffffffffu, task, 0);
-    if (task >= n_tasks) break;
-    const int c = task / groups, g = task - c * groups;
+  int c, g;
+  while (sched_claim(io.sched, n_tasks, groups, lane, c, g)) {
     const int k0 = c * io.chunk_len, k1 = min(io.steps, k0 + io.chunk_len);
-    if (c > 0) nl_acquire_group(done + g, c, lane);
+    if (c > 0) sched_acquire_group(io.sched + 1 + g, c, lane);
     const int64_t tid = (int64_t)g * 32 + lane;
     if (tid < io.nf) strict_task<N, M, true>(md, io, Ps, Ws, Hs, Fs, tid, k0, k1);
-    if (c != io.chunks - 1) {  // publish the state to whichever warp claims the next chunk of this group
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + g), "r"(c + 1) : "memory");
-    }
+    if (c != io.chunks - 1) sched_release_group(io.sched + 1 + g, c + 1, lane);
   }
 }
 
@@ -466,29 +444,12 @@ static int launch_nl_general(const HostModel& hm, const NlIo& io, cudaStream_t s
     const int64_t groups = (io.nf + 31) / 32;
     const int64_t slots = (int64_t)sms * per_sm * kWarps;
     NlIo io2 = io;
-    io2.chunks = 0;
-    io2.chunk_len = io.steps;
     int64_t ctas = (groups + kWarps - 1) / kWarps;
-    // more groups than resident warps: (chunk, group) tasks claimed dynamically, ~8 per resident warp, chunks >= 16 epochs
-    int chunks = 1;
-    if (groups > slots && io.sched != nullptr) {
-      const double per_slot = (double)groups / (double)slots;
-      const int base = (int)(kStrictTasksPerWarp / per_slot + 0.5);
-      double best = -1.0;
-      for (int c = base - 1; c <= base + 1; ++c) {
-        if (c < 2 || io.steps / c < 16) continue;
-        const double rounds = per_slot * c;
-        const double eff = rounds / (double)(int64_t)(rounds + 0.999999);
-        if (eff > best + 1e-9) { best = eff; chunks = c; }
-      }
-    }
-    if (const char* e = getenv("GKB_NL_CHUNKS")) {  // tests force the scheduler on small batches
-      const int c = atoi(e);
-      if (io.sched != nullptr && c >= 1 && c <= io.steps) chunks = c;
-    }
-    if (chunks > 1 || (getenv("GKB_NL_CHUNKS") != nullptr && io.sched != nullptr)) {
-      io2.chunk_len = (io.steps + chunks - 1) / chunks;
-      io2.chunks = (io.steps + io2.chunk_len - 1) / io2.chunk_len;
+    bool forced = false;
+    const int chunks = io.sched != nullptr ? sched_pick_chunks(groups, slots, io.steps, kStrictTasksPerWarp, &forced) : 1;
+    const bool scheduled = io.sched != nullptr && (chunks > 1 || forced);
+    sched_set_chunks(io2, chunks, scheduled);
+    if (scheduled) {
       if (ctas > (int64_t)sms * per_sm) ctas = (int64_t)sms * per_sm;
       cudaMemsetAsync(io.sched, 0, sizeof(int) * (size_t)(groups + 1), s);
     }

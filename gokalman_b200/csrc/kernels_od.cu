@@ -6,13 +6,15 @@
 //   od_run_kernel     the same synthesis FUSED with the hybrid CKF / EKF step (hybrid.go:104-204): every epoch's Phi,
 //                     Htilde and observations are produced in the thread that consumes them and never touch HBM.
 //                     Host traffic of a whole run: 48 B per filter in (initial orbit), the final estimate out.
-// Both call the same non-inlined od_step, so the fused run is bit-identical to gkb_nl_run on the synthesised streams.
+// od_step is inlined into both with explicit fma()s, so the fused run is bit-identical to gkb_nl_run on the synthesised
+// streams.  The fused run is scheduled in (chunk, group) tasks when there are more groups than resident warps (sched.cuh).
 #include <cstring>
 
 #include "engine_internal.h"
 #include "filters_nl.cuh"
 #include "filters_strict.cuh"
 #include "od_synth.cuh"
+#include "sched.cuh"
 
 namespace gkb {
 
@@ -55,33 +57,31 @@ od_synth_kernel(const __grid_constant__ OdParams c, int64_t nf, int steps, doubl
 }
 
 // Fused run: N = 6, M = 2 (the statOD shape).  STRICT selects the reference-order filter step (filters_strict.cuh).
-template <bool STRICT>
-__global__ void __launch_bounds__(kThreads)
-od_run_kernel(const __grid_constant__ NlModel<6, 2> md, const __grid_constant__ OdParams c,
-              const __grid_constant__ NlIo io, double* __restrict__ orbit, const double* __restrict__ station,
-              const double* __restrict__ tobs) {
+// Epochs [k0, k1) of filter `tid`: reference orbit, filter state and covariance come from and go back to the handle's
+// arrays; `last` = these are the final epochs of the call (the final-estimate outputs are written).
+template <bool STRICT, bool SCHED>
+__device__ __forceinline__ void od_task(const NlModel<6, 2>& md, const OdParams& c, const NlIo& io, double* __restrict__ orbit,
+                                        const double* __restrict__ station, const double* __restrict__ tobs,
+                                        const double* icdf_tab, int64_t tid, int k0, int k1, bool last) {
   constexpr int N = 6, M = 2, SN = N * (N + 1) / 2, PN = STRICT ? N * N : SN;
-  extern __shared__ __align__(16) double icdf_tab[];
-  icdf_load(icdf_tab);
-  __syncthreads();
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= io.nf) return;
+  auto ld_state = [](const double* p) { return SCHED ? __ldcg(p) : *p; };  // SCHED: written by another SM -> read from L2
   double X[6], x[N], P[PN];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) X[i] = orbit[(int64_t)i * io.nf + tid];
+  for (int i = 0; i < 6; ++i) X[i] = ld_state(orbit + (int64_t)i * io.nf + tid);
 #pragma unroll
-  for (int i = 0; i < N; ++i) x[i] = io.vec[(int64_t)i * io.nf + tid];
+  for (int i = 0; i < N; ++i) x[i] = ld_state(io.vec + (int64_t)i * io.nf + tid);
 #pragma unroll
   for (int i = 0; i < N; ++i)
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      const double v = io.mat[(int64_t)((i <= j) ? (i * N + j) : (j * N + i)) * io.nf + tid];
+      if (!STRICT && i > j) continue;
+      const double v = ld_state(io.mat + (int64_t)((i <= j) ? (i * N + j) : (j * N + i)) * io.nf + tid);
       if constexpr (STRICT) P[i * N + j] = v;
-      else if (i <= j) P[sym_idx<N>(i, j)] = v;
+      else P[sym_idx<N>(i, j)] = v;
     }
   const uint64_t gf = (uint64_t)(c.filter_offset + tid);
   int status = 0;
-  for (int k = 0; k < io.steps; ++k) {
+  for (int k = k0; k < k1; ++k) {
     const unsigned fl = io.flags ? io.flags[k] : (unsigned)GKB_F_MEAS;
     const bool has_meas = (fl & GKB_F_MEAS) != 0, ekf = (fl & GKB_F_EKF) != 0;
     double st[6], to[2], z[2], o[kOdRows];
@@ -128,12 +128,13 @@ od_run_kernel(const __grid_constant__ NlModel<6, 2> md, const __grid_constant__ 
       }
     }
   }
+  const bool final_out = last && !io.every_step;
 #pragma unroll
   for (int i = 0; i < 6; ++i) orbit[(int64_t)i * io.nf + tid] = X[i];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     io.vec[(int64_t)i * io.nf + tid] = x[i];
-    if (!io.every_step && io.o_state != nullptr) io.o_state[(int64_t)i * io.nf + tid] = x[i];
+    if (final_out && io.o_state != nullptr) io.o_state[(int64_t)i * io.nf + tid] = x[i];
   }
 #pragma unroll
   for (int i = 0; i < N; ++i)
@@ -143,9 +144,38 @@ od_run_kernel(const __grid_constant__ NlModel<6, 2> md, const __grid_constant__ 
       if constexpr (STRICT) v = P[i * N + j];
       else v = P[sym_idx<N>(i, j)];
       io.mat[(int64_t)(i * N + j) * io.nf + tid] = v;
-      if (!io.every_step && io.o_covar != nullptr) io.o_covar[(int64_t)(i * N + j) * io.nf + tid] = v;
+      if (final_out && io.o_covar != nullptr) io.o_covar[(int64_t)(i * N + j) * io.nf + tid] = v;
     }
   if (io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
+}
+
+// io.chunks == 0: one whole-run task per warp (grid = all groups); otherwise persistent warps under the (chunk, group)
+// scheduler of sched.cuh -- same per-filter arithmetic, hence the same bits.
+template <bool STRICT>
+__global__ void __launch_bounds__(kThreads)
+od_run_kernel(const __grid_constant__ NlModel<6, 2> md, const __grid_constant__ OdParams c,
+              const __grid_constant__ NlIo io, double* __restrict__ orbit, const double* __restrict__ station,
+              const double* __restrict__ tobs) {
+  extern __shared__ __align__(16) double icdf_tab[];
+  icdf_load(icdf_tab);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (io.chunks <= 0) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < io.nf) od_task<STRICT, false>(md, c, io, orbit, station, tobs, icdf_tab, tid, 0, io.steps, true);
+    return;
+  }
+  const int groups = (int)((io.nf + 31) / 32);
+  const int n_tasks = groups * io.chunks;
+  (void)warp;
+  int ch, g;
+  while (sched_claim(io.sched, n_tasks, groups, lane, ch, g)) {
+    const int k0 = ch * io.chunk_len, k1 = min(io.steps, k0 + io.chunk_len);
+    if (ch > 0) sched_acquire_group(io.sched + 1 + g, ch, lane);
+    const int64_t tid = (int64_t)g * 32 + lane;
+    if (tid < io.nf) od_task<STRICT, true>(md, c, io, orbit, station, tobs, icdf_tab, tid, k0, k1, ch == io.chunks - 1);
+    if (ch != io.chunks - 1) sched_release_group(io.sched + 1 + g, ch + 1, lane);
+  }
 }
 
 static constexpr size_t kOdSmem = sizeof(double) * kIcdfSegments * kIcdfCoefs;
@@ -165,9 +195,28 @@ int launch_od_run(const HostModel& hm, const OdParams& c, const NlIo& io, double
   for (int i = 0; i < hm.q * hm.q; ++i) md.Q[i] = hm.Q[i];
   for (int i = 0; i < 4; ++i) { md.R[i] = hm.R[i]; md.L[i] = hm.L[i]; }
   md.q = hm.q;
-  const unsigned grid = (unsigned)((io.nf + kThreads - 1) / kThreads);
-  if (io.strict) od_run_kernel<true><<<grid, kThreads, kOdSmem, s>>>(md, c, io, orbit, station, tobs);
-  else od_run_kernel<false><<<grid, kThreads, kOdSmem, s>>>(md, c, io, orbit, station, tobs);
+  auto launch = [&](auto kern) {
+    int sms = 148, device = 0, per_sm = 1;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, kOdSmem);
+    if (per_sm < 1) per_sm = 1;
+    constexpr int kWarps = kThreads / 32;
+    const int64_t groups = (io.nf + 31) / 32;
+    int64_t ctas = (groups + kWarps - 1) / kWarps;
+    NlIo io2 = io;
+    bool forced = false;
+    const int chunks = io.sched != nullptr ? sched_pick_chunks(groups, (int64_t)sms * per_sm * kWarps, io.steps, 16.0, &forced) : 1;
+    const bool scheduled = io.sched != nullptr && (chunks > 1 || forced);
+    sched_set_chunks(io2, chunks, scheduled);
+    if (scheduled) {
+      if (ctas > (int64_t)sms * per_sm) ctas = (int64_t)sms * per_sm;
+      cudaMemsetAsync(io.sched, 0, sizeof(int) * (size_t)(groups + 1), s);
+    }
+    kern<<<(unsigned)ctas, kThreads, kOdSmem, s>>>(md, c, io2, orbit, station, tobs);
+  };
+  if (io.strict) launch(od_run_kernel<true>);
+  else launch(od_run_kernel<false>);
   return 0;
 }
 

@@ -86,6 +86,16 @@ def test_od_fused_run_is_bit_identical_to_streams(oracle, strict):
     assert np.all(a.status == 0) and np.all(b.status == 0)
     assert np.array_equal(a.State(), b.State())
     assert np.array_equal(a.Covariance(), b.Covariance())
+    # the (chunk, group) scheduler of the fused kernel, forced onto this small batch: chunk boundaries inside passes and gaps
+    import os
+    for chunks in ("1", "3", "7"):
+        os.environ["GKB_NL_CHUNKS"] = chunks
+        try:
+            c = make().RunOD(scn, orbit0, 1e-3, 1e-3, seed=9)
+        finally:
+            del os.environ["GKB_NL_CHUNKS"]
+        assert np.all(c.status == 0)
+        assert np.array_equal(b.State(), c.State()) and np.array_equal(b.Covariance(), c.Covariance()), chunks
     if strict:
         rPhi, rHt, rreal, rcomp, _ = oracle.od_synth(scn.mu, scn.j2, scn.re, scn.dt, orbit0[:, :4], scn.station, scn.truth_obs,
                                                      1e-3, 1e-3, 9)
