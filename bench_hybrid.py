@@ -255,7 +255,8 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
                "h2d_bytes_per_step": 8 * 6 * nf + 8 * 8 * steps_full + steps_full, "d2h_bytes_per_step": 8 * nf * (6 + 36) + 4 * nf,
                "api": "HybridKF.RunOD -> gkb_od_run: per-epoch Phi / Htilde / observations computed on the device from the "
                       "initial reference orbits (two-body + J2 RK4 STM, range / range-rate partials) and consumed in the same "
-                      "kernel; host buffers: orbits + per-epoch tables in, final state + covariance out",
+                      "kernel (chunk-scheduled); host buffers: orbits + per-epoch tables in, final state + covariance out -- written by the "
+                      "kernel straight into the caller's pinned buffers (mapped host memory), so the D2H rides under the compute",
                "frac_of_value": e2e_value / value, "fused_kernel_ms": fused_kernel_ms,
                "bit_identical_to_streamed_run": same,
                "host_streams": {"value": host_value, "unit": "filter-updates/s", "epochs": e_steps,

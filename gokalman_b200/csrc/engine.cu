@@ -1149,11 +1149,34 @@ int gkb_od_run(gkb_filter* f, const gkb_od_config* cfg, int steps, const uint8_t
   io.mat = f->mat.as<double>();
   io.flags = dfl;
   io.strict = f->strict ? 1 : 0;
+  // Final-estimate outputs into PINNED host buffers are written by the kernel itself (mapped host memory: every group's
+  // rows leave over PCIe as its last chunk ends, under the compute of the other groups) instead of being staged in HBM
+  // and copied after the kernel.  Pageable buffers, every-step outputs and GKB_OD_STAGED_OUTPUTS=1 take the staged path.
+  gkb_outputs out_staged;
+  double *direct_state = nullptr, *direct_covar = nullptr;
+  if (out && out->mem == GKB_HOST && !out->every_step && getenv("GKB_OD_STAGED_OUTPUTS") == nullptr) {
+    auto mapped = [](void* p) -> double* {
+      cudaPointerAttributes a;
+      if (p == nullptr || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      return (a.type == cudaMemoryTypeHost && a.devicePointer != nullptr) ? static_cast<double*>(a.devicePointer) : nullptr;
+    };
+    direct_state = mapped(out->state);
+    direct_covar = mapped(out->covar);
+    if (direct_state || direct_covar) {
+      out_staged = *out;
+      if (direct_state) out_staged.state = nullptr;
+      if (direct_covar) out_staged.covar = nullptr;
+      out = &out_staged;
+    }
+  }
   OutPlan pl;
   if ((rc = plan_outputs(f, out, steps, hm.m, pl))) return rc;
   io.every_step = out ? out->every_step : 0;
-  io.o_state = pl.state;
-  io.o_covar = pl.covar;
+  io.o_state = direct_state ? direct_state : pl.state;
+  io.o_covar = direct_covar ? direct_covar : pl.covar;
   io.status = f->status.as<int32_t>();
   if ((rc = f->sched.ensure(sizeof(int) * (size_t)((f->nf + 31) / 32 + 1)))) return rc;
   io.sched = f->sched.as<int>();

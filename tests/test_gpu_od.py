@@ -96,6 +96,20 @@ def test_od_fused_run_is_bit_identical_to_streams(oracle, strict):
             del os.environ["GKB_NL_CHUNKS"]
         assert np.all(c.status == 0)
         assert np.array_equal(b.State(), c.State()) and np.array_equal(b.Covariance(), c.Covariance()), chunks
+    # final outputs into PINNED caller buffers are written by the kernel itself (mapped host memory); same bits as staged
+    import torch
+    pinned = {"state": torch.zeros(6 * nf, dtype=torch.float64).pin_memory().numpy(),
+              "covar": torch.zeros(36 * nf, dtype=torch.float64).pin_memory().numpy(),
+              "status": torch.zeros(nf, dtype=torch.int32).pin_memory().numpy()}
+    d = make().RunOD(scn, orbit0, 1e-3, 1e-3, seed=9, out_buffers=pinned)
+    assert np.all(d.status == 0)
+    assert np.array_equal(b.State(), d.State()) and np.array_equal(b.Covariance(), d.Covariance())
+    os.environ["GKB_OD_STAGED_OUTPUTS"] = "1"
+    try:
+        e = make().RunOD(scn, orbit0, 1e-3, 1e-3, seed=9, out_buffers=pinned)
+    finally:
+        del os.environ["GKB_OD_STAGED_OUTPUTS"]
+    assert np.array_equal(b.State(), e.State()) and np.array_equal(b.Covariance(), e.Covariance())
     if strict:
         rPhi, rHt, rreal, rcomp, _ = oracle.od_synth(scn.mu, scn.j2, scn.re, scn.dt, orbit0[:, :4], scn.station, scn.truth_obs,
                                                      1e-3, 1e-3, 9)

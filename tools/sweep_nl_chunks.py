@@ -34,7 +34,9 @@ def main():
         out = L.Outputs()
         out.mem, out.every_step = L.DEVICE, 0
         out.state, out.covar = xs.data_ptr(), Ps.data_ptr()
-        for chunks in ["default"] + [str(c) for c in (2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64)]:
+        order = os.environ.get("SWEEP_CHUNKS")  # e.g. "default,6,default,6,3,5,7": an interleaved A/B (the GPU is power-capped
+        # when this kernel runs back to back, so the position in the sequence matters as much as the chunk count)
+        for chunks in (order.split(",") if order else ["default"] + [str(c) for c in (2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64)]):
             if chunks == "default":
                 os.environ.pop("GKB_NL_CHUNKS", None)
             else:
