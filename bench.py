@@ -586,15 +586,20 @@ def run_reference_filters(args, rank, world):
     value = nf * steps * reps * args.steps / total
     sample = ("%d filters x %d epochs x %d passes per step (bounded sample of the 10^5-filter workload), OpenMP x %d"
               % (nf, steps, reps, cores))
+    if wl in ("hybrid6", "hybrid6_strict", "srif6"):  # the same config object as our arm (the sample is in cpu_baseline)
+        from bench_hybrid import nl_config
+        config = nl_config(wl, 100000 if args.trials == 1000000 else args.trials, args.filter_steps)
+    else:
+        n = int(wl[7:])
+        config = {"workload": FILTER_WORKLOADS[wl], "filters_per_gpu": 26640 if wl == "vanilla64" else 100000,
+                  "epochs": 100 if wl == "vanilla64" else 200, "n": n, "m": 8}
     return {
         "impl": "reference", "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": FILTER_WORKLOADS[wl], "filters_per_gpu": 26640 if wl == "vanilla64" else 100000,
-                   "epochs": args.filter_steps if wl in ("hybrid6", "hybrid6_strict", "srif6") else (100 if wl == "vanilla64" else 200),
-                   "n": int(wl[7:]) if wl.startswith("vanilla") else 6, "m": 8 if wl.startswith("vanilla") else 2,
-                   "sample_filters": nf, "sample_epochs": steps},
-        "cpu_baseline": {"value": value, "unit": "filter-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config,
+        "cpu_baseline": {"value": value, "unit": "filter-updates/s", "cores": cores, "kind": "port", "sample": sample,
+                         "sample_filters": nf, "sample_epochs": steps, "sample_passes": reps},
         "e2e": {"value": value, "unit": "filter-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU oracle port (C, OpenMP); the reference is Go + un-vendored gonum and cannot be built in this image",
     }

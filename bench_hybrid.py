@@ -31,6 +31,19 @@ WORKLOADS = {
 }
 
 
+def nl_config(workload, nf, steps, every=False, failed=0):
+    """The `config` object of a hybrid6 / hybrid6_strict / srif6 line: shared by our arm and the reference arm (the
+    reference arm runs a bounded SAMPLE of this workload -- its size is stated in its `cpu_baseline`, not here)."""
+    return {"workload": WORKLOADS[workload], "filters_per_gpu": nf, "epochs": steps, "n": 6, "m": 2,
+            "ekf_after": None if workload == "srif6" else 15,
+            "streams": "statOD scenario: LEO two-body + J2 RK4 STM, range / range-rate partials, R = diag(1e-6), perturbed "
+                       "reference orbits (1 km, 1 m/s); synthesised by each arm's own generator (GPU: gkb_od_synthesize on the "
+                       "device; reference arm: the oracle's generic RK4 on the host)",
+            "outputs": "state + covariance of every epoch" if every else "final state + covariance only",
+            "failed_filters": failed, "sharding": "disjoint filter ranges per GPU, no collective (replicas)",
+            "l2": "inputs (%.1f GB) exceed L2; flushed anyway" % (nf * steps * BYTES_IN / 1e9)}
+
+
 def od_scenario(steps, dt=10.0):
     from gokalman_b200 import od
     return od.Scenario(steps, dt, od.leo_truth0(), always_track=True, theta0=2.5)
@@ -300,13 +313,7 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
         "metric": "filter-updates/sec (batch x steps, FP64)", "value": value, "unit": "filter-updates/s",
         "n_gpus": world, "steps": n_steps, "warmup": args.warmup if not sub else 3, "ms_per_step": total_ms / n_steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[workload], "filters_per_gpu": nf, "epochs": steps, "n": 6, "m": 2,
-                   "ekf_after": None if srif else 15,
-                   "streams": "statOD scenario synthesised on the device (gkb_od_synthesize): LEO two-body + J2 RK4 STM, "
-                              "range / range-rate partials, R = diag(1e-6), perturbed reference orbits (1 km, 1 m/s)",
-                   "outputs": "state + covariance of every epoch" if every else "final state + covariance only",
-                   "failed_filters": bad, "sharding": "disjoint filter ranges per GPU, no collective (replicas)",
-                   "l2": "inputs (%.1f GB) exceed L2; flushed anyway" % (nf * steps * BYTES_IN / 1e9)},
+        "config": nl_config(workload, nf, steps, every, bad),
         "roofline": roof,
         "gpu_launches": n_steps, "clocks": clocks, "wall_s": wall,
     }

@@ -131,7 +131,8 @@ int gkb_set_stream(gkb_filter* f, void* stream);
 /* Reference-order ("strict") arithmetic for a GKB_HYBRID handle: every product of hybrid.go:114-182 as a full
  * dense product in the written order, no fused multiply-adds (Go on amd64 never fuses), IEEE divisions, the
  * dense Joseph form and AsSymDense (GKB_ERR_ASYMMETRIC can be raised in this mode) -- the arithmetic the
- * reference itself executes, at a fraction of the production kernels' speed.  For validation: the fast kernels
+ * reference itself executes (the `0 +` that starts each of gonum's sums is elided: exact up to the sign of a zero),
+ * at about a third of the production kernels' speed.  For validation: the fast kernels
  * restructure the Joseph update and use FMAs, which moves ill-conditioned runs (statOD: R = 1e-6 against
  * P0 = 10) by more than 1e-10.  On a GKB_SRIF handle it selects the literal epoch of srif.go:101-160 (the general
  * kernel: x-bar = Phi inv(R) b, b-bar = R-bar x-bar formed explicitly, full mat64.Inverse tests) instead of the
@@ -218,7 +219,10 @@ int gkb_od_synthesize(const gkb_od_config* cfg, int steps, int64_t n_filters, in
  * Prepare + Update / Predict (flags as in gkb_nl_run, host array or NULL = Update every epoch; no SNC), in one
  * kernel -- Phi / Htilde / observations live in registers and never reach HBM.  Bit-identical to gkb_od_synthesize
  * followed by gkb_nl_run on its streams.  Outputs: state / covar (+ status), final or every step.  Honours
- * gkb_set_strict.  The handle keeps the advanced reference orbits: cfg->orbit0 = NULL continues from them. */
+ * gkb_set_strict.  The handle keeps the advanced reference orbits: cfg->orbit0 = NULL continues from them.
+ * Final-estimate outputs with out->mem = GKB_HOST: when out->state / out->covar are page-locked (cudaHostAlloc /
+ * cudaHostRegister) the kernel writes them directly over PCIe while it runs; pageable buffers are staged and copied
+ * after the kernel.  Either way the arrays are complete when the call returns. */
 int gkb_od_run(gkb_filter* f, const gkb_od_config* cfg, int steps, const uint8_t* flags, const gkb_outputs* out);
 
 /* ---- SmoothAll (hybrid.go:209-238, srif.go:165-192): backward sweep over the stored estimates of a
