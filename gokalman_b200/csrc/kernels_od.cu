@@ -18,6 +18,8 @@
 
 namespace gkb {
 
+using strict::kStrictThreads;  // (GKB_SM's stride)
+
 __global__ void __launch_bounds__(kThreads)
 od_synth_kernel(const __grid_constant__ OdParams c, int64_t nf, int steps, double* __restrict__ orbit,
                 const double* __restrict__ station, const double* __restrict__ tobs, double* __restrict__ Phi,
@@ -62,8 +64,14 @@ od_synth_kernel(const __grid_constant__ OdParams c, int64_t nf, int steps, doubl
 template <bool STRICT, bool SCHED>
 __device__ __forceinline__ void od_task(const NlModel<6, 2>& md, const OdParams& c, const NlIo& io, double* __restrict__ orbit,
                                         const double* __restrict__ station, const double* __restrict__ tobs,
-                                        const double* icdf_tab, int64_t tid, int k0, int k1, bool last) {
-  constexpr int N = 6, M = 2, SN = N * (N + 1) / 2, PN = STRICT ? N * N : SN;
+                                        const double* icdf_tab, double* sm, int64_t tid, int k0, int k1, bool last) {
+  // STRICT: the covariance (packed), the work matrix and the K R slot live in lane-private shared-memory columns at `sm`
+  // (filters_strict.cuh: hybrid_sm_predict / hybrid_sm_update), exactly as in hybrid_run_strict_kernel
+  constexpr int N = 6, M = 2, SN = N * (N + 1) / 2, PN = STRICT ? 1 : SN;
+  static_assert(strict::kStrictThreads == kThreads, "the strict step's shared-memory stride is the CTA size");
+  double* Ps = sm;
+  double* Ws = sm + SN * kThreads;
+  double* Hs = Ws + N * N * kThreads;
   auto ld_state = [](const double* p) { return SCHED ? __ldcg(p) : *p; };  // SCHED: written by another SM -> read from L2
   double X[6], x[N], P[PN];
 #pragma unroll
@@ -74,9 +82,9 @@ __device__ __forceinline__ void od_task(const NlModel<6, 2>& md, const OdParams&
   for (int i = 0; i < N; ++i)
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      if (!STRICT && i > j) continue;
-      const double v = ld_state(io.mat + (int64_t)((i <= j) ? (i * N + j) : (j * N + i)) * io.nf + tid);
-      if constexpr (STRICT) P[i * N + j] = v;
+      if (i > j) continue;  // the stored matrix is the mirrored upper triangle (AsSymDense)
+      const double v = ld_state(io.mat + (int64_t)(i * N + j) * io.nf + tid);
+      if constexpr (STRICT) GKB_SM(Ps, sym_idx<N>(i, j)) = v;
       else P[sym_idx<N>(i, j)] = v;
     }
   const uint64_t gf = (uint64_t)(c.filter_offset + tid);
@@ -100,8 +108,10 @@ __device__ __forceinline__ void od_task(const NlModel<6, 2>& md, const OdParams&
     for (int a = 0; a < M; ++a) { ro[a] = has_meas ? o[kOdReal + a] : 0.0; co[a] = has_meas ? o[kOdComp + a] : 0.0; }
     int err;
     if constexpr (STRICT) {
-      double Ppred[N * N], K[N * M], innov[M], obsdev[M];
-      err = strict::hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, nullptr, has_meas, ekf, false, Ppred, K, innov, obsdev);
+      double xbar[N], K[N * M], innov[M], obsdev[M];
+      strict::hybrid_sm_predict<N, M>(md, x, Ps, Ws, Phi, nullptr, false, xbar);
+      err = strict::hybrid_sm_update<N, M>(md, x, Ws, Hs, xbar, Ht, ro, co, has_meas, ekf, nullptr, io.nf, K, innov, obsdev);
+      if (err == 0) strict::hybrid_sm_commit<N>(Ps, Ws);
     } else {
       NlOut<N, M> no;
       err = hybrid_step<N, M>(md, x, P, Phi, Ht, ro, co, nullptr, has_meas, ekf, false, no);
@@ -122,7 +132,7 @@ __device__ __forceinline__ void od_task(const NlModel<6, 2>& md, const OdParams&
         for (int i = 0; i < N; ++i)
 #pragma unroll
           for (int j = 0; j < N; ++j) {
-            if constexpr (STRICT) __stcs(dst + (int64_t)(i * N + j) * io.nf, P[i * N + j]);
+            if constexpr (STRICT) __stcs(dst + (int64_t)(i * N + j) * io.nf, GKB_SM(Ps, sym_idx<N>(i, j)));
             else __stcs(dst + (int64_t)(i * N + j) * io.nf, P[sym_idx<N>(i, j)]);
           }
       }
@@ -141,7 +151,7 @@ __device__ __forceinline__ void od_task(const NlModel<6, 2>& md, const OdParams&
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       double v;
-      if constexpr (STRICT) v = P[i * N + j];
+      if constexpr (STRICT) v = GKB_SM(Ps, sym_idx<N>(i, j));
       else v = P[sym_idx<N>(i, j)];
       io.mat[(int64_t)(i * N + j) * io.nf + tid] = v;
       if (final_out && io.o_covar != nullptr) io.o_covar[(int64_t)(i * N + j) * io.nf + tid] = v;
@@ -159,21 +169,21 @@ od_run_kernel(const __grid_constant__ NlModel<6, 2> md, const __grid_constant__ 
   extern __shared__ __align__(16) double icdf_tab[];
   icdf_load(icdf_tab);
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  double* sm = STRICT ? icdf_tab + kIcdfSegments * kIcdfCoefs + threadIdx.x : nullptr;  // the strict step's matrix columns
   if (io.chunks <= 0) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid < io.nf) od_task<STRICT, false>(md, c, io, orbit, station, tobs, icdf_tab, tid, 0, io.steps, true);
+    if (tid < io.nf) od_task<STRICT, false>(md, c, io, orbit, station, tobs, icdf_tab, sm, tid, 0, io.steps, true);
     return;
   }
   const int groups = (int)((io.nf + 31) / 32);
   const int n_tasks = groups * io.chunks;
-  (void)warp;
   int ch, g;
   while (sched_claim(io.sched, n_tasks, groups, lane, ch, g)) {
     const int k0 = ch * io.chunk_len, k1 = min(io.steps, k0 + io.chunk_len);
     if (ch > 0) sched_acquire_group(io.sched + 1 + g, ch, lane);
     const int64_t tid = (int64_t)g * 32 + lane;
-    if (tid < io.nf) od_task<STRICT, true>(md, c, io, orbit, station, tobs, icdf_tab, tid, k0, k1, ch == io.chunks - 1);
+    if (tid < io.nf) od_task<STRICT, true>(md, c, io, orbit, station, tobs, icdf_tab, sm, tid, k0, k1, ch == io.chunks - 1);
     if (ch != io.chunks - 1) sched_release_group(io.sched + 1 + g, ch + 1, lane);
   }
 }
@@ -195,11 +205,15 @@ int launch_od_run(const HostModel& hm, const OdParams& c, const NlIo& io, double
   for (int i = 0; i < hm.q * hm.q; ++i) md.Q[i] = hm.Q[i];
   for (int i = 0; i < 4; ++i) { md.R[i] = hm.R[i]; md.L[i] = hm.L[i]; }
   md.q = hm.q;
-  auto launch = [&](auto kern) {
+  auto launch = [&](auto kern, size_t smem) {
     int sms = 148, device = 0, per_sm = 1;
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, kOdSmem);
+    if (smem > 48 * 1024) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
     if (per_sm < 1) per_sm = 1;
     constexpr int kWarps = kThreads / 32;
     const int64_t groups = (io.nf + 31) / 32;
@@ -213,10 +227,11 @@ int launch_od_run(const HostModel& hm, const OdParams& c, const NlIo& io, double
       if (ctas > (int64_t)sms * per_sm) ctas = (int64_t)sms * per_sm;
       cudaMemsetAsync(io.sched, 0, sizeof(int) * (size_t)(groups + 1), s);
     }
-    kern<<<(unsigned)ctas, kThreads, kOdSmem, s>>>(md, c, io2, orbit, station, tobs);
+    kern<<<(unsigned)ctas, kThreads, smem, s>>>(md, c, io2, orbit, station, tobs);
   };
-  if (io.strict) launch(od_run_kernel<true>);
-  else launch(od_run_kernel<false>);
+  // strict: + packed P (21), work matrix (36) and the K R slot (12) per thread = 70.7 KB per CTA; two CTAs per SM still fit
+  if (io.strict) launch(od_run_kernel<true>, kOdSmem + sizeof(double) * (21 + 36 + 12) * kThreads);
+  else launch(od_run_kernel<false>, kOdSmem);
   return 0;
 }
 
