@@ -16,7 +16,7 @@
 //   P-   = T F^T + Q             upper 10 tiles x 8     =  80 DMMA   (bufB -> bufA)
 //   PHt  = P- H^T                4 tiles x 8            =  32 DMMA   (H x, H x- ride on the B fragments)
 //   S    = H PHt + R             1 tile x 8             =   8 DMMA   -> registers (C fragment)
-//   S^-1                         Gauss-Jordan on the C fragment, warp shuffles only (S is SPD: no pivoting)
+//   S^-1                         Gauss-Jordan on the C fragment, warp shuffles only (S is SPD: no pivoting; cond <= 1e16 test)
 //   K    = PHt S^-1              4 tiles x 2            =   8 DMMA   (S^-1 reaches the B fragment by shuffles)
 //   T2   = P- - K PHt^T          upper 10 tiles x 2     =  20 DMMA   (Joseph form with the products by I removed,
 //   V    = T2 H^T - K R          4 tiles x (8 + 2)      =  40 DMMA    as in filters.cuh: vanilla_step)
@@ -338,6 +338,17 @@ __device__ __forceinline__ void tile_run(const TileIo& io, const double* sF, con
       }
       // ---- S <- inv(S) (164-167): in-place Gauss-Jordan; S is symmetric positive definite, so the
       //      diagonal pivots are safe; a non-positive pivot is the reference's singular-S error
+      // mat64.Dense.Inverse also fails when ||S||inf ||inv(S)||inf > 1e16 (the oracle's exact form of gonum's condition
+      // test): infinity norms over the true m x m block (the padding rows carry a unit diagonal and must not count)
+      auto inf_norm = [&](const double (&e)[2]) {
+        double a = (g < m) ? fabs(e[0]) + fabs(e[1]) : 0.0;
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, off));
+        return a;
+      };
+      const double s_norm = inf_norm(s);
       bool bad = false;
 #pragma unroll
       for (int p = 0; p < kMP; ++p) {
@@ -358,7 +369,8 @@ __device__ __forceinline__ void tile_run(const TileIo& io, const double* sF, con
           s[1] = fma(-fcol, r1, (2 * t + 1 == p) ? 0.0 : s[1]);
         }
       }
-      if (bad) {  // warp-uniform: d is the same in every lane
+      bad = bad || !(s_norm * inf_norm(s) <= 1e16);
+      if (bad) {  // warp-uniform: d and the norms are the same in every lane
         status = GKB_ERR_SINGULAR_S;
         break;
       }

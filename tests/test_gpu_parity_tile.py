@@ -86,6 +86,34 @@ def test_tile_vanilla_shared_measurement_and_singular_s(oracle):
     assert np.all(est2.status == -2)
 
 
+@pytest.mark.parametrize("n,m", [(16, 5), (32, 8), (64, 3)])
+def test_tile_vanilla_ill_conditioned_s_is_the_reference_error(oracle, n, m):
+    """mat64.Dense.Inverse also fails on cond(S) > 1e16 (vanilla.go:164-167 returns the error): an S that is positive
+    definite with exact, positive Gauss-Jordan pivots but badly scaled (R = diag(1e12, 1e-8, 1, ...) against P ~ 1e-8) is
+    refused by the oracle's condition test and must be refused by the large-state kernel too -- while the same model with a
+    benign R runs."""
+    gk = _gpu()
+    nf = 5
+    f = fx.synth_lti(n, m, seed=3)
+    P0, Q = 1e-8 * np.eye(n), 1e-8 * f["Q"]
+    R_bad = np.diag(([1e12, 1e-8] + [1.0] * 8)[:m])
+    y = np.zeros((3, m))
+    with pytest.raises(oracle.OracleError):
+        oracle.NewVanilla(f["x0"], P0, f["F"], None, f["H"], Q, R_bad).Update(y[0], None)
+    kf, _ = gk.NewVanilla(f["x0"], P0, f["F"], None, f["H"], gk.NewNoiseless(Q, R_bad), n_filters=nf)
+    assert kf._fm
+    est = kf.UpdateBatch(y, None, every_step=False, want=("state",))
+    assert np.all(est.status == -2)
+    R_ok = np.diag(([1e3, 1e-3] + [1.0] * 8)[:m])
+    kf2, _ = gk.NewVanilla(f["x0"], P0, f["F"], None, f["H"], gk.NewNoiseless(Q, R_ok), n_filters=nf)
+    est2 = kf2.UpdateBatch(y, None, every_step=False, want=("state", "covar"))
+    assert np.all(est2.status == 0)
+    ref = oracle.NewVanilla(f["x0"], P0, f["F"], None, f["H"], Q, R_ok)
+    for k in range(3):
+        r = ref.Update(y[k], None)
+    assert fx.scaled_err(np.asarray(est2.Covariance())[:, :, 0], r.Covariance()) <= TOL
+
+
 def test_tile_vanilla_with_input_control(oracle):
     """x- = F x + G u (vanilla.go:138-143) on a large-state handle: the control term G u is formed once per step
     for the whole batch; a missing control is the reference's dimension error."""
