@@ -448,10 +448,11 @@ GKB_DEV bool sm_as_sym(double* A) {
   return true;
 }
 
-// Phase A (hybrid.go:114-123 and the x-bar of 126 / 163): Ws = P-bar, xbar = Phi x.  Phi is dead afterwards.
+// Phase A (hybrid.go:114-123 and the x-bar of 126 / 163): Ws = P-bar, xbar = Phi x (CKF).  Phi is dead afterwards.
 template <int N, int M>
 GKB_DEV void hybrid_sm_predict(const NlModel<N, M>& md, const double (&x)[N], const double* Ps, double* Ws,
-                               const double (&Phi)[N * N], const double* __restrict__ Gamma, bool snc, double (&xbar)[N]) {
+                               const double (&Phi)[N * N], const double* __restrict__ Gamma, bool snc, bool ekf,
+                               double (&xbar)[N]) {
   sm_left_mul_sym<N>(Phi, Ps, Ws);  // T = Phi P
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {  // P-bar = T Phi^T, row i in place
@@ -491,12 +492,18 @@ GKB_DEV void hybrid_sm_predict(const NlModel<N, M>& md, const double (&x)[N], co
       }
     }
   }
+  // x-bar = Phi x is formed by the reference only where it is used (hybrid.go:127-131, 162-164): never in EKF mode
+  // (`ekf` is shared by the batch: a uniform branch)
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double s = mul2(Phi[i * N], x[0]);
+  for (int i = 0; i < N; ++i) xbar[i] = 0.0;
+  if (!ekf) {
 #pragma unroll
-    for (int j = 1; j < N; ++j) s = add2(s, mul2(Phi[i * N + j], x[j]));
-    xbar[i] = s;
+    for (int i = 0; i < N; ++i) {
+      double s = mul2(Phi[i * N], x[0]);
+#pragma unroll
+      for (int j = 1; j < N; ++j) s = add2(s, mul2(Phi[i * N + j], x[j]));
+      xbar[i] = s;
+    }
   }
 }
 
@@ -602,7 +609,7 @@ GKB_DEV int hybrid_sm_update(const NlModel<N, M>& md, double (&x)[N], double* Ws
         double s = mul2(Kn[i * M], Ht[j]);
 #pragma unroll
         for (int a = 1; a < M; ++a) s = add2(s, mul2(Kn[i * M + a], Ht[a * N + j]));
-        A[i * N + j] = add2(i == j ? 1.0 : 0.0, -s);
+        A[i * N + j] = (i == j) ? add2(1.0, -s) : -s;  // (0 + (-s) elided off the diagonal: exact up to the sign of a zero)
       }
 #pragma unroll
     for (int i = 0; i < N; ++i)

@@ -206,7 +206,7 @@ GKB_DEV void strict_task(const NlModel<N, M>& md, const NlIo& io, double* Ps, do
     }
     const double* Gk = (snc && io.Gamma) ? io.Gamma + (int64_t)k * N * md.q : nullptr;
     double xbar[N];
-    strict::hybrid_sm_predict<N, M>(md, x, Ps, Ws, Phi, Gk, snc, xbar);
+    strict::hybrid_sm_predict<N, M>(md, x, Ps, Ws, Phi, Gk, snc, ekf, xbar);
     if (phi_staged && k + 1 < k1) request_phi(k + 1);  // (the stage's values have all been used by now)
     double Ht[M * N], ro[M], co[M];
     if (has_meas) {

@@ -109,7 +109,7 @@ __device__ __forceinline__ void od_task(const NlModel<6, 2>& md, const OdParams&
     int err;
     if constexpr (STRICT) {
       double xbar[N], K[N * M], innov[M], obsdev[M];
-      strict::hybrid_sm_predict<N, M>(md, x, Ps, Ws, Phi, nullptr, false, xbar);
+      strict::hybrid_sm_predict<N, M>(md, x, Ps, Ws, Phi, nullptr, false, ekf, xbar);
       err = strict::hybrid_sm_update<N, M>(md, x, Ws, Hs, xbar, Ht, ro, co, has_meas, ekf, nullptr, io.nf, K, innov, obsdev);
       if (err == 0) strict::hybrid_sm_commit<N>(Ps, Ws);
     } else {
