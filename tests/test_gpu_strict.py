@@ -207,6 +207,47 @@ def test_strict_hybrid_full_size_plain_tolerance(oracle):
     assert q[0] <= PRODUCTION_VS_STRICT_MEDIAN and q[1] <= PRODUCTION_VS_STRICT_P99 and emax <= PRODUCTION_VS_STRICT_MAX
 
 
+def test_strict_hybrid_bench_configuration_full_length(oracle):
+    """The bench's default workload itself -- BASELINE configs[3] as `bench.py` runs it: 10^5 filters x 1000 epochs of the
+    device-synthesised statOD streams (41.6 GB), CKF -> EKF after 15 epochs -- through the strict kernel (scheduler on: 3125
+    groups over 1184 resident warps) and eight filters cut out of it replayed through the oracle on the SAME streams: plain
+    1e-10 on the final state and covariance after 1000 epochs (measured: exactly 0)."""
+    import torch
+    import gokalman_b200 as gk
+    from gokalman_b200 import _lib as L
+    from bench_hybrid import make_streams_od, SIGMA
+    lib = gk.load()
+    nf, steps, n, m = 100000, 1000, 6, 2
+    dev = torch.device("cuda", 0)
+    Phi, Ht, real, comp, scn, _ = make_streams_od(torch, L, lib, nf, steps, 1234, 0)
+    flags_np = np.ascontiguousarray(scn.flags[:steps])
+    flags = torch.from_numpy(flags_np).to(dev)
+    R = np.diag([SIGMA ** 2, SIGMA ** 2])
+    kf, _ = gk.NewHybridKF(np.zeros(n), P0_APPD, gk.NewNoiseless(Q_APPD, R), m, n_filters=nf)
+    kf.SetStrict(True)
+    xs = torch.zeros(n, nf, dtype=torch.float64, device=dev)
+    Ps = torch.zeros(n * n, nf, dtype=torch.float64, device=dev)
+    st = torch.zeros(nf, dtype=torch.int32, device=dev)
+    out = L.Outputs()
+    out.mem, out.every_step = L.DEVICE, 0
+    out.state, out.covar, out.status = xs.data_ptr(), Ps.data_ptr(), st.data_ptr()
+    L.check(lib.gkb_nl_run(kf._h, steps, flags.data_ptr(), Phi.data_ptr(), 0, Ht.data_ptr(), 0, real.data_ptr(),
+                           comp.data_ptr(), None, L.DEVICE, C.byref(out)))
+    torch.cuda.synchronize()
+    assert int((st != 0).sum().item()) == 0
+    pick = [0, 31, 32, 4095, 50001, 77777, 99967, 99999]
+    idx = torch.tensor(pick, device=dev)
+    hPhi, hHt = Phi[:, :, idx].cpu().numpy(), Ht[:, :, idx].cpu().numpy()
+    hreal, hcomp = real[:, :, idx].cpu().numpy(), comp[:, :, idx].cpu().numpy()
+    del Phi, Ht, real, comp
+    xr, Pr = oracle.run_nl_batch(oracle.HYBRID, np.zeros(n), P0_APPD, R, flags_np, hPhi, hHt, hreal, hcomp, threads=4)
+    gx, gP = xs[:, idx].cpu().numpy(), Ps[:, idx].cpu().numpy()
+    report = [(pick[j], fx.scaled_err(gx[:, j], xr[:, j]), fx.scaled_err(gP[:, j], Pr[:, j])) for j in range(len(pick))]
+    print("strict, bench configuration 10^5 x 1000 (filter, scaled err x, scaled err P): %s; kernel %.2f ms"
+          % (report, lib.gkb_last_kernel_ms()))
+    assert all(ex <= TOL and eP <= TOL for _, ex, eP in report), report
+
+
 def test_strict_on_srif_selects_the_literal_epoch(oracle):
     """gkb_set_strict on a GKB_SRIF handle runs the literal epoch of srif.go:101-160 (x-bar = Phi inv(R) b and
     b-bar = R-bar x-bar formed explicitly): bit-identical to the general kernel, 1e-10 to the oracle; the production
