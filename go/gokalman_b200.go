@@ -15,6 +15,7 @@ import "C"
 
 import (
 	"errors"
+	"fmt"
 	"unsafe"
 
 	"github.com/ChristopherRabotin/gokalman"
@@ -281,8 +282,102 @@ func VanLoanBatch(n, q int, count int64, device int, A []float64, aShared bool, 
 	return F, Q, lastErr(rc)
 }
 
-// HybridHandle is the NLDKF handle of NewHybridKF (gkb_create_hybrid); only what round 2 added is sketched here.
+// HybridHandle is the NLDKF handle of NewHybridKF (gkb_create_hybrid).
 type HybridHandle struct{ h *C.gkb_filter }
+
+// ---- the NLDKF interface (kalman.go:46-62) on the GPU: the headline path ------------------------------------------
+//
+// HybridKF satisfies gokalman.NLDKF: Prepare / PreparePNT stash the epoch's matrices exactly like hybrid.go:78-89,
+// Update / Predict make ONE gkb_nl_run(steps = 1) call with them (flags = GKB_F_MEAS | GKB_F_EKF | GKB_F_SNC as the
+// reference's state says) and lock the filter again (hybrid.go:140,201-203).  With nFilters = 1 it is a drop-in for the
+// Go object; RunBatch below is the batched form the benchmark measures (N filters x steps epochs in one call).
+type HybridKF struct {
+	HybridHandle
+	n, m, q  int
+	noise    gokalman.Noise
+	phi, ht  []float64 // this epoch's Phi (n x n) and Htilde (m x n), row-major
+	gamma    []float64 // PreparePNT's Gamma (n x q) or nil
+	locked   bool
+	ekf, snc bool
+}
+
+func NewHybridKF(x0 *mat64.Vector, P0 mat64.Symmetric, noise gokalman.Noise, measSize int, nFilters, device int) (*HybridKF, error) {
+	n, _ := P0.Dims()
+	q, _ := noise.ProcessMatrix().Dims()
+	kf := &HybridKF{n: n, m: measSize, q: q, noise: noise, locked: true}
+	rc := C.gkb_create_hybrid(C.int(n), C.int(measSize), C.int(q), C.int64_t(nFilters), C.int(device), ptr(raw(x0)), 0,
+		ptr(raw(P0)), ptr(raw(noise.ProcessMatrix())), ptr(raw(noise.MeasurementMatrix())), &kf.h)
+	return kf, lastErr(rc)
+}
+
+func (kf *HybridKF) EKFEnabled() bool { return kf.ekf }
+func (kf *HybridKF) EnableEKF()       { kf.ekf = true }
+func (kf *HybridKF) DisableEKF()      { kf.ekf = false }
+func (kf *HybridKF) SetNoise(n gokalman.Noise) {
+	kf.noise = n
+	R := n.MeasurementMatrix()
+	mr, _ := R.Dims()
+	C.gkb_set_noise(kf.h, ptr(raw(n.ProcessMatrix())), C.int(mr), ptr(raw(R)))
+}
+func (kf *HybridKF) Prepare(Phi, Htilde *mat64.Dense) { // hybrid.go:78-82
+	kf.phi, kf.ht, kf.locked = raw(Phi), raw(Htilde), false
+}
+func (kf *HybridKF) PreparePNT(Gamma *mat64.Dense) { // hybrid.go:86-89
+	kf.gamma, kf.snc = raw(Gamma), true
+}
+func (kf *HybridKF) Update(real, computed *mat64.Vector) (gokalman.Estimate, error) {
+	return kf.step(C.GKB_F_MEAS, raw(real), raw(computed))
+}
+func (kf *HybridKF) Predict() (gokalman.Estimate, error) { return kf.step(0, nil, nil) }
+
+func (kf *HybridKF) step(fl C.int, real, computed []float64) (gokalman.Estimate, error) {
+	if kf.locked { // hybrid.go:105-107
+		return nil, fmt.Errorf("kf is locked (call Prepare first)")
+	}
+	if kf.ekf {
+		fl |= C.GKB_F_EKF
+	}
+	if kf.snc {
+		fl |= C.GKB_F_SNC
+	}
+	flags := []C.uint8_t{C.uint8_t(fl)}
+	est := &Estimate{n: kf.n, m: kf.m, state: make([]float64, kf.n), meas: make([]float64, kf.m), innov: make([]float64, kf.m),
+		covar: make([]float64, kf.n*kf.n), pred: make([]float64, kf.n*kf.n), gain: make([]float64, kf.n*kf.m)}
+	var status C.int32_t
+	out := C.gkb_outputs{mem: C.GKB_HOST, state: ptr(est.state), meas: ptr(est.meas), innov: ptr(est.innov),
+		covar: ptr(est.covar), pred_covar: ptr(est.pred), gain: ptr(est.gain), status: &status}
+	// one filter: its Phi / Htilde / Gamma are "shared by the batch" (phi_shared = h_shared = 1)
+	rc := C.gkb_nl_run(kf.h, 1, &flags[0], ptr(kf.phi), 1, ptr(kf.ht), 1, ptr(real), ptr(computed), ptr(kf.gamma), C.GKB_HOST, &out)
+	kf.locked, kf.snc = true, false // hybrid.go:140, 201-203
+	if rc != 0 {
+		return nil, lastErr(rc)
+	}
+	if status != 0 { // the reference returns (nil, err): singular S, asymmetric covariance (strict mode)
+		return nil, fmt.Errorf("gokalman_b200: update failed with status %d", int(status))
+	}
+	return est, nil
+}
+
+// RunBatch advances every filter of the handle through `steps` epochs in one call: per-filter streams laid out
+// [steps][component][nFilters] (Phi 36, Htilde 12, real 2, computed 2 at n = 6, m = 2), flags[k] per epoch shared by the
+// batch.  This is the call bench.py times (device-resident streams: in_mem / out.mem = GKB_DEVICE).
+func (kf *HybridKF) RunBatch(steps int, flags []uint8, Phi, Htilde, real, computed, Gamma []float64, inMem C.int, out *C.gkb_outputs) error {
+	return lastErr(C.gkb_nl_run(kf.h, C.int(steps), (*C.uint8_t)(unsafe.Pointer(&flags[0])), ptr(Phi), 0, ptr(Htilde), 0,
+		ptr(real), ptr(computed), ptr(Gamma), inMem, out))
+}
+
+// SRIF (srif.go:14-49) is the same binding over gkb_create_srif; EnableEKF / DisableEKF / PreparePNT are the reference's no-ops.
+func NewSRIF(x0 *mat64.Vector, P0 mat64.Symmetric, measSize int, nonTriR bool, n gokalman.Noise, nFilters, device int) (*HybridKF, error) {
+	dim, _ := P0.Dims()
+	kf := &HybridKF{n: dim, m: measSize, noise: n, locked: true}
+	tri := C.int(0)
+	if nonTriR {
+		tri = 1
+	}
+	rc := C.gkb_create_srif(C.int(dim), C.int(measSize), C.int64_t(nFilters), C.int(device), ptr(raw(x0)), 0, ptr(raw(P0)),
+		ptr(raw(n.MeasurementMatrix())), tri, &kf.h)
+	return kf, lastErr(rc)
+}
 
 // SetStrict selects the reference-order arithmetic (bit-identical to the CPU restatement of hybrid.go:104-204).
 func (kf *HybridHandle) SetStrict(on bool) error {
