@@ -369,11 +369,9 @@ __device__ __forceinline__ void tile_run(const TileIo& io, const double* sF, con
           s[1] = fma(-fcol, r1, (2 * t + 1 == p) ? 0.0 : s[1]);
         }
       }
-      bad = bad || !(s_norm * inf_norm(s) <= 1e16);
-      if (bad) {  // warp-uniform: d and the norms are the same in every lane
-        status = GKB_ERR_SINGULAR_S;
-        break;
-      }
+      // (the verdict is taken after the gain and state update below: neither is committed on an error, and the norm
+      // reduction then overlaps their tensor-core work instead of lengthening the serial inverse)
+      const double sinv_norm = inf_norm(s);
       // ---- K = PHt inv(S) (168): inv(S) is symmetric, so B[k][a] = Sinv[a][k] sits in this lane's own row
       double kc[TM][2];
 #pragma unroll
@@ -408,6 +406,11 @@ __device__ __forceinline__ void tile_run(const TileIo& io, const double* sF, con
         sinn[kMP + g] = (g < m) ? yhat : 0.0;
       }
       psync();
+      bad = bad || !(s_norm * sinv_norm <= 1e16);
+      if (bad) {  // warp-uniform (and identical in both warps of a pair): pivots and norms are the same in every lane
+        status = GKB_ERR_SINGULAR_S;
+        break;
+      }
       // ---- Joseph form (197-205), restructured: T2 = P- - K PHt^T (symmetric: upper tiles)
 #pragma unroll
       for (int t0 = 0; t0 < TM; t0 += TB) {
