@@ -86,3 +86,22 @@ def test_awgn_requires_positive_definite_noise():
     f = fx.jerk3()
     with pytest.raises(ValueError):  # noise.go:149-156 panics
         gk.NewAWGN(np.zeros((3, 3)), f["R"])
+
+
+def test_awgn_samples_like_noise_test_go():
+    """The sample half of TestAWGN (noise_test.go:136-170): Process / Measurement return vectors of the sizes of Q / R,
+    different at two different steps; plus what a clock-seeded stream cannot promise: the same (seed, step) gives the same
+    sample again, and the sample covariance over many steps approaches Q and R."""
+    import gokalman_b200 as gk
+    gk.load()
+    Q, R = np.eye(2), np.array([[20.0, 0.05], [0.05, 20.0]])
+    n = gk.NewAWGN(Q, R, seed=11)
+    pk0, pk1, mk0, mk1 = n.Process(0), n.Process(1), n.Measurement(0), n.Measurement(1)
+    assert pk0.shape == (2,) and mk0.shape == (2,)
+    assert not np.array_equal(pk0, pk1) and not np.array_equal(mk0, mk1)
+    n2 = gk.NewAWGN(Q, R, seed=11)
+    assert np.array_equal(n2.Process(0), pk0) and np.array_equal(n2.Measurement(1), mk1)
+    W = np.array([gk.NewAWGN(Q, R, seed=11).Process(k) for k in range(4000)])
+    V = np.array([n.Measurement(k) for k in range(4000)])
+    assert np.allclose(np.cov(W.T), Q, atol=0.08) and np.allclose(np.cov(V.T), R, atol=1.6)
+    assert abs(W.mean()) < 0.05 and abs(V.mean()) < 0.25
