@@ -52,3 +52,21 @@ def test_batch_ground_truth_error_offsets():
     assert not np.any(e3.State()) and not np.any(e3.Measurement())
     with pytest.raises(ValueError):
         gk.NewBatchGroundTruth([np.zeros(3)], [np.zeros(1)]).Error(0, est)
+
+
+def test_implements_ldkf_nldkf_estimate():
+    """kalman_test.go:9-33 (TestImplementsLDKF / TestImplementsNLDKF / TestImplementsEst): the host mirror carries the method
+    sets of kalman.go:35-72 under the reference's names."""
+    import gokalman_b200 as gk
+    ldkf = ("Update", "GetNoise", "GetStateTransition", "GetInputControl", "GetMeasurementMatrix", "SetStateTransition",
+            "SetInputControl", "SetMeasurementMatrix", "SetNoise", "Reset", "__str__")
+    nldkf = ("Prepare", "Predict", "Update", "EKFEnabled", "EnableEKF", "DisableEKF", "PreparePNT", "SetNoise")
+    est = ("IsWithinNσ", "State", "Measurement", "Innovation", "Covariance", "PredCovariance", "__str__")
+    for cls in (gk.Vanilla, gk.Information, gk.SquareRoot):
+        for name in ldkf:
+            assert callable(getattr(cls, name, None)), (cls.__name__, name)
+    for cls in (gk.HybridKF, gk.SRIF):
+        for name in nldkf:
+            assert callable(getattr(cls, name, None)), (cls.__name__, name)
+    for name in est:
+        assert callable(getattr(gk.Estimate, name, None)), name
