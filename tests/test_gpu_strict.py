@@ -318,3 +318,37 @@ def test_strict_scheduler_and_register_twin_are_bit_identical():
             got = run(every, env)
             for a, b in zip(ref, got):
                 assert np.array_equal(a, b), (every, env)
+
+
+def test_strict_shared_streams_match_per_filter_streams_and_oracle(oracle):
+    """Phi / H-tilde shared by the batch (the [steps, n, n] call shape: uniform loads instead of the cp.async stages) with
+    per-filter observations: same bits as the same run fed with per-filter copies of the matrices, and exactly the oracle."""
+    import gokalman_b200 as gk
+    from gokalman_b200 import _lib as L
+    rng = np.random.default_rng(17)
+    nf, steps, n, m = 45, 30, 6, 2
+    Phi = np.eye(n)[None] + 0.02 * rng.standard_normal((steps, n, n))
+    Ht = rng.standard_normal((steps, m, n))
+    real = rng.standard_normal((steps, m, nf))
+    comp = real + 0.05 * rng.standard_normal((steps, m, nf))
+    flags = np.array([(0 if k == 11 else L.F_MEAS) | (L.F_EKF if k >= 15 else 0) for k in range(steps)], dtype=np.uint8)
+    R = np.diag([1e-2, 1e-2])
+
+    def run(Phi_, Ht_):
+        kf, _ = gk.NewHybridKF(np.zeros(n), P0_APPD, gk.NewNoiseless(Q_APPD, R), m, n_filters=nf)
+        kf.SetStrict(True)
+        est = kf.RunBatch(flags, Phi_, Ht_, real, comp, None, every_step=True)
+        assert np.all(est.status == 0)
+        return est
+    a = run(Phi, Ht)
+    b = run(np.repeat(Phi[..., None], nf, axis=3), np.repeat(Ht[..., None], nf, axis=3))
+    for g in ("State", "Covariance", "PredCovariance", "Gain", "Innovation"):
+        assert np.array_equal(np.asarray(getattr(a, g)()), np.asarray(getattr(b, g)())), g
+    for f in (0, 31, 32, nf - 1):
+        o = oracle.NewHybridKF(np.zeros(n), P0_APPD, Q_APPD, R, m)
+        for k in range(steps):
+            o.Prepare(Phi[k], Ht[k])
+            (o.EnableEKF if flags[k] & L.F_EKF else o.DisableEKF)()
+            eo = o.UpdateNL(real[k, :, f], comp[k, :, f]) if flags[k] & L.F_MEAS else o.Predict()
+            assert np.array_equal(a.State()[k, :, f], eo.State()), (f, k)
+            assert np.array_equal(a.Covariance()[k, :, :, f], eo.Covariance()), (f, k)
