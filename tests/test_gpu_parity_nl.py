@@ -55,7 +55,7 @@ def _check(est, refs, fields, tag):
             assert err <= TOL, (tag, fld, f, err)
 
 
-@pytest.mark.parametrize("n,m,q", [(6, 2, 3), (4, 2, 2), (3, 1, 0), (6, 3, 3), (8, 3, 3), (7, 2, 2), (8, 1, 0)])
+@pytest.mark.parametrize("n,m,q", [(6, 2, 3), (4, 2, 2), (3, 1, 0), (6, 3, 3), (8, 3, 3), (7, 2, 2), (8, 1, 0), (8, 2, 3), (7, 3, 0), (7, 1, 1)])
 def test_hybrid_ckf_ekf_snc_matches_oracle(oracle, n, m, q):
     """hybrid.go:104-204: Predict / CKF update / EKF update / SNC epochs mixed in one batched run
     with per-filter Phi, Htilde and observations (BASELINE config 4 shape is n=6, m=2, q=3)."""
@@ -483,3 +483,42 @@ def test_failed_epoch_writes_nan_rows_and_keeps_previous_estimate(oracle):
             assert k == 5
             continue
         assert fx.scaled_err(xs[k, :, 2], e.State()) <= TOL, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,shared", [(6, 2, False), (8, 2, False), (8, 3, False), (7, 2, True)])
+def test_hybrid_failed_epoch_keeps_previous_estimate(oracle, n, m, shared):
+    """hybrid.go:104-204 returns (nil, err) from a failed Update and leaves the filter as it was.  One filter gets a NaN
+    observation at one epoch: that epoch's rows are NaN, status names the error, and every later epoch equals an oracle
+    filter that never saw the epoch.  n = 7, 8 run the shared-memory-column kernel (Phi / H-tilde staged by cp.async,
+    P-bar written out before the Joseph form): the previous covariance must survive there too."""
+    gk = _gpu()
+    from gokalman_b200._lib import F_MEAS, F_EKF
+    rng = np.random.default_rng(77 + n + m)
+    nf, steps, bad_k, bad_f = 37, 14, 5, 3
+    Phi, Ht, real, comp = _od_streams(rng, n, m, nf, steps)
+    if shared:
+        Phi = np.ascontiguousarray(Phi[:, :, :, 0])
+        Ht = np.ascontiguousarray(Ht[:, :, :, 0])
+    real[bad_k, 0, bad_f] = np.nan
+    P0 = np.diag(np.concatenate([np.full(n - n // 2, 10.0), np.full(n // 2, 1.0)]))
+    R = np.diag(np.full(m, 1e-2))
+    flags = np.array([F_MEAS | (F_EKF if k >= 8 else 0) for k in range(steps)], dtype=np.uint8)
+    kf, _ = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(np.diag(np.full(3, 1e-9)), R), m, n_filters=nf)
+    est = kf.RunBatch(flags, Phi, Ht, real, comp, None, every_step=True)
+    assert est.status[bad_f] != 0 and np.all(np.delete(est.status, bad_f) == 0)
+    xs, Ps, Pp = est.State(), est.Covariance(), est.PredCovariance()
+    assert np.all(np.isnan(xs[bad_k, :, bad_f])) and np.all(np.isnan(Ps[bad_k, :, :, bad_f]))
+    assert np.all(np.isnan(Pp[bad_k, :, :, bad_f]))
+    assert np.all(np.isfinite(np.delete(xs, bad_f, axis=2)))
+    for f in (bad_f, bad_f + 1):
+        o = oracle.NewHybridKF(np.zeros(n), P0, np.diag(np.full(3, 1e-9)), R, m)
+        for k in range(steps):
+            if f == bad_f and k == bad_k:
+                continue
+            o.Prepare(Phi[k] if shared else Phi[k, :, :, f], Ht[k] if shared else Ht[k, :, :, f])
+            (o.EnableEKF if flags[k] & F_EKF else o.DisableEKF)()
+            e = o.UpdateNL(real[k, :, f], comp[k, :, f])
+            assert fx.scaled_err(xs[k, :, f], e.State()) <= TOL, (f, k)
+            assert fx.scaled_err(Ps[k, :, :, f], e.Covariance()) <= TOL, (f, k)
+            assert fx.scaled_err(Pp[k, :, :, f], e.PredCovariance()) <= TOL, (f, k)
