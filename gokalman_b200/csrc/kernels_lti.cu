@@ -98,13 +98,16 @@ vanilla_update_kernel(const __grid_constant__ VanillaModel<N, M> md, const __gri
       for (int i = 0; i < N; ++i) gu[i] = __ldg(io.gu + (int64_t)k * N + i);
     }
     StepOut<N, M> o;
-    if (io.w2 != nullptr) {  // AWGN: the second Process(k) call of the step draws afresh (noise.go:127-131)
-      double w2[N];
+    // AWGN: the second Process(k) call of the step draws afresh (noise.go:127-131); replay / noiseless: the same vector.
+    // ONE call site: two inlined copies of the step made ptxas give up on the n = 8, m = 3 shape (32 registers, 38 KB spill).
+    double w2[N];
+    if (io.w2 != nullptr) {
       load_soa<N>(w2, io.w2 + (int64_t)(io.step0 + k) * N * io.nf, io.nf, tid);
-      if (err == 0) err = vanilla_step<N, M, PREDICTOR>(md, x, P, y, gu, w, v, o, w2);
-    } else if (err == 0) {
-      err = vanilla_step<N, M, PREDICTOR>(md, x, P, y, gu, w, v, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) w2[i] = w[i];
     }
+    if (err == 0) err = vanilla_step<N, M, PREDICTOR>(md, x, P, y, gu, w, v, o, w2);
     if (err != 0) {
       if (status == 0) status = err;
       fail_outputs<N, M, M>(io, k, tid);
