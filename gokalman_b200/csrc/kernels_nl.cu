@@ -144,7 +144,9 @@ int launch_householder(int n, int m, int64_t count, double* A, cudaStream_t s) {
 // Solve(): P0 = inv(Lambda) by LU (upper triangle kept, AsSymDense), xHat0 = P0 N.  The full dense Lambda is
 // accumulated in the reference's operation order.  Streams H [steps][m*n][N], observations [steps][m][N].
 template <int N, int M>
-__global__ void __launch_bounds__(kThreads, 3)
+// n = 7, 8 with m >= 2: Lambda alone is 49 / 64 doubles -- no register cap there (measured: x2.5 at (8,2), x1.5 at (8,3), x1.3 at
+// (7,2); m = 1 keeps the cap: its thin stream wants the third CTA more than the registers, 0.86 without it)
+__global__ void __launch_bounds__(kThreads, ((N <= 6 || M == 1) ? 3 : 2))
 batch_solve_kernel(const __grid_constant__ NlModel<N, M> md, int64_t nf, int steps, const double* __restrict__ H,
                    int h_shared, const double* __restrict__ real_obs, const double* __restrict__ computed_obs,
                    double* __restrict__ xhat0, double* __restrict__ P0, int32_t* __restrict__ status) {

@@ -17,12 +17,21 @@ import gokalman_b200 as gk  # noqa: E402
 from gokalman_b200 import _lib as L  # noqa: E402
 from bench_hybrid import make_streams  # noqa: E402
 
+if os.environ.get("GKB_BENCH_LIB"):
+    L.LIB_PATH = os.path.abspath(os.environ["GKB_BENCH_LIB"])
 lib = gk.load()
-nf, steps, n, m = 100000, 200, 6, 2
+nf, steps = 100000, 200
+n, m = int(os.environ.get("N", 6)), int(os.environ.get("M", 2))
 dev = torch.device("cuda", 0)
-Phi, Ht, real, comp = make_streams(torch, nf, steps, 1234, dev)
-del Phi
-R = np.ascontiguousarray(np.diag([1e-6, 1e-6]))
+if (n, m) == (6, 2):
+    Phi, Ht, real, comp = make_streams(torch, nf, steps, 1234, dev)
+    del Phi
+else:  # other compiled shapes (N=, M= in the environment): random partials
+    g = torch.Generator(device=dev).manual_seed(7)
+    Ht = torch.randn(steps, m * n, nf, dtype=torch.float64, device=dev, generator=g)
+    real = torch.randn(steps, m, nf, dtype=torch.float64, device=dev, generator=g)
+    comp = real + 0.05 * torch.randn(steps, m, nf, dtype=torch.float64, device=dev, generator=g)
+R = np.ascontiguousarray(np.diag([1e-6] * m))
 xhat = torch.zeros(n, nf, dtype=torch.float64, device=dev)
 P0 = torch.zeros(n * n, nf, dtype=torch.float64, device=dev)
 status = torch.zeros(nf, dtype=torch.int32, device=dev)
@@ -35,5 +44,5 @@ for it in range(6):
         ms.append(lib.gkb_last_kernel_ms())
 t = sum(ms) / len(ms)
 ups = nf * steps / (t * 1e-3)
-print(json.dumps({"kernel": "batch_solve_kernel<6,2>", "kernel_ms": t, "measurements_per_s": ups,
-                  "hbm_gbs": ups * 128 / 1e9, "bad": int((status != 0).sum().item())}))
+print(json.dumps({"kernel": "batch_solve_kernel<%d,%d>" % (n, m), "kernel_ms": t, "measurements_per_s": ups,
+                  "hbm_gbs": ups * 8 * (m * n + 2 * m) / 1e9, "bad": int((status != 0).sum().item())}))
