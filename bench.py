@@ -7,13 +7,17 @@ One "step" = one pass of the hot path over one batch of synthetic input.  Worklo
   hybrid6 (DEFAULT: BASELINE configs[3], the north star's Target config): 10^5 six-state hybrid CKF->EKF filters per
       GPU x 1000 epochs, per-filter per-epoch Phi / Htilde / observations (416 B per filter-update) resident in HBM:
       41.6 GB per GPU, synthesised on the device from a LEO statOD scenario (gkb_od_synthesize: two-body + J2 STM,
-      range / range-rate partials, App. D constants).  `value` = production kernel (TMA pipelines); `e2e` = the
-      fused OD run through the public API (host: initial orbits in, final estimates out); the same line carries the
-      host-fed-streams figure against the measured PCIe bandwidth.  Multi-GPU: disjoint filter ranges, no collective.
+      range / range-rate partials, App. D constants).  `value` = the REFERENCE-ORDER kernel (gkb_set_strict: dense
+      products in the written order, no FMA contraction, dense Joseph form): bit-identical to the CPU oracle on these
+      streams, which drive the covariance to cond ~ 1e13 -- nothing but the reference's own rounding sequence holds the
+      north star's 1e-10 there.  `e2e` = the fused OD run through the public API in the same arithmetic (host: initial
+      orbits in, final estimates out); the same line carries the host-fed-streams figure against the measured PCIe
+      bandwidth.  Multi-GPU: disjoint filter ranges, no collective.
+  hybrid6_fma: the same run through the production (FMA, TMA-pipelined) kernel -- 2.5x faster, HBM-bound, equal to the
+      reference up to the rounding sensitivity of the run (`production_vs_strict` in its record).
   srif6 (configs[3], SRIF arm), mc_jerk3 (configs[1]: 10^6 Monte Carlo trials x 1000 steps + chi-square, one NCCL
       all-reduce of the NEES / NIS sums), mc_robot_info / mc_robot_sqrt (configs[2]), vanilla32 / vanilla64 (configs[4]).
-Unless --no-sub is given the default run appends `"sub"`: short records of hybrid6 in STRICT (reference-order,
-bit-exact) arithmetic, srif6, mc_jerk3 (weak and, at N > 1, strong scaling) and vanilla32, each with its own clocks.
+Unless --no-sub is given the default run appends `"sub"`: records of hybrid6_fma, srif6, mc_jerk3 (weak and, at N > 1, strong scaling) and vanilla32, each with its own clocks.
 Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle on the same workload (the reference itself is
 Go + un-vendored gonum and cannot be built in this image).
 """
@@ -544,6 +548,7 @@ def oracle_filter_rate(workload, nf, steps, threads, reps=1):
 FILTER_WORKLOADS = {
     "hybrid6": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
     "hybrid6_strict": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
+    "hybrid6_fma": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
     "srif6": "srif6: 6-state SRIF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
     "vanilla32": "vanilla32: synthetic 32-state vanilla KF, m = 8 (BASELINE configs[4])",
     "vanilla64": "vanilla64: synthetic 64-state vanilla KF, m = 8 (the n = 64 shape of BASELINE configs[4])",
@@ -561,11 +566,39 @@ def filter_sample_size(workload, cores, target_s):
     return nf, steps, reps
 
 
+def oracle_fma_spread(nf=256, steps=200):
+    """How far the REFERENCE'S OWN formulas move on the bench's statOD streams when a*b+c is merely contracted: the CPU
+    oracle built with -ffp-contract=fast against the same oracle unfused, same streams, same metric as the GPU arm's
+    production_vs_strict (per filter: max |fma - unfused| over the final array / max |unfused|)."""
+    from oracle import gko
+    from gokalman_b200 import od  # host-side numpy tables only
+    scn = od.Scenario(steps, 10.0, od.leo_truth0(), always_track=True, theta0=2.5)
+    orbit0 = od.perturbed_orbits(od.leo_truth0(), nf, sigma_r=1.0, sigma_v=1e-3, seed=1234)
+    Phi, Ht, real, comp, _ = gko.od_synth(scn.mu, scn.j2, scn.re, scn.dt, orbit0, scn.station, scn.truth_obs, 1e-3, 1e-3, 1234)
+    P0, R, flags = np.diag([10, 10, 10, 1, 1, 1.0]), np.diag([1e-6, 1e-6]), np.ascontiguousarray(scn.flags)
+    xr, Pr = gko.run_nl_batch(gko.HYBRID, np.zeros(6), P0, R, flags, Phi, Ht, real, comp, threads=os.cpu_count() or 1)
+    xf, Pf = gko.run_nl_batch(gko.HYBRID, np.zeros(6), P0, R, flags, Phi, Ht, real, comp, threads=os.cpu_count() or 1, fma=True)
+
+    def scaled(a, b):
+        e = np.abs(a - b).max(axis=0) / np.abs(b).max(axis=0)
+        return {"median": float(np.median(e)), "p99": float(np.quantile(e, 0.99)), "max": float(e.max())}
+    cond = [float(np.linalg.cond(Pr[:, j].reshape(6, 6))) for j in range(min(nf, 32))]
+    return {"filters": nf, "epochs": steps, "state": scaled(xf, xr), "covariance": scaled(Pf, Pr),
+            "cond_final_covariance_median": float(np.median(cond)),
+            "what": "CPU oracle with -ffp-contract=fast vs the same oracle unfused (the reference's formulas, both)"}
+
+
 def cpu_baseline_filters(workload, target_s=10.0):
     cores = os.cpu_count() or 1
     nf, steps, reps = filter_sample_size(workload, cores, target_s)
     rate, dt = oracle_filter_rate(workload, nf, steps, cores, reps)
-    return {"value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+    extra = {}
+    if workload.startswith("hybrid6"):
+        try:
+            extra["fma_spread"] = oracle_fma_spread()
+        except Exception as e:
+            extra["fma_spread"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return {**extra, "value": rate, "unit": "filter-updates/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
             "omp_num_threads": cores,
             "sample": "%d filters x %d epochs of %s, %d passes (%.1f s of filter work), C oracle restatement with OpenMP over "
                       "filters; the Go/gonum reference cannot be built here (no Go toolchain)" % (nf, steps, workload, reps, dt)}
@@ -586,7 +619,7 @@ def run_reference_filters(args, rank, world):
     value = nf * steps * reps * args.steps / total
     sample = ("%d filters x %d epochs x %d passes per step (bounded sample of the 10^5-filter workload), OpenMP x %d"
               % (nf, steps, reps, cores))
-    if wl in ("hybrid6", "hybrid6_strict", "srif6"):  # the same config object as our arm (the sample is in cpu_baseline)
+    if wl in ("hybrid6", "hybrid6_strict", "hybrid6_fma", "srif6"):  # the same config object as our arm (the sample is in cpu_baseline)
         from bench_hybrid import nl_config
         config = nl_config(wl, 100000 if args.trials == 1000000 else args.trials, args.filter_steps)
     else:
@@ -648,7 +681,7 @@ def run_subrecords(args, rank, world, local, shared):
             sub[name] = fn()
         except Exception as e:  # a sub-record must never take the headline down with it
             sub[name] = {"error": "%s: %s" % (type(e).__name__, e)}
-    add("hybrid6_strict", lambda: run_ours_hybrid(args, rank, world, local, workload="hybrid6_strict", sub=True, shared=shared))
+    add("hybrid6_fma", lambda: run_ours_hybrid(args, rank, world, local, workload="hybrid6_fma", sub=True, shared=shared))
     add("srif6", lambda: run_ours_hybrid(args, rank, world, local, workload="srif6", sub=True, shared=shared))
     shared.clear()  # frees the 41.6 GB of streams
     import torch
@@ -670,7 +703,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hybrid6", choices=["hybrid6", "hybrid6_strict", "srif6", "mc_jerk3", "mc_robot_info",
+    ap.add_argument("--workload", default="hybrid6", choices=["hybrid6", "hybrid6_strict", "hybrid6_fma", "srif6", "mc_jerk3", "mc_robot_info",
                                                               "mc_robot_sqrt", "vanilla32", "vanilla64"])
     ap.add_argument("--trials", type=int, default=1000000, help="Monte Carlo trials per GPU (MC workloads) / filters per GPU "
                     "(filter workloads: the default means 10^5, or 26 640 for vanilla64)")
@@ -693,7 +726,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     shared = {}
-    if args.workload in ("hybrid6", "hybrid6_strict", "srif6"):
+    if args.workload in ("hybrid6", "hybrid6_strict", "hybrid6_fma", "srif6"):
         from bench_hybrid import run_ours_hybrid
         line = run_ours_hybrid(args, rank, world, local, shared=shared)
     elif args.workload in ("vanilla32", "vanilla64"):

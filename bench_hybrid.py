@@ -23,10 +23,16 @@ import numpy as np
 
 FLOPS_CKF, FLOPS_EKF, FLOPS_SRIF, BYTES_IN = 2526.0, 2422.0, 2168.0, 416.0  # BASELINE.md section 3 / SURVEY App. B
 SIGMA = 1e-3  # km, km/s: sigma^2 = 1e-6 (hybrid_test.go:77)
+_HYB = "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])"
 WORKLOADS = {
-    "hybrid6": "hybrid6: 6-state hybrid CKF->EKF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
-    "hybrid6_strict": "hybrid6_strict: the same run in reference-order arithmetic (gkb_set_strict: dense products, no FMA, "
-                      "dense Joseph form) -- bit-identical to the CPU oracle (BASELINE configs[3])",
+    # the headline: reference-order arithmetic (gkb_set_strict: dense products in the written order, no FMA contraction, dense
+    # Joseph form) -- bit-identical to the CPU oracle, i.e. to the reference's formulas, on every stream
+    "hybrid6": _HYB + "; reference-order arithmetic (bit-identical to the reference's formulas)",
+    "hybrid6_strict": _HYB + "; reference-order arithmetic (bit-identical to the reference's formulas)",
+    # the fast mode: FMA contraction, packed covariance, restructured Joseph form, TMA pipelines -- 1e-10 on well-conditioned
+    # runs; on THESE streams (cond(P) ~ 1e13) it moves the result as far as fusing a*b+c moves the reference's own formulas
+    "hybrid6_fma": _HYB + "; production (FMA) kernel: the fast mode, equal to the reference up to the rounding sensitivity "
+                          "of the run (see production_vs_strict)",
     "srif6": "srif6: 6-state SRIF, range + range-rate, per-filter Phi/Htilde streams (BASELINE configs[3])",
 }
 
@@ -126,13 +132,13 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
     nf = args.trials if args.trials != 1000000 else 100000
     steps_full = args.filter_steps  # default 1000 (steps >= 1000; 41.6 GB of inputs)
     n, m = 6, 2
-    srif, strict = workload == "srif6", workload == "hybrid6_strict"
+    srif, strict, fma = workload == "srif6", workload in ("hybrid6", "hybrid6_strict"), workload == "hybrid6_fma"
     shared = shared if shared is not None else {}
     if "streams" not in shared:
         shared["streams"] = make_streams_od(torch, L, lib, nf, steps_full, 1234 + rank, local, filter_offset=rank * nf)
     Phi, Ht, real, comp, scn, orbit0 = shared["streams"]
-    # sub-records run a prefix of the resident streams (the strict kernel is ~4x slower per epoch)
-    steps = steps_full if not sub else min(steps_full, 200)
+    # the srif6 sub-record runs a prefix of the resident streams; the fast-mode record runs all of them (sustained figure)
+    steps = steps_full if (not sub or fma) else min(steps_full, 200)
     flags_np = np.ascontiguousarray(scn.flags[:steps])  # every epoch an Update, EKF after 15 (hybrid_test.go:65)
     P0 = np.diag([10, 10, 10, 1, 1, 1.0])
     R = np.diag([SIGMA ** 2, SIGMA ** 2])
@@ -251,30 +257,39 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
                 "frac_of_value": rate / value, "fused_kernel_ms": kernel_ms, "bit_identical_to_streamed_run": same}
 
     e2e, prod_vs_strict = None, None
-    if strict:
-        # The headline (production) kernel against this one on the same resident streams, same epochs: per filter,
+    if fma:
+        # This kernel against the headline (strict) one on the same resident streams, first 200 epochs: per filter,
         # max |production - strict| over the final state (covariance) / max |strict| of that array -- SURVEY 8(c)'s metric.
         # The strict kernel IS the CPU oracle bit for bit (tests/test_gpu_strict.py), so this is production-vs-reference.
-        kfp = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R), m, n_filters=nf, device=local)[0]
-        p_state, p_cov, p_status = torch.zeros_like(out_state), torch.zeros_like(out_cov), torch.zeros_like(status)
-        outp = L.Outputs()
-        outp.mem, outp.every_step = L.DEVICE, 0
-        outp.state, outp.covar, outp.status = p_state.data_ptr(), p_cov.data_ptr(), p_status.data_ptr()
-        L.check(lib.gkb_nl_run(kfp._h, steps, flags.data_ptr(), Phi.data_ptr(), 0, Ht.data_ptr(), 0, real.data_ptr(),
-                               comp.data_ptr(), None, L.DEVICE, C.byref(outp)))
-        torch.cuda.synchronize()
+        c_steps = min(steps_full, 200)
+
+        def run_prefix(strict_mode):
+            kfx = gk.NewHybridKF(np.zeros(n), P0, gk.NewNoiseless(Q, R), m, n_filters=nf, device=local)[0]
+            kfx.SetStrict(strict_mode)
+            xs, Ps, stx = torch.zeros(n, nf, dtype=torch.float64, device=dev), torch.zeros(n * n, nf, dtype=torch.float64, device=dev), \
+                torch.zeros(nf, dtype=torch.int32, device=dev)
+            ox = L.Outputs()
+            ox.mem, ox.every_step = L.DEVICE, 0
+            ox.state, ox.covar, ox.status = xs.data_ptr(), Ps.data_ptr(), stx.data_ptr()
+            L.check(lib.gkb_nl_run(kfx._h, c_steps, flags.data_ptr(), Phi.data_ptr(), 0, Ht.data_ptr(), 0, real.data_ptr(),
+                                   comp.data_ptr(), None, L.DEVICE, C.byref(ox)))
+            torch.cuda.synchronize()
+            return xs, Ps
+        (p_state, p_cov), (s_state, s_cov) = run_prefix(False), run_prefix(True)
 
         def scaled(a, b):
             e = (a - b).abs().amax(dim=0) / b.abs().amax(dim=0)
             return {"median": float(e.median().item()), "p99": float(e.quantile(0.99).item()), "max": float(e.max().item())}
-        prod_vs_strict = {"epochs": steps, "filters": nf, "state": scaled(p_state, out_state), "covariance": scaled(p_cov, out_cov),
+        prod_vs_strict = {"epochs": c_steps, "filters": nf, "state": scaled(p_state, s_state), "covariance": scaled(p_cov, s_cov),
                           "metric": "per filter: max|production - strict| / max|strict| over the final array",
-                          "note": "strict == CPU oracle bit for bit; the production kernel's FMA contraction and restructured "
-                                  "Joseph form move the result by the conditioning of the statOD streams (R = 1e-6, P0 = 10)"}
-        del kfp, p_state, p_cov
-    if sub and strict:  # the end-to-end figure that carries the 1e-10 parity: the fused run in reference-order arithmetic
-        rate, kernel_ms, _, same = run_fused(od_scenario(steps), steps)
-        e2e = fused_record(rate, kernel_ms, same, steps, "; reference-order (strict) filter step: bit-identical to the CPU oracle")
+                          "note": "strict == CPU oracle bit for bit.  These streams drive the conventional covariance form to "
+                                  "cond(P) ~ 1e13 (R = 1e-6 against P0 = 10): the reference's OWN formulas move this much when "
+                                  "a*b+c is merely contracted on the CPU (cpu_baseline.fma_spread: oracle built with "
+                                  "-ffp-contract=fast against the same oracle unfused).  On well-conditioned runs both modes "
+                                  "sit at rounding level against the oracle (tests/test_gpu_strict.py, 1e-10 asserted)"}
+        del p_state, p_cov, s_state, s_cov
+        rate, kernel_ms, _, same = run_fused(scn, steps_full)
+        e2e = fused_record(rate, kernel_ms, same, steps_full)
     if not sub:
         if srif:  # no fused OD run for the SRIF: its end-to-end path is the host-stream pipeline below
             h_out = {"state": torch.zeros(n * nf, dtype=torch.float64).pin_memory().numpy(),
@@ -312,7 +327,8 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
                    "api": "SRIF.RunBatch (pinned host streams, chunked double-buffered H2D overlapped with the kernels; "
                           "PCIe-bound: 416 B per filter-update; the fused OD run exists for the HybridKF only)"}
         else:
-            e2e = fused_record(e2e_value, fused_kernel_ms, same, steps_full)
+            e2e = fused_record(e2e_value, fused_kernel_ms, same, steps_full,
+                               "; reference-order (strict) filter step: bit-identical to the CPU oracle" if strict else "")
         e2e.update({
                "host_streams": {"value": host_value, "unit": "filter-updates/s", "epochs": e_steps,
                                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8 * nf * (6 + 36) + 4 * nf,
@@ -341,7 +357,7 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
         roof = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
         kernel = ("nl_run_wtma_sched_kernel<6,2,SRIF> (speculative straight-line SRIF epoch)" if srif else
                   "nl_run_wtma_sched_kernel<6,2> (warp-private TMA tensor-map pipelines, persistent chunk scheduler)")
-    roof.update({"traffic": measured_traffic(workload, nf == 100000 and steps == 1000),
+    roof.update({"traffic": measured_traffic(workload, nf == 100000 and steps == 1000 and not every),
                  "algorithmic_bytes": float(nf) * steps * BYTES_IN, "kernel": kernel, "kernel_ms": main_ms,
                  "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm, "bytes_per_unit": bytes_unit, "source": hbm_src},
                  "fp64": {"achieved_tflops": tf, "peak_tflops": None, "frac": None, "flops_per_unit": flops, "source": None}})
