@@ -132,9 +132,13 @@ int gkb_set_stream(gkb_filter* f, void* stream);
  * dense product in the written order, no fused multiply-adds (Go on amd64 never fuses), IEEE divisions, the
  * dense Joseph form and AsSymDense (GKB_ERR_ASYMMETRIC can be raised in this mode) -- the arithmetic the
  * reference itself executes (the `0 +` that starts each of gonum's sums is elided: exact up to the sign of a zero),
- * at about a third of the production kernels' speed.  For validation: the fast kernels
- * restructure the Joseph update and use FMAs, which moves ill-conditioned runs (statOD: R = 1e-6 against
- * P0 = 10) by more than 1e-10.  On a GKB_SRIF handle it selects the literal epoch of srif.go:101-160 (the general
+ * at about 0.4 of the production kernels' speed (5.1e9 against 1.2-1.4e10 updates/s at n = 6, m = 2 on one B200).
+ * WHEN TO USE IT: whenever the results have to be the reference's.  The fast kernels restructure the Joseph update
+ * and use FMAs; that is invisible (<= 1e-10) on well-conditioned runs, but the conventional covariance form of an
+ * orbit-determination run (statOD: R = 1e-6 against P0 = 10, cond(P) ~ 1e13) amplifies ANY change of rounding to
+ * percent level after a few dozen epochs -- the reference's own formulas move that much when a C compiler merely
+ * contracts a*b+c (bench.py: production_vs_strict, cpu_baseline.fma_spread).  bench.py's headline runs in this mode.
+ * On a GKB_SRIF handle it selects the literal epoch of srif.go:101-160 (the general
  * kernel: x-bar = Phi inv(R) b, b-bar = R-bar x-bar formed explicitly, full mat64.Inverse tests) instead of the
  * production epoch, which takes b-bar = b and differs from it at rounding level (1.5e-13 on the full-size run).
  * on = 0 (default) selects the production kernels. */
