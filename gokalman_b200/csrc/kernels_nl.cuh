@@ -345,6 +345,32 @@ hybrid_run_strict_regs_kernel(const __grid_constant__ NlModel<N, M> md, const __
   if (io.status != nullptr && status != 0 && io.status[tid] == 0) io.status[tid] = status;
 }
 
+// Out-of-line read-outs for n = 7, 8: State() / Covariance() each carry an unrolled 8 x 8 LU inverse; inlined into the
+// epoch loop (they run only when an output row is due) they cost the loop its registers.  The arrays cross the call in
+// local memory -- same arithmetic, same bits.
+template <int N>
+__device__ __noinline__ bool srif_state_ool(double* xs, const double* R, const double* b) {
+  double x_[N], R_[N * N], b_[N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) R_[i] = R[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) b_[i] = b[i];
+  const bool ok = srif_state<N>(x_, R_, b_);
+#pragma unroll
+  for (int i = 0; i < N; ++i) xs[i] = x_[i];
+  return ok;
+}
+template <int N>
+__device__ __noinline__ bool srif_covariance_ool(double* Pc, const double* R) {
+  double P_[N * N], R_[N * N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) R_[i] = R[i];
+  const bool ok = srif_covariance<N>(P_, R_);
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) Pc[i] = P_[i];
+  return ok;
+}
+
 template <int N, int M>
 __global__ void __launch_bounds__(kThreads)
 srif_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant__ NlIo io) {
@@ -384,7 +410,18 @@ srif_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant_
       nl_out<M>(io.o_obsdev, k, io.every_step, o.obsdev, io.nf, tid);
       if (io.o_state != nullptr) {  // srif.go:223-235
         double xs[N];
-        if (!srif_state<N>(xs, R, b)) {
+        bool st_ok;
+        if constexpr (N >= 7) {  // copies cross the call: R and b themselves stay in registers
+          double Rc[N * N], bc[N];
+#pragma unroll
+          for (int i = 0; i < N * N; ++i) Rc[i] = R[i];
+#pragma unroll
+          for (int i = 0; i < N; ++i) bc[i] = b[i];
+          st_ok = srif_state_ool<N>(xs, Rc, bc);
+        } else {
+          st_ok = srif_state<N>(xs, R, b);
+        }
+        if (!st_ok) {
           if (status == 0) status = GKB_ERR_SINGULAR_R;
 #pragma unroll
           for (int i = 0; i < N; ++i) xs[i] = 0.0;
@@ -393,12 +430,26 @@ srif_run_kernel(const __grid_constant__ NlModel<N, M> md, const __grid_constant_
       }
       if (io.o_covar != nullptr) {  // srif.go:253-265
         double Pc[N * N];
-        srif_covariance<N>(Pc, R);
+        if constexpr (N >= 7) {
+          double Rc[N * N];
+#pragma unroll
+          for (int i = 0; i < N * N; ++i) Rc[i] = R[i];
+          srif_covariance_ool<N>(Pc, Rc);
+        } else {
+          srif_covariance<N>(Pc, R);
+        }
         nl_out<N * N>(io.o_covar, k, io.every_step, Pc, io.nf, tid);
       }
       if (io.o_pred != nullptr) {  // srif.go:268-281
         double Pc[N * N];
-        srif_covariance<N>(Pc, o.Rbar);
+        if constexpr (N >= 7) {
+          double Rc[N * N];
+#pragma unroll
+          for (int i = 0; i < N * N; ++i) Rc[i] = o.Rbar[i];
+          srif_covariance_ool<N>(Pc, Rc);
+        } else {
+          srif_covariance<N>(Pc, o.Rbar);
+        }
         nl_out<N * N>(io.o_pred, k, io.every_step, Pc, io.nf, tid);
       }
     }
