@@ -143,3 +143,44 @@ def test_od_run_converges_on_the_truth():
     drift = np.linalg.norm(orb_end[:3] - scn.truth[-1][:3, None], axis=0)
     err = np.linalg.norm((orb_end + est.State())[:3] - scn.truth[-1][:3, None], axis=0)
     assert np.median(drift) > 1.0 and np.median(err) < 0.02, (np.median(drift), np.median(err))
+
+
+def test_bench_scenario_strict_is_exact_and_production_is_within_the_reference_fma_spread(oracle):
+    """The bench's own configuration (bench_hybrid.od_scenario: every epoch a measurement, sigma = 1e-3 against P0 = 10,
+    CKF -> EKF after 15 epochs) drives the conventional covariance form to cond(P) ~ 1e13: the answer is not determined
+    to better than a few percent by ANY rounding sequence but the reference's own.  On 512 filters x 200 epochs:
+      (1) strict kernel == oracle on the same streams, EXACTLY (the parity bar of the bench headline);
+      (2) labelled "production-vs-strict": the production (FMA) kernel moves the result no further than the reference's
+          own formulas move when gcc merely contracts a*b+c (oracle FMA build vs oracle unfused build, same streams,
+          same per-filter scaled metric) -- median within 4x of that spread.  This is a sensitivity statement, not parity."""
+    import gokalman_b200 as gk
+    from gokalman_b200 import od
+    gk.load()
+    nf, steps = 512, 200
+    scn = od.Scenario(steps, 10.0, od.leo_truth0(), always_track=True, theta0=2.5)
+    orbit0 = od.perturbed_orbits(od.leo_truth0(), nf, sigma_r=1.0, sigma_v=1e-3, seed=1234)
+    Phi, Ht, real, comp, _ = od.synthesize(scn, orbit0, 1e-3, 1e-3, seed=1234)
+
+    def run(strict):
+        kf, _ = gk.NewHybridKF(np.zeros(6), P0, gk.NewNoiseless(Q, R), 2, n_filters=nf)
+        kf.SetStrict(strict)
+        e = kf.RunBatch(scn.flags, Phi, Ht, real, comp, None, every_step=False, want=("state", "covar"))
+        assert np.all(e.status == 0)
+        return e.State(), e.Covariance().reshape(36, nf)
+    xs, Ps = run(True)
+    xp, Pp = run(False)
+    xr, Pr = oracle.run_nl_batch(oracle.HYBRID, np.zeros(6), P0, R, scn.flags, Phi, Ht, real, comp, threads=4)
+    xf, Pf = oracle.run_nl_batch(oracle.HYBRID, np.zeros(6), P0, R, scn.flags, Phi, Ht, real, comp, threads=4, fma=True)
+    assert np.array_equal(xs, xr) and np.array_equal(Ps, Pr)  # (1): bit for bit
+
+    def spread(a, b):
+        return np.abs(a - b).max(axis=0) / np.abs(b).max(axis=0)
+    prod = np.maximum(spread(xp, xs), spread(Pp, Ps))
+    ref = np.maximum(spread(xf, xr), spread(Pf, Pr))
+    cond = np.median([np.linalg.cond(Pr[:, j].reshape(6, 6)) for j in range(32)])
+    print("bench scenario, %d filters x %d epochs: cond(P) median %.1e; production-vs-strict median %.2e p99 %.2e; "
+          "reference formulas FMA-vs-unfused median %.2e p99 %.2e" % (nf, steps, cond, np.median(prod), np.quantile(prod, 0.99),
+                                                                     np.median(ref), np.quantile(ref, 0.99)))
+    assert cond > 1e10                                  # the premise: this run IS ill-conditioned
+    assert np.median(ref) > 1e-6                        # ... and the reference's own formulas are rounding-sensitive on it
+    assert np.median(prod) <= 4.0 * np.median(ref)      # (2)
