@@ -434,6 +434,10 @@ int gkb_create_hybrid(int n, int m, int q, int64_t n_filters, int device, const 
   sym_from_upper(A0, P0, n);
   rc = finish_create(f, x0, x0_per_filter, A0);
   if (rc) { destroy_filter(f); return rc; }
+  // A single-filter handle is the reference-shaped use (one HybridKF, Prepare + Update per epoch through the shim): it
+  // starts in reference-order arithmetic, so that its estimates are the reference's bit for bit whatever the conditioning
+  // of the run.  Batched handles start in the production (FMA) mode; gkb_set_strict switches either.
+  f->strict = (n_filters == 1);
   *out = f;
   return 0;
 }

@@ -141,7 +141,8 @@ int gkb_set_stream(gkb_filter* f, void* stream);
  * On a GKB_SRIF handle it selects the literal epoch of srif.go:101-160 (the general
  * kernel: x-bar = Phi inv(R) b, b-bar = R-bar x-bar formed explicitly, full mat64.Inverse tests) instead of the
  * production epoch, which takes b-bar = b and differs from it at rounding level (1.5e-13 on the full-size run).
- * on = 0 (default) selects the production kernels. */
+ * on = 0 selects the production kernels.  DEFAULT: on = 1 for a GKB_HYBRID handle created with n_filters = 1 (the
+ * reference-shaped, one-filter use: its estimates are the reference's bit for bit), on = 0 for batched handles and SRIF. */
 int gkb_set_strict(gkb_filter* f, int on);
 int64_t gkb_n_filters(const gkb_filter* f);
 /* 1 when the handle's per-filter arrays are filter-major [N][C] (large-state handles), 0 for SoA [C][N]. */
