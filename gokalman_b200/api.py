@@ -661,7 +661,9 @@ class HybridKF(_NLDKF):
 
     def SetStrict(self, on=True):
         """Reference-order arithmetic (gkb_set_strict): dense products in the written order, no FMA contraction,
-        dense Joseph form -- the validation twin of the production kernels."""
+        dense Joseph form -- bit-identical to the reference's formulas; the mode to use whenever the results have to be
+        the reference's (ill-conditioned OD runs amplify the fast kernels' rounding differences to percent level).
+        Default: on for a single-filter HybridKF (the reference-shaped use), off for batched handles."""
         _lib.check(_lib.load().gkb_set_strict(self._h, int(bool(on))))
 
     def RunOD(self, scenario, orbit0, sigma_range, sigma_rate, seed, flags=None, every_step=False, filter_offset=0,
@@ -714,6 +716,8 @@ class SRIF(_NLDKF):
 
 
 def NewHybridKF(x0, P0, noise, measSize, n_filters=1, device=0):
+    """hybrid.go:23-34.  n_filters = 1: the drop-in filter, reference-order arithmetic by default (its estimates equal
+    the reference's bit for bit); n_filters > 1: a batch in lockstep, production (FMA) kernels by default -- SetStrict()."""
     lib = _lib.load()
     x0, P0 = _arr(x0), _arr(P0)
     n = x0.shape[0]
