@@ -301,6 +301,9 @@ type HybridKF struct {
 	ekf, snc bool
 }
 
+// NewHybridKF mirrors hybrid.go:23-34.  nFilters = 1 is the drop-in filter: the handle starts in reference-order
+// arithmetic (gkb_create_hybrid), so every Estimate equals the reference's bit for bit; a batch (nFilters > 1) starts in
+// the fast FMA mode -- SetStrict(true) selects the reference's arithmetic for it (what ill-conditioned OD runs need).
 func NewHybridKF(x0 *mat64.Vector, P0 mat64.Symmetric, noise gokalman.Noise, measSize int, nFilters, device int) (*HybridKF, error) {
 	n, _ := P0.Dims()
 	q, _ := noise.ProcessMatrix().Dims()
