@@ -288,8 +288,9 @@ def run_ours_hybrid(args, rank, world, local, workload=None, sub=False, shared=N
                                   "-ffp-contract=fast against the same oracle unfused).  On well-conditioned runs both modes "
                                   "sit at rounding level against the oracle (tests/test_gpu_strict.py, 1e-10 asserted)"}
         del p_state, p_cov, s_state, s_cov
-        rate, kernel_ms, _, same = run_fused(scn, steps_full)
-        e2e = fused_record(rate, kernel_ms, same, steps_full)
+        if sub:  # (run stand-alone, the common e2e block below measures the same thing)
+            rate, kernel_ms, _, same = run_fused(scn, steps_full)
+            e2e = fused_record(rate, kernel_ms, same, steps_full)
     if not sub:
         if srif:  # no fused OD run for the SRIF: its end-to-end path is the host-stream pipeline below
             h_out = {"state": torch.zeros(n * nf, dtype=torch.float64).pin_memory().numpy(),
